@@ -1,0 +1,199 @@
+/* restir_b200.h — C ABI of the B200-native ReSTIR resampling passes.
+ *
+ * Drop-in boundary for the reference's four GPU passes and the resources they bind.  Each entry point
+ * names the reference interface it replaces (paths relative to lukedan/ReSTIR-Vulkan).  Plain
+ * pointers and sizes only; no Vulkan, no torch.  Every call returns 0 on success or a negative
+ * RESTIR_E_* code (the reference's vkCheck aborts instead, src/misc.cpp:21-26); the message is
+ * available from restir_last_error().  CUDA errors are sticky.
+ *
+ * Threading/ordering (reference: one queue, full barriers between passes, one frame in flight —
+ * restirPass.h:37-41, app.cpp:771-773): calls on one context are issued in order on one CUDA stream
+ * and are asynchronous with respect to the host unless stated; restir_synchronize() waits.  Uniform
+ * blocks are snapshotted at call time.  A context is not thread-safe; contexts are independent.
+ *
+ * Ownership (reference: App owns every buffer, passes hold handles — src/app.h:113-148): the context
+ * owns the device memory it allocates (reservoirs, scene copies, G-buffer copies made by
+ * restir_upload_gbuffer); the caller owns every pointer it passes in.
+ */
+#ifndef RESTIR_B200_H_
+#define RESTIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "restir_layouts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RESTIR_OK 0
+#define RESTIR_E_INVALID (-1)  /* bad argument / wrong call order */
+#define RESTIR_E_CUDA (-2)     /* CUDA runtime error (sticky) */
+#define RESTIR_E_NOMEM (-3)
+#define RESTIR_E_UNSUPPORTED (-4)
+
+typedef struct restir_context restir_context;
+
+/* Reservoir buffer ids — the three buffers App keeps (src/app.h:264-284): two per-frame buffers that
+ * ping-pong with the G-buffers, and the temporary the unbiased path writes its initial samples to. */
+#define RESTIR_BUF_FRAME0 0
+#define RESTIR_BUF_FRAME1 1
+#define RESTIR_BUF_TEMP 2
+
+/* Output formats of the lighting pass (reference renders into the swapchain image, lightingPass.h). */
+#define RESTIR_OUT_RGBA32F 0     /* linear, before any quantisation: the parity format */
+#define RESTIR_OUT_RGBA8_SRGB 1  /* 8-bit sRGB-encoded, what a *_SRGB swapchain stores */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Replaces: pass construction in App::App (src/app.cpp:437-536, Pass::create<> src/passes/pass.h:112-119).
+ * `device` is a CUDA device ordinal; `stream` is a cudaStream_t to issue on, or NULL for a stream the
+ * context creates. */
+int restir_create(restir_context **out, int device, void *stream);
+void restir_destroy(restir_context *ctx);
+const char *restir_last_error(const restir_context *ctx);
+/* Replaces: waiting on _mainFence (src/app.cpp:771-773). */
+int restir_synchronize(restir_context *ctx);
+
+/* ---- scene resources (set 0 / set 2 descriptors) ------------------------------------------------ */
+
+/* Replaces: AabbTreeBuffers::create (src/aabbTreeBuilder.h:25-51) + initializeSoftwareRayTracingDescriptorSet
+ * (src/passes/restirPass.h:221-237).  Bytes exactly as AabbTree::build produces them: n_nodes x 80, n_tris x 48. */
+int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles);
+
+/* Replaces: the three light SSBOs of SceneBuffers (src/sceneBuffers.h:100-124, 241-270) +
+ * initializeStaticDescriptorSetFor (restirPass.h:120-150).  Blobs = {int32 count; pad to 16; array}. */
+int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t point_bytes, const void *tri_blob,
+                         size_t tri_bytes, const void *alias_blob, size_t alias_bytes);
+
+/* ---- per-resolution resources ------------------------------------------------------------------- */
+
+/* Replaces: App::_updateRestirBuffers (src/app.h:264-284): allocates and ZERO-FILLS the three
+ * reservoir buffers for a width x height screen and drops any bound G-buffers. */
+int restir_resize(restir_context *ctx, uint32_t width, uint32_t height);
+
+/* Row-band variant for multi-GPU (no reference equivalent — the reference is single-GPU): this
+ * context shades rows [row_begin, row_end) of a width x height screen and keeps `halo` extra rows
+ * on each side (clipped to the screen) for neighbour / reprojection reads.  All per-pixel pointers
+ * passed to or returned by this context then cover rows [alloc_begin, alloc_end) =
+ * [max(0,row_begin-halo), min(height,row_end+halo)), see restir_get_band(). */
+int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end,
+                       uint32_t halo);
+int restir_get_band(const restir_context *ctx, uint32_t *row_begin, uint32_t *row_end, uint32_t *alloc_begin,
+                    uint32_t *alloc_end);
+
+/* Replaces: the G-buffer image bindings of initializeFrameDescriptorSetFor (restirPass.h:152-219),
+ * SpatialReusePass::initializeDescriptorSetFor (spatialReusePass.h:28-89), UnbiasedReusePass
+ * (unbiasedReusePass.h:111-161) and LightingPass (lightingPass.h:48-96).  slot is the G-buffer index
+ * (0/1, src/app.h numGBuffers).  Planes are DEVICE pointers that must stay valid while bound. */
+int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *device_planes);
+/* Same, from HOST memory (pinned or pageable): copies the planes into context-owned device memory on the
+ * context's stream (asynchronous when the host memory is pinned) and binds them. */
+int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *host_planes);
+
+/* ---- uniforms ------------------------------------------------------------------------------------ */
+
+/* Replaces: the mapped write of the RestirUniforms UBO each frame (src/app.cpp:775-826, initial values
+ * :414-434).  The 128-byte block is taken verbatim.  In band mode screenSize must be the FULL screen. */
+int restir_set_uniforms(restir_context *ctx, const restir_uniforms *uniforms);
+/* Replaces: the LightingPassUniforms UBO write (src/app.cpp:793-800). */
+int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_uniforms *uniforms);
+/* The unbiased pass's neighbour count is a compile-time 3 in the reference (unbiasedReuse.glsl:48) and
+ * ignores uniforms.spatialNeighbors; this overrides it (1..16) for the north-star's 5-neighbour runs. */
+int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
+
+/* ---- the passes ---------------------------------------------------------------------------------- */
+
+/* Replaces: RestirPass::issueCommands, software-ray-tracing pipeline (restirPass.h:36-62) running
+ * restirOmniSoftware.comp -> restirOmni.glsl:86-212.  Reads G-buffer slots `gbuffer` (current) and
+ * gbuffer^1 (previous; zero texels if unbound), reservoir buffer `prev_buffer`; writes `out_buffer`. */
+int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int prev_buffer);
+/* Replaces: SpatialReusePass::issueCommands (spatialReusePass.h:11-26) running spatialReuse.comp:30-86
+ * with push constant `iter`. */
+int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter);
+/* Replaces: UnbiasedReusePass::issueCommands, software pipeline (unbiasedReusePass.h:23-49) running
+ * unbiasedReuseSoftware.comp -> unbiasedReuse.glsl:50-185. */
+int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer);
+/* Replaces: LightingPass::issueCommands (lightingPass.h:14-42) running lighting.frag:43-71,103
+ * (debugMode 0 only).  `out` is a DEVICE pointer to rows [alloc_begin, alloc_end) x width pixels of
+ * `out_format`; only rows [row_begin,row_end) are written. */
+int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out_device, int out_format);
+
+/* Replaces: the pre-recorded command buffer of App::_recordMainCommandBuffers (src/app.h:212-262)
+ * minus the G-buffer pass, with App's buffer roles (src/app.h:298-332): frame index i in {0,1};
+ *   unbiased != 0: restir(out=TEMP, prev=FRAME[i^1]) ; unbiased(in=TEMP, out=FRAME[i])
+ *   unbiased == 0: restir(out=FRAME[i], prev=FRAME[i^1]) ; for j < spatial_iterations:
+ *                  spatial(in=FRAME[i], out=FRAME[i^1], iter=2j) ; spatial(in=FRAME[i^1], out=FRAME[i], iter=2j+1)
+ * Single-GPU contexts only (band contexts need halo exchanges between the passes; see restir_halo_*). */
+int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations);
+
+/* ---- reservoir access (parity / replay / halo exchange) -------------------------------------- */
+
+/* Copy reservoir buffer `buffer` to / from HOST memory in the reference's 64-byte layout
+ * (restir_reservoir), rows [alloc_begin, alloc_end).  Synchronous.  No reference equivalent (the
+ * reference cannot dump); SURVEY.md §5 "checkpoint / resume". */
+int restir_download_reservoirs(restir_context *ctx, int buffer, restir_reservoir *dst_host);
+int restir_upload_reservoirs(restir_context *ctx, int buffer, const restir_reservoir *src_host);
+/* Device pointer and row pitch (bytes) of the context's internal packed reservoir buffer, for
+ * GPU-to-GPU halo exchange (row r of the screen lives at ptr + (r - alloc_begin) * pitch). */
+int restir_reservoir_device_ptr(restir_context *ctx, int buffer, void **ptr, size_t *row_pitch_bytes);
+
+/* ---- stand-alone visibility (the minimum parity slice) ---------------------------------------- */
+
+/* testVisibility(p1,p2) of visibilityTest.glsl:1-4,27-28 over n segments (raytrace of
+ * softwareRaytracing.glsl:39-85).  p1/p2: DEVICE float[n][3]; shadowed: DEVICE uint8[n] (1 = shadowed). */
+int restir_trace_segments(restir_context *ctx, const float *p1_device, const float *p2_device, uint64_t n,
+                          uint8_t *shadowed_device);
+
+/* ---- counters --------------------------------------------------------------------------------- */
+
+typedef struct restir_counters {
+	uint64_t shadow_rays;       /* testVisibility calls executed since the last reset */
+	uint64_t stack_overflows;   /* pushes dropped on a full 32-entry traversal stack (UB in the reference) */
+	uint64_t halo_misses;       /* band mode: neighbour / reprojection reads outside [alloc_begin, alloc_end) */
+	uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
+} restir_counters;
+/* Synchronises the stream. */
+int restir_get_counters(restir_context *ctx, restir_counters *out, int reset);
+
+/* ---- scene-side builders (host, once per scene) ------------------------------------------------ */
+
+/* Replaces: AabbTree::build (src/aabbTreeBuilder.cpp:52-214) for world-space triangles already in the
+ * reference's order.  triangles: n x 48 bytes (restir_triangle).  nodes_out: (n-1) x 80 bytes. n >= 2. */
+int restir_build_aabb_tree(const void *triangles, uint32_t n_triangles, void *nodes_out);
+/* Replaces: collectTriangleLightsFromScene (src/misc.cpp:380-414).  tri_material[i] indexes
+ * material_emissive (n_materials x float[3]); a triangle is a light if |emissive|^2 > 1e-6.
+ * Returns the number of lights written (<= n_triangles) or a negative error. */
+int64_t restir_collect_triangle_lights(const void *triangles, const int32_t *tri_material, uint32_t n_triangles,
+                                        const float *material_emissive, uint32_t n_materials, restir_tri_light *out);
+/* Replaces: generateRandomPointLights (src/misc.cpp:358-378) with the default colour ranges [0,1):
+ * libstdc++'s std::default_random_engine, default-seeded; draw order z,y,x,b,g,r (g++ evaluates the
+ * reference's constructor arguments right to left). */
+int restir_generate_random_point_lights(uint64_t count, const float min_xyz[3], const float max_xyz[3], restir_point_light *out);
+/* Replaces: createAliasTable (src/misc.cpp:418-497).  Exactly one of the two arrays is used: point lights
+ * if n_point > 0, else triangle lights. */
+int restir_create_alias_table(const restir_point_light *point, uint64_t n_point, const restir_tri_light *tri,
+                              uint64_t n_tri, restir_alias_column *out);
+
+/* ---- fixture tool (synthesises INPUTS; not part of the reference's hot path) ------------------ */
+
+typedef struct restir_camera { /* src/camera.h:7-13 */
+	float position[3], lookAt[3], worldUp[3];
+	float zNear, zFar, fovYRadians, aspectRatio;
+} restir_camera;
+/* src/camera.h:25-50: column-major projectionViewMatrix. */
+int restir_camera_matrix(const restir_camera *camera, float out_pv[16]);
+/* Primary-visibility ray cast of the uploaded BVH into the five G-buffer planes (DEVICE pointers, rows
+ * [alloc_begin, alloc_end) of the context's screen), semantics in SURVEY.md §8d / Appendix E.
+ * tri_material: DEVICE int32[n_triangles]; material_table: DEVICE uint32[n_materials][4] =
+ * {albedo RGBA8, material RG16, flags(bit0: discarded), 0}. */
+int restir_tools_raycast_gbuffer(restir_context *ctx, const restir_camera *camera, const int32_t *tri_material_device,
+                                 const uint32_t *material_table_device, void *albedo, void *normal, void *material,
+                                 void *worldPos, void *depth);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* RESTIR_B200_H_ */

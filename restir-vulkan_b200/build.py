@@ -1,0 +1,48 @@
+"""Builds librestir_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_capi.cu", "host/scene_build.cpp"]
+HEADERS = ["csrc/restir_math.cuh", "csrc/restir_device.cuh", "csrc/restir_kernels.h", "../include/restir_b200.h",
+           "../include/restir_layouts.h", "host/passes.hpp"]
+OUT = os.path.join(HERE, "librestir_b200.so")
+
+# -fmad=false: no FMA contraction (arithmetic policy P1); division and sqrt stay IEEE (-prec-div/-prec-sqrt
+# default true), denormals are kept (-ftz default false).
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared",
+]
+
+
+def nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.exists(os.path.join(HERE, s)) and os.path.getmtime(os.path.join(HERE, s)) > t for s in SOURCES + HEADERS + ["build.py"])
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    ccbin = "/usr/bin/g++"
+    if os.path.exists(ccbin):
+        cmd[1:1] = ["-ccbin", ccbin]
+    subprocess.check_call(cmd, cwd=HERE)
+    # the C++ mirror of the reference's pass classes is header-only: make sure it compiles against the ABI
+    example = os.path.join(HERE, "host", "passes_example.cpp")
+    if os.path.exists(example):
+        subprocess.check_call([ccbin if os.path.exists(ccbin) else "g++", "-std=c++17", "-fsyntax-only", "-Wall", example], cwd=HERE)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,670 @@
+// restir_capi.cu — the context behind include/restir_b200.h: device memory, the reference's buffer
+// roles, and one in-order CUDA stream.  No CPU fallback: every pass is a kernel launch or an error.
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/restir_b200.h"
+#include "restir_kernels.h"
+
+using namespace restir;
+
+struct restir_context {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	std::string error;
+	bool cudaFailed = false;
+
+	// scene
+	float4 *nodes = nullptr, *tris = nullptr;
+	uint32_t nNodes = 0, nTris = 0;
+	unsigned char *pointBlob = nullptr, *triBlob = nullptr, *aliasBlob = nullptr;
+	float4 *pointPosLum = nullptr, *triAux = nullptr;
+	int pointCount = 0, triCount = 0, aliasCount = 0;
+	float *srgbLut = nullptr;
+
+	// screen
+	Band band{0, 0, 0, 0, 0, 0};
+	PackedReservoir *reservoirs[3] = {nullptr, nullptr, nullptr};
+	GBufferView gbuf[2] = {};
+	void *ownedPlanes[2][5] = {};
+	restir_reservoir *staging = nullptr; // device scratch for 64-byte <-> 32-byte conversion
+	size_t stagingPixels = 0;
+
+	restir_uniforms uniforms{};
+	bool haveUniforms = false;
+	restir_lighting_uniforms lighting{};
+	bool haveLighting = false;
+	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
+
+	unsigned long long *counters = nullptr; // device, kCounterCount entries
+	uint64_t launches = 0;
+
+	size_t allocPixels() const { return (size_t)(band.allocEnd - band.allocBegin) * (size_t)band.W; }
+};
+
+namespace {
+
+int fail(restir_context *ctx, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx) {
+		ctx->error = buf;
+	}
+	return code;
+}
+
+int cudaCheck(restir_context *ctx, cudaError_t e, const char *what) {
+	if (e == cudaSuccess) {
+		return RESTIR_OK;
+	}
+	ctx->cudaFailed = true;
+	return fail(ctx, e == cudaErrorMemoryAllocation ? RESTIR_E_NOMEM : RESTIR_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(ctx, call)                                              \
+	do {                                                           \
+		int rc_ = cudaCheck((ctx), (call), #call);                 \
+		if (rc_ != RESTIR_OK) return rc_;                          \
+	} while (0)
+
+#define ENTER(ctx)                                                                            \
+	do {                                                                                      \
+		if ((ctx) == nullptr) return RESTIR_E_INVALID;                                        \
+		if ((ctx)->cudaFailed) return RESTIR_E_CUDA; /* sticky */                             \
+		cudaError_t e_ = cudaSetDevice((ctx)->device);                                        \
+		if (e_ != cudaSuccess) return cudaCheck((ctx), e_, "cudaSetDevice");                  \
+	} while (0)
+
+template <typename T> void freeDev(T *&p) {
+	if (p) {
+		cudaFree(p);
+		p = nullptr;
+	}
+}
+
+void dropGBuffers(restir_context *ctx) {
+	for (int s = 0; s < 2; ++s) {
+		for (int k = 0; k < 5; ++k) {
+			freeDev(ctx->ownedPlanes[s][k]);
+		}
+		ctx->gbuf[s] = GBufferView{};
+	}
+}
+
+SceneView sceneView(const restir_context *ctx) {
+	SceneView v{};
+	v.nodes = ctx->nodes;
+	v.tris = ctx->tris;
+	v.pointLights = ctx->pointBlob ? reinterpret_cast<const restir_point_light *>(ctx->pointBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
+	v.triLights = ctx->triBlob ? reinterpret_cast<const restir_tri_light *>(ctx->triBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
+	v.alias = ctx->aliasBlob ? reinterpret_cast<const restir_alias_column *>(ctx->aliasBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
+	v.pointPosLum = ctx->pointPosLum;
+	v.triAux = ctx->triAux;
+	v.srgbLut = ctx->srgbLut;
+	v.pointCount = ctx->pointCount;
+	v.triCount = ctx->triCount;
+	v.aliasCount = ctx->aliasCount;
+	v.nNodes = ctx->nNodes;
+	v.nTris = ctx->nTris;
+	return v;
+}
+
+int checkBuffer(restir_context *ctx, int b) {
+	if (b < 0 || b > 2 || ctx->reservoirs[b] == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "reservoir buffer id %d invalid or restir_resize not called", b);
+	}
+	return RESTIR_OK;
+}
+
+int makeParams(restir_context *ctx, int gbuffer, bool needScene, bool needLights, PassParams &p) {
+	if (ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_resize has not been called");
+	}
+	if (gbuffer < 0 || gbuffer > 1 || ctx->gbuf[gbuffer].worldPos == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "G-buffer slot %d is not bound", gbuffer);
+	}
+	if (needScene && ctx->nodes == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh has not been called");
+	}
+	if (needLights && ctx->aliasBlob == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_lights has not been called");
+	}
+	if (!ctx->haveUniforms) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_set_uniforms has not been called");
+	}
+	if ((int)ctx->uniforms.screenSize[0] != ctx->band.W || (int)ctx->uniforms.screenSize[1] != ctx->band.H) {
+		return fail(ctx, RESTIR_E_INVALID, "uniforms.screenSize %ux%u does not match restir_resize %dx%d", ctx->uniforms.screenSize[0],
+		            ctx->uniforms.screenSize[1], ctx->band.W, ctx->band.H);
+	}
+	p.scene = sceneView(ctx);
+	p.cur = ctx->gbuf[gbuffer];
+	p.prev = ctx->gbuf[gbuffer ^ 1];
+	p.band = ctx->band;
+	p.u = ctx->uniforms;
+	p.counters = ctx->counters;
+	return RESTIR_OK;
+}
+
+int afterLaunch(restir_context *ctx, const char *what) {
+	ctx->launches++;
+	return cudaCheck(ctx, cudaGetLastError(), what);
+}
+
+const size_t kPlaneBytes[5] = {4, 8, 4, 16, 4}; // albedo, normal, material, worldPos, depth
+
+} // namespace
+
+extern "C" {
+
+int restir_create(restir_context **out, int device, void *stream) {
+	if (out == nullptr) {
+		return RESTIR_E_INVALID;
+	}
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || device < 0 || device >= count) {
+		return RESTIR_E_CUDA; // no context to carry a message: there is no CPU fallback
+	}
+	restir_context *ctx = new (std::nothrow) restir_context();
+	if (ctx == nullptr) {
+		return RESTIR_E_NOMEM;
+	}
+	ctx->device = device;
+	int rc = RESTIR_OK;
+	do {
+		if ((rc = cudaCheck(ctx, cudaSetDevice(device), "cudaSetDevice")) != RESTIR_OK) break;
+		if (stream != nullptr) {
+			ctx->stream = static_cast<cudaStream_t>(stream);
+		} else {
+			if ((rc = cudaCheck(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) != RESTIR_OK) break;
+			ctx->ownStream = true;
+		}
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->counters, sizeof(unsigned long long) * kCounterCount), "cudaMalloc counters")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * kCounterCount, ctx->stream), "memset")) != RESTIR_OK) break;
+		// P12: sRGB8 -> linear table, EOTF in double rounded to float
+		float lut[256];
+		for (int i = 0; i < 256; ++i) {
+			double c = i / 255.0;
+			lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+		}
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->srgbLut, sizeof(lut)), "cudaMalloc lut")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMemcpy(ctx->srgbLut, lut, sizeof(lut), cudaMemcpyHostToDevice), "memcpy lut")) != RESTIR_OK) break;
+	} while (false);
+	if (rc != RESTIR_OK) {
+		restir_destroy(ctx);
+		return rc;
+	}
+	*out = ctx;
+	return RESTIR_OK;
+}
+
+void restir_destroy(restir_context *ctx) {
+	if (ctx == nullptr) {
+		return;
+	}
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) {
+		cudaStreamSynchronize(ctx->stream);
+	}
+	dropGBuffers(ctx);
+	freeDev(ctx->nodes);
+	freeDev(ctx->tris);
+	freeDev(ctx->pointBlob);
+	freeDev(ctx->triBlob);
+	freeDev(ctx->aliasBlob);
+	freeDev(ctx->pointPosLum);
+	freeDev(ctx->triAux);
+	freeDev(ctx->srgbLut);
+	freeDev(ctx->staging);
+	freeDev(ctx->counters);
+	for (auto &r : ctx->reservoirs) {
+		freeDev(r);
+	}
+	if (ctx->ownStream && ctx->stream) {
+		cudaStreamDestroy(ctx->stream);
+	}
+	delete ctx;
+}
+
+const char *restir_last_error(const restir_context *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int restir_synchronize(restir_context *ctx) {
+	ENTER(ctx);
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	return RESTIR_OK;
+}
+
+int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles) {
+	ENTER(ctx);
+	if (nodes == nullptr || triangles == nullptr || n_nodes == 0 || n_triangles == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: empty tree");
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	freeDev(ctx->nodes);
+	freeDev(ctx->tris);
+	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
+	CU(ctx, cudaMalloc(&ctx->tris, (size_t)n_triangles * sizeof(restir_triangle)));
+	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
+	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, (size_t)n_triangles * sizeof(restir_triangle), cudaMemcpyHostToDevice, ctx->stream));
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->nNodes = n_nodes;
+	ctx->nTris = n_triangles;
+	return RESTIR_OK;
+}
+
+static int uploadBlob(restir_context *ctx, const void *blob, size_t bytes, size_t stride, unsigned char *&dst, int &count, const char *name) {
+	freeDev(dst);
+	count = 0;
+	if (blob == nullptr || bytes < RESTIR_BLOB_HEADER_BYTES) {
+		return fail(ctx, RESTIR_E_INVALID, "%s blob must be at least %d bytes", name, RESTIR_BLOB_HEADER_BYTES);
+	}
+	int32_t n;
+	std::memcpy(&n, blob, 4);
+	if (n < 0 || (size_t)n * stride + RESTIR_BLOB_HEADER_BYTES > bytes) {
+		return fail(ctx, RESTIR_E_INVALID, "%s blob: count %d does not fit in %zu bytes", name, n, bytes);
+	}
+	CU(ctx, cudaMalloc(&dst, bytes));
+	CU(ctx, cudaMemcpyAsync(dst, blob, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	count = n;
+	return RESTIR_OK;
+}
+
+int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t point_bytes, const void *tri_blob, size_t tri_bytes,
+                         const void *alias_blob, size_t alias_bytes) {
+	ENTER(ctx);
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	int rc;
+	if ((rc = uploadBlob(ctx, point_blob, point_bytes, sizeof(restir_point_light), ctx->pointBlob, ctx->pointCount, "point-light")) != RESTIR_OK) return rc;
+	if ((rc = uploadBlob(ctx, tri_blob, tri_bytes, sizeof(restir_tri_light), ctx->triBlob, ctx->triCount, "triangle-light")) != RESTIR_OK) return rc;
+	if ((rc = uploadBlob(ctx, alias_blob, alias_bytes, sizeof(restir_alias_column), ctx->aliasBlob, ctx->aliasCount, "alias-table")) != RESTIR_OK) return rc;
+	int lights = ctx->pointCount != 0 ? ctx->pointCount : ctx->triCount; // restirOmni.glsl:116 picks the list the same way
+	if (ctx->aliasCount == 0 || ctx->aliasCount != lights) {
+		return fail(ctx, RESTIR_E_INVALID, "alias table has %d columns for %d lights", ctx->aliasCount, lights);
+	}
+	freeDev(ctx->pointPosLum);
+	freeDev(ctx->triAux);
+	if (ctx->pointCount) CU(ctx, cudaMalloc(&ctx->pointPosLum, sizeof(float4) * (size_t)ctx->pointCount));
+	if (ctx->triCount) CU(ctx, cudaMalloc(&ctx->triAux, sizeof(float4) * (size_t)ctx->triCount));
+	SceneView v = sceneView(ctx);
+	launch_derive_light_tables(v.pointLights, ctx->pointCount, ctx->pointPosLum, v.triLights, ctx->triCount, ctx->triAux, ctx->stream);
+	CU(ctx, cudaGetLastError());
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	return RESTIR_OK;
+}
+
+int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end, uint32_t halo) {
+	ENTER(ctx);
+	if (width == 0 || height == 0 || row_begin >= row_end || row_end > height || width > (1u << 20) || height > (1u << 20)) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_resize: bad geometry %ux%u rows [%u,%u)", width, height, row_begin, row_end);
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	dropGBuffers(ctx);
+	for (auto &r : ctx->reservoirs) {
+		freeDev(r);
+	}
+	freeDev(ctx->staging);
+	ctx->stagingPixels = 0;
+	Band b;
+	b.W = (int)width;
+	b.H = (int)height;
+	b.rowBegin = (int)row_begin;
+	b.rowEnd = (int)row_end;
+	b.allocBegin = (int)(row_begin > halo ? row_begin - halo : 0);
+	b.allocEnd = (int)((uint64_t)row_end + halo < height ? row_end + halo : height);
+	ctx->band = b;
+	size_t bytes = ctx->allocPixels() * sizeof(PackedReservoir);
+	for (auto &r : ctx->reservoirs) { // app.h:264-284: three buffers, zero-filled
+		CU(ctx, cudaMalloc(&r, bytes));
+		CU(ctx, cudaMemsetAsync(r, 0, bytes, ctx->stream));
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	return RESTIR_OK;
+}
+
+int restir_resize(restir_context *ctx, uint32_t width, uint32_t height) { return restir_resize_band(ctx, width, height, 0, height, 0); }
+
+int restir_get_band(const restir_context *ctx, uint32_t *row_begin, uint32_t *row_end, uint32_t *alloc_begin, uint32_t *alloc_end) {
+	if (ctx == nullptr) {
+		return RESTIR_E_INVALID;
+	}
+	if (row_begin) *row_begin = (uint32_t)ctx->band.rowBegin;
+	if (row_end) *row_end = (uint32_t)ctx->band.rowEnd;
+	if (alloc_begin) *alloc_begin = (uint32_t)ctx->band.allocBegin;
+	if (alloc_end) *alloc_end = (uint32_t)ctx->band.allocEnd;
+	return RESTIR_OK;
+}
+
+int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *pl) {
+	ENTER(ctx);
+	if (slot < 0 || slot > 1 || pl == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_bind_gbuffer: bad slot");
+	}
+	if (format != RESTIR_GBUFFER_NVIDIA_DEFAULT) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "G-buffer format %d not supported", (int)format);
+	}
+	if (!pl->albedo || !pl->normal || !pl->material || !pl->worldPos || !pl->depth) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_bind_gbuffer: all five planes are required");
+	}
+	GBufferView v;
+	v.albedo = static_cast<const uchar4 *>(pl->albedo);
+	v.normal = static_cast<const short4 *>(pl->normal);
+	v.material = static_cast<const ushort2 *>(pl->material);
+	v.worldPos = static_cast<const float4 *>(pl->worldPos);
+	v.depth = static_cast<const float *>(pl->depth);
+	ctx->gbuf[slot] = v;
+	return RESTIR_OK;
+}
+
+int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *pl) {
+	ENTER(ctx);
+	if (slot < 0 || slot > 1 || pl == nullptr || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_gbuffer: bad slot or restir_resize not called");
+	}
+	if (format != RESTIR_GBUFFER_NVIDIA_DEFAULT) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "G-buffer format %d not supported", (int)format);
+	}
+	const void *src[5] = {pl->albedo, pl->normal, pl->material, pl->worldPos, pl->depth};
+	size_t px = ctx->allocPixels();
+	for (int k = 0; k < 5; ++k) {
+		if (src[k] == nullptr) {
+			return fail(ctx, RESTIR_E_INVALID, "restir_upload_gbuffer: all five planes are required");
+		}
+		if (ctx->ownedPlanes[slot][k] == nullptr) {
+			CU(ctx, cudaMalloc(&ctx->ownedPlanes[slot][k], px * kPlaneBytes[k]));
+		}
+		CU(ctx, cudaMemcpyAsync(ctx->ownedPlanes[slot][k], src[k], px * kPlaneBytes[k], cudaMemcpyHostToDevice, ctx->stream));
+	}
+	restir_gbuffer_planes dev{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],
+	                          ctx->ownedPlanes[slot][4]};
+	return restir_bind_gbuffer(ctx, slot, format, &dev);
+}
+
+int restir_set_uniforms(restir_context *ctx, const restir_uniforms *u) {
+	ENTER(ctx);
+	if (u == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "null uniforms");
+	}
+	ctx->uniforms = *u;
+	ctx->haveUniforms = true;
+	return RESTIR_OK;
+}
+
+int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_uniforms *u) {
+	ENTER(ctx);
+	if (u == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "null uniforms");
+	}
+	if (u->debugMode != 0) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "lighting debugMode %d: only GBUFFER_DEBUG_NONE (0) is on the hot path", u->debugMode);
+	}
+	ctx->lighting = *u;
+	ctx->haveLighting = true;
+	return RESTIR_OK;
+}
+
+int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count) {
+	ENTER(ctx);
+	if (count < 1 || count > 16) {
+		return fail(ctx, RESTIR_E_INVALID, "unbiased neighbour count must be in 1..16");
+	}
+	ctx->unbiasedNeighbors = count;
+	return RESTIR_OK;
+}
+
+int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int prev_buffer) {
+	ENTER(ctx);
+	PassParams p;
+	int rc;
+	if ((rc = makeParams(ctx, gbuffer, true, true, p)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, out_buffer)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, prev_buffer)) != RESTIR_OK) return rc;
+	if (out_buffer == prev_buffer) {
+		return fail(ctx, RESTIR_E_INVALID, "restir pass: out and prev buffers must differ");
+	}
+	launch_restir_omni(p, ctx->reservoirs[out_buffer], ctx->reservoirs[prev_buffer], ctx->stream);
+	return afterLaunch(ctx, "restir_omni_kernel");
+}
+
+int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter) {
+	ENTER(ctx);
+	PassParams p;
+	int rc;
+	if ((rc = makeParams(ctx, gbuffer, false, true, p)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, in_buffer)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, out_buffer)) != RESTIR_OK) return rc;
+	if (in_buffer == out_buffer) {
+		return fail(ctx, RESTIR_E_INVALID, "spatial pass: in and out buffers must differ");
+	}
+	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, ctx->stream);
+	return afterLaunch(ctx, "spatial_reuse_kernel");
+}
+
+int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer) {
+	ENTER(ctx);
+	PassParams p;
+	int rc;
+	if ((rc = makeParams(ctx, gbuffer, true, true, p)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, in_buffer)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, out_buffer)) != RESTIR_OK) return rc;
+	if (in_buffer == out_buffer) {
+		return fail(ctx, RESTIR_E_INVALID, "unbiased pass: in and out buffers must differ");
+	}
+	launch_unbiased_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], (int)ctx->unbiasedNeighbors, ctx->stream);
+	return afterLaunch(ctx, "unbiased_reuse_kernel");
+}
+
+int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out_device, int out_format) {
+	ENTER(ctx);
+	PassParams p;
+	int rc;
+	if ((rc = makeParams(ctx, gbuffer, false, true, p)) != RESTIR_OK) return rc;
+	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
+	if (!ctx->haveLighting) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_set_lighting_uniforms has not been called");
+	}
+	if (out_device == nullptr || (out_format != RESTIR_OUT_RGBA32F && out_format != RESTIR_OUT_RGBA8_SRGB)) {
+		return fail(ctx, RESTIR_E_INVALID, "lighting pass: bad output");
+	}
+	if ((int)ctx->lighting.bufferSize[0] != ctx->band.W || (int)ctx->lighting.bufferSize[1] != ctx->band.H) {
+		return fail(ctx, RESTIR_E_INVALID, "lighting uniforms bufferSize does not match restir_resize");
+	}
+	launch_lighting(p, ctx->lighting, ctx->reservoirs[buffer], out_device, out_format, ctx->stream);
+	return afterLaunch(ctx, "lighting_kernel");
+}
+
+int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations) {
+	ENTER(ctx);
+	if (i < 0 || i > 1 || spatial_iterations < 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_frame: bad frame index");
+	}
+	if (ctx->band.rowBegin != 0 || ctx->band.rowEnd != ctx->band.H) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_frame is for single-GPU contexts; band contexts interleave halo exchanges");
+	}
+	int rc;
+	const int cur = i, prev = i ^ 1; // app.h:298-332
+	if (unbiased) {
+		if ((rc = restir_pass_restir(ctx, i, RESTIR_BUF_TEMP, prev)) != RESTIR_OK) return rc;
+		return restir_pass_unbiased(ctx, i, RESTIR_BUF_TEMP, cur);
+	}
+	if ((rc = restir_pass_restir(ctx, i, cur, prev)) != RESTIR_OK) return rc;
+	for (int j = 0; j < spatial_iterations; ++j) {
+		if ((rc = restir_pass_spatial(ctx, i, cur, prev, j * 2)) != RESTIR_OK) return rc;
+		if ((rc = restir_pass_spatial(ctx, i, prev, cur, j * 2 + 1)) != RESTIR_OK) return rc;
+	}
+	return RESTIR_OK;
+}
+
+static int ensureStaging(restir_context *ctx) {
+	size_t px = ctx->allocPixels();
+	if (ctx->stagingPixels < px) {
+		freeDev(ctx->staging);
+		ctx->stagingPixels = 0;
+		CU(ctx, cudaMalloc(&ctx->staging, px * sizeof(restir_reservoir)));
+		ctx->stagingPixels = px;
+	}
+	return RESTIR_OK;
+}
+
+int restir_download_reservoirs(restir_context *ctx, int buffer, restir_reservoir *dst_host) {
+	ENTER(ctx);
+	int rc;
+	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
+	if (dst_host == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "null destination");
+	}
+	if ((rc = ensureStaging(ctx)) != RESTIR_OK) return rc;
+	size_t px = ctx->allocPixels();
+	launch_unpack_reservoirs(sceneView(ctx), ctx->reservoirs[buffer], ctx->staging, px, ctx->stream);
+	if ((rc = afterLaunch(ctx, "unpack_reservoirs_kernel")) != RESTIR_OK) return rc;
+	CU(ctx, cudaMemcpyAsync(dst_host, ctx->staging, px * sizeof(restir_reservoir), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	return RESTIR_OK;
+}
+
+int restir_upload_reservoirs(restir_context *ctx, int buffer, const restir_reservoir *src_host) {
+	ENTER(ctx);
+	int rc;
+	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
+	if (src_host == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "null source");
+	}
+	if ((rc = ensureStaging(ctx)) != RESTIR_OK) return rc;
+	size_t px = ctx->allocPixels();
+	CU(ctx, cudaMemcpyAsync(ctx->staging, src_host, px * sizeof(restir_reservoir), cudaMemcpyHostToDevice, ctx->stream));
+	launch_pack_reservoirs(ctx->staging, ctx->reservoirs[buffer], px, ctx->stream);
+	if ((rc = afterLaunch(ctx, "pack_reservoirs_kernel")) != RESTIR_OK) return rc;
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	return RESTIR_OK;
+}
+
+int restir_reservoir_device_ptr(restir_context *ctx, int buffer, void **ptr, size_t *row_pitch_bytes) {
+	ENTER(ctx);
+	int rc;
+	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
+	if (ptr) *ptr = ctx->reservoirs[buffer];
+	if (row_pitch_bytes) *row_pitch_bytes = (size_t)ctx->band.W * sizeof(PackedReservoir);
+	return RESTIR_OK;
+}
+
+int restir_trace_segments(restir_context *ctx, const float *p1, const float *p2, uint64_t n, uint8_t *shadowed) {
+	ENTER(ctx);
+	if (ctx->nodes == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh has not been called");
+	}
+	if (n != 0 && (p1 == nullptr || p2 == nullptr || shadowed == nullptr)) {
+		return fail(ctx, RESTIR_E_INVALID, "null segment arrays");
+	}
+	if (n == 0) {
+		return RESTIR_OK;
+	}
+	launch_trace_segments(sceneView(ctx), p1, p2, n, shadowed, ctx->counters, ctx->stream);
+	return afterLaunch(ctx, "trace_segments_kernel");
+}
+
+int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
+	ENTER(ctx);
+	unsigned long long h[kCounterCount];
+	CU(ctx, cudaMemcpyAsync(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	if (out) {
+		out->shadow_rays = h[kCounterRays];
+		out->stack_overflows = h[kCounterOverflow];
+		out->halo_misses = h[kCounterHaloMiss];
+		out->kernel_launches = ctx->launches;
+	}
+	if (reset) {
+		CU(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(h), ctx->stream));
+		ctx->launches = 0;
+	}
+	return RESTIR_OK;
+}
+
+// ---- fixture tool ------------------------------------------------------------------------------
+
+namespace {
+struct H3 {
+	float x, y, z;
+};
+inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float hdot(H3 a, H3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return H3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline H3 hnorm(H3 v) {
+	float inv = 1.0f / sqrtf(hdot(v, v));
+	return H3{v.x * inv, v.y * inv, v.z * inv};
+}
+void cameraBasis(const restir_camera *c, H3 &pos, H3 &fwd, H3 &right, H3 &up) { // camera.h:25-28
+	pos = H3{c->position[0], c->position[1], c->position[2]};
+	fwd = hnorm(hsub(H3{c->lookAt[0], c->lookAt[1], c->lookAt[2]}, pos));
+	right = hnorm(hcross(fwd, H3{c->worldUp[0], c->worldUp[1], c->worldUp[2]}));
+	up = hcross(right, fwd);
+}
+} // namespace
+
+int restir_camera_matrix(const restir_camera *c, float out_pv[16]) {
+	if (c == nullptr || out_pv == nullptr) {
+		return RESTIR_E_INVALID;
+	}
+	H3 pos, fwd, right, up;
+	cameraBasis(c, pos, fwd, right, up);
+	H3 r0 = right, r1 = H3{-up.x, -up.y, -up.z}, r2 = fwd; // camera.h:30-33: row 1 carries the y flip
+	float view[4][4] = {{r0.x, r0.y, r0.z, -hdot(r0, pos)}, {r1.x, r1.y, r1.z, -hdot(r1, pos)}, {r2.x, r2.y, r2.z, -hdot(r2, pos)}, {0, 0, 0, 1}};
+	float f = 1.0f / tanf(0.5f * c->fovYRadians); // camera.h:41-47
+	float proj[4][4] = {{f / c->aspectRatio, 0, 0, 0},
+	                    {0, f, 0, 0},
+	                    {0, 0, -c->zFar / (c->zNear - c->zFar), c->zNear * c->zFar / (c->zNear - c->zFar)},
+	                    {0, 0, 1, 0}};
+	for (int r = 0; r < 4; ++r) {
+		for (int col = 0; col < 4; ++col) {
+			float acc = 0.0f;
+			for (int k = 0; k < 4; ++k) {
+				acc = acc + proj[r][k] * view[k][col];
+			}
+			out_pv[col * 4 + r] = acc;
+		}
+	}
+	return RESTIR_OK;
+}
+
+int restir_tools_raycast_gbuffer(restir_context *ctx, const restir_camera *camera, const int32_t *tri_material_device,
+                                 const uint32_t *material_table_device, void *albedo, void *normal, void *material, void *worldPos,
+                                 void *depth) {
+	ENTER(ctx);
+	if (ctx->nodes == nullptr || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "raycast: upload the BVH and call restir_resize first");
+	}
+	if (!camera || !tri_material_device || !material_table_device || !albedo || !normal || !material || !worldPos || !depth) {
+		return fail(ctx, RESTIR_E_INVALID, "raycast: null argument");
+	}
+	RaycastCamera rc;
+	H3 pos, fwd, right, up;
+	cameraBasis(camera, pos, fwd, right, up);
+	float f = 1.0f / tanf(0.5f * camera->fovYRadians);
+	rc.pos[0] = pos.x; rc.pos[1] = pos.y; rc.pos[2] = pos.z;
+	rc.fwd[0] = fwd.x; rc.fwd[1] = fwd.y; rc.fwd[2] = fwd.z;
+	rc.right[0] = right.x; rc.right[1] = right.y; rc.right[2] = right.z;
+	rc.up[0] = up.x; rc.up[1] = up.y; rc.up[2] = up.z;
+	rc.sx = camera->aspectRatio / f;
+	rc.sy = 1.0f / f;
+	restir_camera_matrix(camera, rc.pv);
+	Band full = ctx->band; // the fixture covers every row the context holds, halo included
+	full.rowBegin = full.allocBegin;
+	full.rowEnd = full.allocEnd;
+	launch_raycast_gbuffer(sceneView(ctx), full, rc, tri_material_device, reinterpret_cast<const uint4 *>(material_table_device), albedo, normal,
+	                       material, worldPos, depth, ctx->stream);
+	return afterLaunch(ctx, "raycast_gbuffer_kernel");
+}
+
+} // extern "C"

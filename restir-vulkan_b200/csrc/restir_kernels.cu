@@ -1,0 +1,763 @@
+// restir_kernels.cu — hand-written sm_100a kernels of the ReSTIR resampling path.
+//
+//   restir_omni_kernel      <- src/shaders/restirOmni.glsl:86-212   (RIS + visibility reuse + temporal reuse)
+//   spatial_reuse_kernel    <- src/shaders/spatialReuse.comp:30-86
+//   unbiased_reuse_kernel   <- src/shaders/unbiasedReuse.glsl:50-185
+//   lighting_kernel         <- src/shaders/lighting.frag:43-71,103  (debugMode 0)
+//   trace_segments_kernel   <- src/shaders/include/visibilityTest.glsl:1-4,27-28 + softwareRaytracing.glsl
+//   raycast_gbuffer_kernel  fixture tool (primary visibility through the same tree)
+//
+// One thread shades one pixel, as in the reference, but a CTA covers a 32x8 screen tile made of
+// eight 8x4 warp tiles (the reference uses 64x1 workgroups, restirStructs.glsl:10-14): rays of a warp
+// start from a compact screen patch and the G-buffer / reservoir rows a warp touches are whole 32-byte
+// sectors.  Reservoirs live in HBM as 32-byte PackedReservoir records.
+
+#include "restir_device.cuh"
+#include "restir_kernels.h"
+
+namespace restir {
+
+// ------------------------------------------------------------------------------------------------
+// thread -> pixel mapping
+constexpr int kTileW = 32, kTileH = 8, kThreads = 256;
+
+__device__ __forceinline__ bool pixel_of_thread(const Band &b, int &x, int &y) {
+	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
+	y = b.rowBegin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+	return x < b.W && y < b.rowEnd;
+}
+__device__ __forceinline__ size_t local_index(const Band &b, int x, int y) {
+	return (size_t)(y - b.allocBegin) * (size_t)b.W + (size_t)x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// G-buffer texel decode (texelFetch of the NVIDIA-default formats)
+__device__ __forceinline__ f3 fetch_albedo(const GBufferView &g, const float *lut, size_t i, float *alpha) {
+	if (g.albedo == nullptr) {
+		if (alpha) *alpha = 0.0f;
+		return mk3(0.0f, 0.0f, 0.0f);
+	}
+	uchar4 c = __ldg(g.albedo + i);
+	if (alpha) *alpha = (float)c.w / 255.0f;
+	return mk3(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z));
+}
+__device__ __forceinline__ f3 fetch_normal(const GBufferView &g, size_t i) {
+	if (g.normal == nullptr) {
+		return mk3(0.0f, 0.0f, 0.0f);
+	}
+	short4 n = __ldg(g.normal + i);
+	return mk3(fmaxf((float)n.x / 32767.0f, -1.0f), fmaxf((float)n.y / 32767.0f, -1.0f), fmaxf((float)n.z / 32767.0f, -1.0f));
+}
+__device__ __forceinline__ void fetch_material(const GBufferView &g, size_t i, float &roughness, float &metallic) {
+	ushort2 m = __ldg(g.material + i);
+	roughness = (float)m.x / 65535.0f;
+	metallic = (float)m.y / 65535.0f;
+}
+__device__ __forceinline__ f3 fetch_world_pos(const GBufferView &g, size_t i) {
+	if (g.worldPos == nullptr) {
+		return mk3(0.0f, 0.0f, 0.0f);
+	}
+	float4 p = __ldg(g.worldPos + i);
+	return mk3(p.x, p.y, p.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed reservoir I/O: two 16-byte transactions per record
+__device__ __forceinline__ PackedReservoir load_reservoir(const PackedReservoir *buf, size_t i) {
+	const float4 *p = reinterpret_cast<const float4 *>(buf + i);
+	float4 a = __ldg(p), b = __ldg(p + 1);
+	PackedReservoir r;
+	r.px = a.x; r.py = a.y; r.pz = a.z; r.lightIndex = __float_as_int(a.w);
+	r.pHat = b.x; r.sumWeights = b.y; r.w = b.z; r.M = __float_as_uint(b.w);
+	return r;
+}
+__device__ __forceinline__ void store_reservoir(PackedReservoir *buf, size_t i, const PackedReservoir &r) {
+	float4 *p = reinterpret_cast<float4 *>(buf + i);
+	p[0] = make_float4(r.px, r.py, r.pz, __int_as_float(r.lightIndex));
+	p[1] = make_float4(r.pHat, r.sumWeights, r.w, __uint_as_float(r.M));
+}
+
+// normal / useLightNormal / emissionLum of a stored sample, re-read from the light tables
+// (restirOmni.glsl:117-133 wrote exactly these values into the reference's 64-byte reservoir).
+__device__ __forceinline__ void sample_light_attrs(const SceneView &sc, const PackedReservoir &r, f3 &n, bool &useN, float &lum) {
+	if (r.pHat == 0.0f) { // never selected: all-zero sample (oracle definition of reservoir.glsl:66-76)
+		n = mk3(0.0f, 0.0f, 0.0f);
+		useN = false;
+		lum = 0.0f;
+	} else if (r.lightIndex >= 0) {
+		n = mk3(0.0f, 0.0f, 0.0f);
+		useN = false;
+		lum = __ldg(sc.pointPosLum + r.lightIndex).w;
+	} else {
+		float4 a = __ldg(sc.triAux + (-1 - r.lightIndex));
+		n = mk3(a.x, a.y, a.z);
+		useN = true;
+		lum = a.w;
+	}
+}
+
+// reservoir.glsl:6-26 on the packed fields.  One RNG draw, always.
+__device__ __forceinline__ void update_reservoir(PackedReservoir &res, float weight, f3 pos, int lightIdx, float pHat, float w, Pcg32 &rng) {
+	res.sumWeights = res.sumWeights + weight;
+	float replacePossibility = weight / res.sumWeights;
+	if (pcg_float(rng) < replacePossibility) {
+		res.px = pos.x; res.py = pos.y; res.pz = pos.z;
+		res.lightIndex = lightIdx;
+		res.pHat = pHat;
+		res.w = w;
+	}
+}
+
+// reservoir.glsl:44-64.  evaluatePHat of the other sample is only needed when the merge weight can be
+// positive: weight = (pHat * other.w) * other.M is +-0 or NaN whenever other.w == 0 or other.M == 0, and
+// then neither the update nor its RNG draw happens — an exact shortcut, not an approximation.
+__device__ __forceinline__ void combine_reservoirs(PackedReservoir &self, const PackedReservoir &other, const SceneView &sc,
+                                                   const Surface &sf, float albedoLum, Pcg32 &rng) {
+	self.M += other.M;
+	if (other.w != 0.0f && other.M != 0u) {
+		f3 n; bool useN; float lum;
+		sample_light_attrs(sc, other, n, useN, lum);
+		float pHat = evaluate_phat(sf, albedoLum, mk3(other.px, other.py, other.pz), n, useN, lum);
+		float weight = (pHat * other.w) * (float)other.M;
+		if (weight > 0.0f) {
+			update_reservoir(self, weight, mk3(other.px, other.py, other.pz), other.lightIndex, pHat, other.w, rng);
+		}
+	}
+	if (self.w > 0.0f) {
+		self.w = self.sumWeights / ((float)self.M * self.pHat);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// shadow rays: softwareRaytracing.glsl + visibilityTest.glsl (software branch)
+
+// softwareRaytracing.glsl:9-14 with the division hoisted (P3): inv = 1/dir once per ray.
+__device__ __forceinline__ bool ray_box(f3 o, f3 inv, float4 bmin, float4 bmax) {
+	float t1x = (bmin.x - o.x) * inv.x, t1y = (bmin.y - o.y) * inv.y, t1z = (bmin.z - o.z) * inv.z;
+	float t2x = (bmax.x - o.x) * inv.x, t2y = (bmax.y - o.y) * inv.y, t2z = (bmax.z - o.z) * inv.z;
+	float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+	float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+	return rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
+}
+// softwareRaytracing.glsl:15-37
+__device__ __forceinline__ bool ray_triangle(const float4 *tris, int id, f3 o, f3 d) {
+	const float4 *t = tris + (size_t)id * 3;
+	float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+	f3 p1 = mk3(a.x, a.y, a.z);
+	f3 e1 = mk3(b.x, b.y, b.z) - p1;
+	f3 e2 = mk3(c.x, c.y, c.z) - p1;
+	f3 p = cross3(d, e2);
+	float f = 1.0f / dot3(e1, p);
+	f3 s = o - p1;
+	float baryX = f * dot3(s, p);
+	if (baryX < 0.0f || baryX > 1.0f) {
+		return false;
+	}
+	f3 q = cross3(s, e1);
+	float baryY = f * dot3(d, q);
+	if (baryY < 0.0f || baryY + baryX > 1.0f) {
+		return false;
+	}
+	f = f * dot3(e2, q);
+	return f > 0.0f && f < 1.0f;
+}
+
+// softwareRaytracing.glsl:39-85.  Any-hit: the answer does not depend on the order in which nodes and
+// triangles are visited, only on which boxes / triangles the segment intersects, so triangles are tested
+// as soon as their leaf box is hit instead of being deferred in batches of 8 node visits.  The stack is
+// the reference's 32 entries with its push order (left, then right); a push onto a full stack is dropped
+// and counted (UB in the reference).  Returns true when nothing is hit.
+__device__ bool trace_any(const SceneView &sc, f3 o, f3 d, unsigned &overflow) {
+	int stack[32];
+	int top = 1;
+	stack[0] = 0;
+	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	while (top > 0) {
+		const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
+		float4 lmin = __ldg(n), lmax = __ldg(n + 1), rmin = __ldg(n + 2), rmax = __ldg(n + 3);
+		float4 ch = __ldg(n + 4);
+		int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
+		if (ray_box(o, inv, lmin, lmax)) {
+			if (left < 0) {
+				if (ray_triangle(sc.tris, ~left, o, d)) {
+					return false;
+				}
+			} else if (top < 32) {
+				stack[top++] = left;
+			} else {
+				overflow++;
+			}
+		}
+		if (ray_box(o, inv, rmin, rmax)) {
+			if (right < 0) {
+				if (ray_triangle(sc.tris, ~right, o, d)) {
+					return false;
+				}
+			} else if (top < 32) {
+				stack[top++] = right;
+			} else {
+				overflow++;
+			}
+		}
+	}
+	return true;
+}
+
+// visibilityTest.glsl:1-4, 27-28.  Returns SHADOWED.
+__device__ __forceinline__ bool test_visibility(const SceneView &sc, f3 p1, f3 p2, unsigned &overflow) {
+	f3 dir = p2 - p1;
+	f3 offset = normalize3(dir) * 0.001f;
+	return !trace_any(sc, p1 + offset, dir - offset * 2.0f, overflow);
+}
+
+__device__ __forceinline__ void add_counter(unsigned long long *counters, int slot, unsigned v) {
+	// one atomic per warp
+	unsigned total = __reduce_add_sync(0xffffffffu, v);
+	if ((threadIdx.x & 31) == 0 && total != 0) {
+		atomicAdd(counters + slot, (unsigned long long)total);
+	}
+}
+
+// restirOmni.glsl:73-83
+__device__ __forceinline__ void alias_sample(const SceneView &sc, float r1, float r2, int &index, float &prob) {
+	int col = min((int)((float)sc.aliasCount * r1), sc.aliasCount - 1);
+	float4 c = __ldg(reinterpret_cast<const float4 *>(sc.alias) + col);
+	if (c.x > r2) {
+		index = col;
+		prob = c.z;
+	} else {
+		index = __float_as_int(c.y);
+		prob = c.w;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// restirOmni.glsl:86-212
+__global__ void __launch_bounds__(kThreads) restir_omni_kernel(PassParams p, PackedReservoir *__restrict__ out,
+                                                              const PackedReservoir *__restrict__ prevReservoirs) {
+	int x, y;
+	bool active = pixel_of_thread(p.band, x, y);
+	unsigned rays = 0, overflow = 0, haloMiss = 0;
+	if (active) {
+		const SceneView &sc = p.scene;
+		size_t pix = local_index(p.band, x, y);
+		f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
+		f3 normal = fetch_normal(p.cur, pix);
+		float roughness, metallic;
+		fetch_material(p.cur, pix, roughness, metallic);
+		f3 worldPos = fetch_world_pos(p.cur, pix);
+		float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
+		f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+		Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+
+		PackedReservoir res;                                                      // :105
+		res.px = res.py = res.pz = 0.0f;
+		res.lightIndex = 0;
+		res.pHat = res.sumWeights = res.w = 0.0f;
+		res.M = 0u;
+		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
+		if (dot3(normal, normal) != 0.0f) {                                       // :107
+			const uint32_t count = p.u.initialLightSampleCount;
+			const bool pointMode = sc.pointCount != 0;
+			for (uint32_t i = 0; i < count; ++i) {                                // :108-142
+				float r1 = pcg_float(rng);
+				float r2 = pcg_float(rng);
+				int idx;
+				float prob;
+				alias_sample(sc, r1, r2, idx, prob);
+				f3 lpos, ln;
+				float lum;
+				int lightIndex;
+				if (pointMode) {                                                  // :116-122
+					float4 pl = __ldg(sc.pointPosLum + idx);
+					lpos = mk3(pl.x, pl.y, pl.z);
+					lum = pl.w;
+					lightIndex = idx;
+					ln = mk3(0.0f, 0.0f, 0.0f);
+				} else {                                                          // :123-133
+					const float4 *tl = reinterpret_cast<const float4 *>(sc.triLights + idx);
+					float4 a = __ldg(tl), b = __ldg(tl + 1), c = __ldg(tl + 2), em = __ldg(tl + 3), na = __ldg(tl + 4);
+					float r3 = pcg_float(rng);
+					float r4 = pcg_float(rng);
+					float sq = sqrtf(r3);                                          // pickPointOnTriangle :68-71
+					lpos = (mk3(a.x, a.y, a.z) * (1.0f - sq) + mk3(b.x, b.y, b.z) * (sq * (1.0f - r4))) + mk3(c.x, c.y, c.z) * (r4 * sq);
+					lum = em.w;
+					lightIndex = -1 - idx;
+					f3 wi = normalize3(worldPos - lpos);
+					ln = mk3(na.x, na.y, na.z);
+					prob = prob / (fabsf(dot3(wi, ln)) * na.w);
+				}
+				float pHat = evaluate_phat(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
+				// addSampleToReservoir, reservoir.glsl:28-42
+				float weight = pHat / prob;
+				res.M += 1u;
+				float w = (res.sumWeights + weight) / ((float)res.M * pHat);
+				update_reservoir(res, weight, lpos, lightIndex, pHat, w, rng);
+			}
+		}
+
+		// visibility reuse, :148-160 (M is kept)
+		if ((p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0) {
+			bool shadowed = test_visibility(sc, worldPos, mk3(res.px, res.py, res.pz), overflow);
+			rays = 1;
+			if (shadowed) {
+				res.w = 0.0f;
+				res.sumWeights = 0.0f;
+			}
+		}
+
+		// temporal reuse, :163-209
+		if ((p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0) {
+			const float *M = p.u.prevFrameProjectionViewMatrix;
+			float px = ((M[0] * worldPos.x + M[4] * worldPos.y) + M[8] * worldPos.z) + M[12] * 1.0f;
+			float py = ((M[1] * worldPos.x + M[5] * worldPos.y) + M[9] * worldPos.z) + M[13] * 1.0f;
+			float pw = ((M[3] * worldPos.x + M[7] * worldPos.y) + M[11] * worldPos.z) + M[15] * 1.0f;
+			float invW = 1.0f / pw;
+			px = px * invW;
+			py = py * invW;
+			px = ((px + 1.0f) * 0.5f) * (float)p.band.W;
+			py = ((py + 1.0f) * 0.5f) * (float)p.band.H;
+			if (px > 0.0f && py > 0.0f && px < (float)p.band.W && py < (float)p.band.H) {
+				int fx = (int)px, fy = (int)py;
+				if (fy < p.band.allocBegin || fy >= p.band.allocEnd) {
+					haloMiss = 1; // band too thin for this camera motion: reported, never silent
+				} else {
+					size_t ppix = local_index(p.band, fx, fy);
+					f3 dp = worldPos - fetch_world_pos(p.prev, ppix);
+					if (dot3(dp, dp) < 0.01f) {
+						f3 da = albedo - fetch_albedo(p.prev, sc.srgbLut, ppix, nullptr);
+						if (dot3(da, da) < 0.01f) {
+							float nd = dot3(normal, fetch_normal(p.prev, ppix));
+							if (nd > 0.5f) {
+								PackedReservoir prevRes = load_reservoir(prevReservoirs, ppix);
+								prevRes.M = min(prevRes.M, p.u.temporalSampleCountMultiplier * res.M); // :189-191
+								combine_reservoirs(res, prevRes, sc, sf, albedoLum, rng);
+							}
+						}
+					}
+				}
+			}
+		}
+		store_reservoir(out, pix, res);                                           // :211
+	}
+	add_counter(p.counters, kCounterRays, rays);
+	add_counter(p.counters, kCounterOverflow, overflow);
+	add_counter(p.counters, kCounterHaloMiss, haloMiss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// spatialReuse.comp:30-86
+__global__ void __launch_bounds__(kThreads) spatial_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+                                                                PackedReservoir *__restrict__ out, int iter) {
+	int x, y;
+	bool active = pixel_of_thread(p.band, x, y);
+	unsigned haloMiss = 0;
+	if (active) {
+		const SceneView &sc = p.scene;
+		size_t pix = local_index(p.band, x, y);
+		f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
+		f3 normal = fetch_normal(p.cur, pix);
+		float roughness, metallic;
+		fetch_material(p.cur, pix, roughness, metallic);
+		f3 worldPos = fetch_world_pos(p.cur, pix);
+		float worldDepth = __ldg(p.cur.depth + pix);
+		float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);
+		f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+		Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+		float sinThr, cosThr;
+		sincos_policy(p.u.spatialNormalThreshold * 0.017453292519943295f, sinThr, cosThr); // :67
+
+		PackedReservoir res = load_reservoir(in, pix);
+		Pcg32 rng = pcg_seed(p.u.frame * 31u + (uint32_t)iter, (uint32_t)y * 10007u + (uint32_t)x); // :47
+		const uint32_t k = p.u.spatialNeighbors;
+		for (uint32_t i = 0; i < k; ++i) {
+			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;                  // :52
+			float radius = sqrtf(pcg_float(rng)) * p.u.spatialRadius;             // :53
+			float sn, cs;
+			sincos_policy(angle, sn, cs);
+			int nx = x + (int)floorf(cs * radius), ny = y + (int)floorf(sn * radius); // :55-57
+			nx = max(0, min(nx, p.band.W - 1));
+			ny = max(0, min(ny, p.band.H - 1));
+			if (ny < p.band.allocBegin || ny >= p.band.allocEnd) {
+				haloMiss = 1;
+				continue;
+			}
+			size_t npix = local_index(p.band, nx, ny);
+			float nDepth = __ldg(p.cur.depth + npix);
+			f3 nNor = fetch_normal(p.cur, npix);
+			if (fabsf(nDepth - worldDepth) > p.u.spatialPosThreshold * fabsf(worldDepth) || dot3(nNor, normal) < cosThr) { // :65-70
+				continue;
+			}
+			PackedReservoir other = load_reservoir(in, npix);
+			combine_reservoirs(res, other, sc, sf, albedoLum, rng);               // :72-83
+		}
+		store_reservoir(out, pix, res);
+	}
+	add_counter(p.counters, kCounterHaloMiss, haloMiss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// unbiasedReuse.glsl:50-185
+constexpr int kMaxUnbiasedNeighbors = 16;
+
+__global__ void __launch_bounds__(kThreads) unbiased_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+                                                                 PackedReservoir *__restrict__ out, int numNeighbors) {
+	int x, y;
+	bool active = pixel_of_thread(p.band, x, y);
+	unsigned rays = 0, overflow = 0, haloMiss = 0;
+	if (active) {
+		const SceneView &sc = p.scene;
+		size_t pix = local_index(p.band, x, y);
+		f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
+		f3 normal = fetch_normal(p.cur, pix);
+		float roughness, metallic;
+		fetch_material(p.cur, pix, roughness, metallic);
+		f3 worldPos = fetch_world_pos(p.cur, pix);
+		float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);
+		f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+		Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+
+		PackedReservoir res = load_reservoir(in, pix);
+		Pcg32 rng = pcg_seed(p.u.frame * 17u, (uint32_t)y * 10007u + (uint32_t)x); // :72
+		uint32_t originalM = res.M;
+		int npx[kMaxUnbiasedNeighbors];
+		uint32_t nM[kMaxUnbiasedNeighbors];
+#pragma unroll 1
+		for (int i = 0; i < numNeighbors; ++i) {                                  // :84-124
+			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;
+			float radius = sqrtf(pcg_float(rng)) * p.u.spatialRadius;
+			float sn, cs;
+			sincos_policy(angle, sn, cs);
+			int nx = x + (int)roundf(cs * radius), ny = y + (int)roundf(sn * radius); // :88-89
+			nx = max(0, min(nx, p.band.W - 1));
+			ny = max(0, min(ny, p.band.H - 1));
+			if (ny < p.band.allocBegin || ny >= p.band.allocEnd) {
+				haloMiss = 1;
+				npx[i] = -1;
+				nM[i] = 0;
+				continue;
+			}
+			size_t npix = local_index(p.band, nx, ny);
+			PackedReservoir other = load_reservoir(in, npix);
+			npx[i] = (int)npix;
+			nM[i] = other.M;
+			res.M += other.M;                                                     // :104
+			if (other.w != 0.0f && other.M != 0u) {                               // see combine_reservoirs
+				f3 n; bool useN; float lum;
+				sample_light_attrs(sc, other, n, useN, lum);
+				float pHat = evaluate_phat(sf, albedoLum, mk3(other.px, other.py, other.pz), n, useN, lum);
+				float weight = (pHat * other.w) * (float)other.M;
+				if (weight > 0.0f) {
+					update_reservoir(res, weight, mk3(other.px, other.py, other.pz), other.lightIndex, pHat, other.w, rng);
+				}
+			}
+		}
+		// :126-182
+		f3 lightPos = mk3(res.px, res.py, res.pz);
+		uint32_t numSamples = originalM;
+		const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
+#pragma unroll 1
+		for (int j = 0; j < numNeighbors; ++j) {
+			if (npx[j] < 0) {
+				continue;
+			}
+			f3 nPos = fetch_world_pos(p.cur, (size_t)npx[j]);
+			f3 nNor = fetch_normal(p.cur, (size_t)npx[j]);
+			if (dot3(lightPos - nPos, nNor) < 0.0f) {
+				continue;
+			}
+			if (vis) {
+				rays++;
+				if (test_visibility(sc, nPos, lightPos, overflow)) {
+					continue;
+				}
+			}
+			numSamples += nM[j];
+		}
+		if (vis) {
+			rays++;
+			if (test_visibility(sc, worldPos, lightPos, overflow)) {
+				numSamples = 0;
+			}
+		}
+		if (numSamples > 0) {
+			res.w = res.sumWeights / ((float)numSamples * res.pHat);
+		} else {
+			res.w = 0.0f;
+			res.sumWeights = 0.0f;
+		}
+		store_reservoir(out, pix, res);
+	}
+	add_counter(p.counters, kCounterRays, rays);
+	add_counter(p.counters, kCounterOverflow, overflow);
+	add_counter(p.counters, kCounterHaloMiss, haloMiss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lighting.frag:43-71,103 (debugMode 0)
+__device__ __forceinline__ float srgb_encode(float c) {
+	c = fminf(fmaxf(c, 0.0f), 1.0f);
+	return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+
+__global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir_lighting_uniforms lu,
+                                                           const PackedReservoir *__restrict__ reservoirs, void *__restrict__ outPixels,
+                                                           int outFormat) {
+	int x, y;
+	if (!pixel_of_thread(p.band, x, y)) {
+		return;
+	}
+	const SceneView &sc = p.scene;
+	size_t pix = local_index(p.band, x, y);
+	float albedoA;
+	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, &albedoA);
+	f3 normal = fetch_normal(p.cur, pix);
+	float roughness, metallic;
+	fetch_material(p.cur, pix, roughness, metallic);
+	f3 worldPos = fetch_world_pos(p.cur, pix);
+	f3 cam = mk3(lu.cameraPos[0], lu.cameraPos[1], lu.cameraPos[2]);
+	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+
+	PackedReservoir r = load_reservoir(reservoirs, pix);
+	f3 emission = mk3(0.0f, 0.0f, 0.0f);                                           // :55-60 (out-of-range reads give 0)
+	if (r.lightIndex < 0) {
+		int ti = -1 - r.lightIndex;
+		if (ti < sc.triCount) {
+			float4 e = __ldg(reinterpret_cast<const float4 *>(sc.triLights + ti) + 3);
+			emission = mk3(e.x, e.y, e.z);
+		}
+	} else if (r.lightIndex < sc.pointCount) {
+		float4 e = __ldg(reinterpret_cast<const float4 *>(sc.pointLights + r.lightIndex) + 1);
+		emission = mk3(e.x, e.y, e.z);
+	}
+	f3 n; bool useN; float lum;
+	sample_light_attrs(sc, r, n, useN, lum);
+	f3 c = evaluate_phat_full(sf, albedo, mk3(r.px, r.py, r.pz), n, useN, emission) * r.w; // :61-66
+	if (albedoA > 0.5f) {                                                          // :69-71
+		c = albedo;
+	}
+	if (lu.gamma != 1.0f) {                                                        // :103, P11
+		float e = 1.0f / lu.gamma;
+		c = mk3(powf(c.x, e), powf(c.y, e), powf(c.z, e));
+	}
+	if (outFormat == 0) {
+		reinterpret_cast<float4 *>(outPixels)[pix] = make_float4(c.x, c.y, c.z, 1.0f);
+	} else {
+		uchar4 q;
+		q.x = (unsigned char)rintf(srgb_encode(c.x) * 255.0f);
+		q.y = (unsigned char)rintf(srgb_encode(c.y) * 255.0f);
+		q.z = (unsigned char)rintf(srgb_encode(c.z) * 255.0f);
+		q.w = 255;
+		reinterpret_cast<uchar4 *>(outPixels)[pix] = q;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone testVisibility over a list of segments
+__global__ void __launch_bounds__(kThreads) trace_segments_kernel(SceneView sc, const float *__restrict__ p1, const float *__restrict__ p2,
+                                                                 unsigned long long n, unsigned char *__restrict__ shadowed,
+                                                                 unsigned long long *counters) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned overflow = 0, rays = 0;
+	if (i < n) {
+		f3 a = mk3(p1[i * 3], p1[i * 3 + 1], p1[i * 3 + 2]);
+		f3 b = mk3(p2[i * 3], p2[i * 3 + 1], p2[i * 3 + 2]);
+		shadowed[i] = test_visibility(sc, a, b, overflow) ? 1 : 0;
+		rays = 1;
+	}
+	add_counter(counters, kCounterRays, rays);
+	add_counter(counters, kCounterOverflow, overflow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixture tool: primary-visibility G-buffer (closest front-facing hit), twin of oracle_raycast_gbuffer
+__global__ void __launch_bounds__(kThreads) raycast_gbuffer_kernel(SceneView sc, Band band, RaycastCamera cam,
+                                                                  const int *__restrict__ triMaterial, const uint4 *__restrict__ materialTable,
+                                                                  uchar4 *albedo, short4 *normal, ushort2 *material, float4 *worldPos, float *depth) {
+	int x, y;
+	if (!pixel_of_thread(band, x, y)) {
+		return;
+	}
+	size_t pix = local_index(band, x, y);
+	float ndcx = (((float)x + 0.5f) / (float)band.W) * 2.0f - 1.0f;
+	float ndcy = (((float)y + 0.5f) / (float)band.H) * 2.0f - 1.0f;
+	f3 pos = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
+	f3 fwd = mk3(cam.fwd[0], cam.fwd[1], cam.fwd[2]);
+	f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+	f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+	f3 dir = (fwd + right * (ndcx * cam.sx)) - up * (ndcy * cam.sy);
+	f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+	float best = __int_as_float(0x7f800000), bu = 0.0f, bv = 0.0f;
+	int bestTri = -1;
+	int stack[64];
+	int top = 1;
+	stack[0] = 0;
+	while (top > 0) {
+		const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
+		float4 ch = __ldg(n + 4);
+#pragma unroll
+		for (int side = 0; side < 2; ++side) {
+			float4 bmin = __ldg(n + side * 2), bmax = __ldg(n + side * 2 + 1);
+			int child = __float_as_int(side ? ch.y : ch.x);
+			float t1x = (bmin.x - pos.x) * inv.x, t1y = (bmin.y - pos.y) * inv.y, t1z = (bmin.z - pos.z) * inv.z;
+			float t2x = (bmax.x - pos.x) * inv.x, t2y = (bmax.y - pos.y) * inv.y, t2z = (bmax.z - pos.z) * inv.z;
+			float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+			float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+			if (!(rmin <= best && rmax >= rmin && rmax > 0.0f)) {
+				continue;
+			}
+			if (child >= 0) {
+				if (top < 64) {
+					stack[top++] = child;
+				}
+				continue;
+			}
+			int ti = ~child;
+			const float4 *t = sc.tris + (size_t)ti * 3;
+			float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+			f3 p1 = mk3(a.x, a.y, a.z);
+			f3 e1 = mk3(b.x, b.y, b.z) - p1;
+			f3 e2 = mk3(c.x, c.y, c.z) - p1;
+			f3 nn = cross3(e1, e2);
+			if (!(dot3(nn, dir) < 0.0f)) {
+				continue;
+			}
+			if (__ldg(materialTable + __ldg(triMaterial + ti)).z & 1u) {
+				continue;
+			}
+			f3 pv = cross3(dir, e2);
+			float fdet = 1.0f / dot3(e1, pv);
+			f3 sv = pos - p1;
+			float u_ = fdet * dot3(sv, pv);
+			if (u_ < 0.0f || u_ > 1.0f) {
+				continue;
+			}
+			f3 q = cross3(sv, e1);
+			float v_ = fdet * dot3(dir, q);
+			if (v_ < 0.0f || v_ + u_ > 1.0f) {
+				continue;
+			}
+			float tt = fdet * dot3(e2, q);
+			if (tt > 0.0f && (tt < best || (tt == best && ti < bestTri))) {
+				best = tt;
+				bestTri = ti;
+				bu = u_;
+				bv = v_;
+			}
+		}
+	}
+	if (bestTri < 0) {
+		albedo[pix] = make_uchar4(0, 0, 0, 255);
+		normal[pix] = make_short4(0, 0, 0, 32767);
+		material[pix] = make_ushort2(0, 0);
+		worldPos[pix] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+		depth[pix] = 1.0f;
+		return;
+	}
+	const float4 *t = sc.tris + (size_t)bestTri * 3;
+	float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+	f3 p1 = mk3(a.x, a.y, a.z), p2 = mk3(b.x, b.y, b.z), p3 = mk3(c.x, c.y, c.z);
+	f3 nn = normalize3(cross3(p2 - p1, p3 - p1));
+	f3 hit = (p1 * ((1.0f - bu) - bv) + p2 * bu) + p3 * bv;
+	uint4 mt = __ldg(materialTable + __ldg(triMaterial + bestTri));
+	albedo[pix] = make_uchar4(mt.x & 255u, (mt.x >> 8) & 255u, (mt.x >> 16) & 255u, mt.x >> 24);
+	material[pix] = make_ushort2(mt.y & 65535u, mt.y >> 16);
+	normal[pix] = make_short4((short)rintf(fminf(fmaxf(nn.x, -1.0f), 1.0f) * 32767.0f), (short)rintf(fminf(fmaxf(nn.y, -1.0f), 1.0f) * 32767.0f),
+	                          (short)rintf(fminf(fmaxf(nn.z, -1.0f), 1.0f) * 32767.0f), 32767);
+	worldPos[pix] = make_float4(hit.x, hit.y, hit.z, 1.0f);
+	const float *PV = cam.pv;
+	float cz = ((PV[2] * hit.x + PV[6] * hit.y) + PV[10] * hit.z) + PV[14];
+	float cw = ((PV[3] * hit.x + PV[7] * hit.y) + PV[11] * hit.z) + PV[15];
+	depth[pix] = cz / cw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64-byte reference layout <-> 32-byte packed layout (boundary conversions for download / upload)
+__global__ void unpack_reservoirs_kernel(SceneView sc, const PackedReservoir *__restrict__ in, restir_reservoir *__restrict__ out, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	PackedReservoir r = load_reservoir(in, i);
+	f3 nrm; bool useN; float lum;
+	sample_light_attrs(sc, r, nrm, useN, lum);
+	float4 *o = reinterpret_cast<float4 *>(out + i);
+	o[0] = make_float4(r.px, r.py, r.pz, lum);
+	o[1] = make_float4(nrm.x, nrm.y, nrm.z, useN ? 1.0f : 0.0f);
+	o[2] = make_float4(__int_as_float(r.lightIndex), r.pHat, r.sumWeights, r.w);
+	o[3] = make_float4(__uint_as_float(r.M), 0.0f, 0.0f, 0.0f);
+}
+__global__ void pack_reservoirs_kernel(const restir_reservoir *__restrict__ in, PackedReservoir *__restrict__ out, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	const float4 *s = reinterpret_cast<const float4 *>(in + i);
+	float4 a = s[0], c = s[2], d = s[3];
+	PackedReservoir r;
+	r.px = a.x; r.py = a.y; r.pz = a.z;
+	r.lightIndex = __float_as_int(c.x);
+	r.pHat = c.y; r.sumWeights = c.z; r.w = c.w;
+	r.M = __float_as_uint(d.x);
+	store_reservoir(out, i, r);
+}
+
+// derived light tables (upload time)
+__global__ void derive_point_table_kernel(const restir_point_light *__restrict__ lights, int n, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		out[i] = make_float4(lights[i].pos[0], lights[i].pos[1], lights[i].pos[2], lights[i].color_luminance[3]);
+	}
+}
+__global__ void derive_tri_table_kernel(const restir_tri_light *__restrict__ lights, int n, float4 *__restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		out[i] = make_float4(lights[i].normalArea[0], lights[i].normalArea[1], lights[i].normalArea[2], lights[i].emission_luminance[3]);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+static dim3 tile_grid(const Band &b) {
+	return dim3((unsigned)((b.W + kTileW - 1) / kTileW), (unsigned)((b.rowEnd - b.rowBegin + kTileH - 1) / kTileH), 1);
+}
+
+void launch_restir_omni(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, cudaStream_t s) {
+	restir_omni_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out, prev);
+}
+void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s) {
+	spatial_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter);
+}
+void launch_unbiased_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, cudaStream_t s) {
+	unbiased_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors);
+}
+void launch_lighting(const PassParams &p, const restir_lighting_uniforms &lu, const PackedReservoir *res, void *out, int fmt, cudaStream_t s) {
+	lighting_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, lu, res, out, fmt);
+}
+void launch_trace_segments(const SceneView &sc, const float *p1, const float *p2, unsigned long long n, unsigned char *shadowed,
+                           unsigned long long *counters, cudaStream_t s) {
+	if (n == 0) {
+		return;
+	}
+	unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+	trace_segments_kernel<<<blocks, kThreads, 0, s>>>(sc, p1, p2, n, shadowed, counters);
+}
+void launch_raycast_gbuffer(const SceneView &sc, const Band &band, const RaycastCamera &cam, const int *triMaterial, const uint4 *materialTable,
+                            void *albedo, void *normal, void *material, void *worldPos, void *depth, cudaStream_t s) {
+	raycast_gbuffer_kernel<<<tile_grid(band), kThreads, 0, s>>>(sc, band, cam, triMaterial, materialTable, (uchar4 *)albedo, (short4 *)normal,
+	                                                           (ushort2 *)material, (float4 *)worldPos, (float *)depth);
+}
+void launch_unpack_reservoirs(const SceneView &sc, const PackedReservoir *in, restir_reservoir *out, size_t n, cudaStream_t s) {
+	if (n) unpack_reservoirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc, in, out, n);
+}
+void launch_pack_reservoirs(const restir_reservoir *in, PackedReservoir *out, size_t n, cudaStream_t s) {
+	if (n) pack_reservoirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+}
+void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
+                                cudaStream_t s) {
+	if (np) derive_point_table_kernel<<<(np + 255) / 256, 256, 0, s>>>(pl, np, pointOut);
+	if (nt) derive_tri_table_kernel<<<(nt + 255) / 256, 256, 0, s>>>(tl, nt, triOut);
+}
+
+} // namespace restir

@@ -1,0 +1,246 @@
+"""Shared machinery of the parity tests: builds a test case (scene, cameras, G-buffers, uniforms), runs the
+same frame sequence through the CPU oracle and through the CUDA path (via the C ABI), and compares.
+
+Parity criteria (made concrete):
+  * shadow-ray visibility bits: identical for every ray;
+  * reservoir integer fields (lightIndex, M): identical;
+  * reservoir float fields (position, pHat, sumWeights, w, and the normal / emissionLum the 64-byte
+    layout carries): BIT-identical (the oracle and the kernels implement the same arithmetic policy);
+    NaN equals NaN;
+  * final linear RGB: max relative error <= 1e-3 (abs floor 1e-6) and PSNR >= 60 dB — it is bit-exact in
+    practice when gamma == 1, the tolerance covers powf when gamma != 1.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import __graft_entry__ as graft  # noqa: E402
+
+pkg = graft.load_package()
+capi, fixtures = pkg.capi, pkg.fixtures
+
+RGB_REL_TOL = 1e-3
+RGB_ABS_FLOOR = 1e-6
+PSNR_MIN_DB = 60.0
+
+
+def oracle():
+    return graft.load_oracle()
+
+
+def oracle_scene(scene):
+    po = oracle()
+    return po.Scene(scene.nodes, scene.triangles, scene.point_blob, scene.tri_blob, scene.alias_blob)
+
+
+class Case:
+    """A frame sequence: per frame a camera; G-buffers rendered by the oracle's fixture generator."""
+
+    def __init__(self, scene, width, height, cameras, candidates=32, unbiased=False, spatial_iterations=1, neighbors=4,
+                 unbiased_neighbors=3, flags=3, multiplier=20, radius=30.0, pos_thr=0.1, nor_thr=25.0, gamma=1.0):
+        self.scene, self.w, self.h = scene, width, height
+        self.cameras = cameras
+        self.candidates, self.unbiased, self.iterations = candidates, unbiased, spatial_iterations
+        self.neighbors, self.unbiased_neighbors = neighbors, unbiased_neighbors
+        self.flags, self.multiplier, self.radius = flags, multiplier, radius
+        self.pos_thr, self.nor_thr, self.gamma = pos_thr, nor_thr, gamma
+        self._gbuffers = None
+
+    def gbuffers(self):
+        if self._gbuffers is None:
+            po = oracle()
+            sc = oracle_scene(self.scene)
+            table = self.scene.material_table()
+            self._gbuffers = [po.raycast_gbuffer(sc, self.scene.tri_material, table, cam, self.w, self.h) for cam in self.cameras]
+        return self._gbuffers
+
+    def uniforms(self, frame_index):
+        """frame_index 0 is the reference's first rendered frame (frame == 1, app.cpp:776)."""
+        po = oracle()
+        cam = self.cameras[frame_index]
+        prev_cam = self.cameras[max(frame_index - 1, 0)]
+        u = capi.make_uniforms(
+            prevFrameProjectionViewMatrix=po.camera_matrix(prev_cam),
+            cameraPos=(cam.position[0], cam.position[1], cam.position[2], 1.0),
+            screenSize=(self.w, self.h), frame=frame_index + 1, initialLightSampleCount=self.candidates,
+            temporalSampleCountMultiplier=self.multiplier, spatialPosThreshold=self.pos_thr,
+            spatialNormalThreshold=self.nor_thr, spatialNeighbors=self.neighbors, spatialRadius=self.radius, flags=self.flags)
+        lu = capi.make_lighting_uniforms(
+            prevFrameProjectionViewMatrix=po.camera_matrix(prev_cam),
+            cameraPos=(cam.position[0], cam.position[1], cam.position[2], 1.0), bufferSize=(self.w, self.h), debugMode=0,
+            gamma=self.gamma)
+        return u, lu
+
+
+def moving_cameras(n, position, look_at, aspect, step=(0.05, 0.0, 0.0), fov_y=None):
+    po = oracle()
+    cams = []
+    for i in range(n):
+        p = tuple(np.float32(position[k]) + np.float32(i) * np.float32(step[k]) for k in range(3))
+        cams.append(po.make_camera(position=p, look_at=look_at, aspect=aspect, fov_y=fov_y))
+    return cams
+
+
+def to_capi_camera(cam):
+    return capi.make_camera(position=tuple(cam.position), look_at=tuple(cam.lookAt), up=tuple(cam.worldUp), z_near=cam.zNear,
+                            z_far=cam.zFar, fov_y=cam.fovYRadians, aspect=cam.aspectRatio)
+
+
+# ---- running both sides -----------------------------------------------------------------------------
+
+def run_oracle(case, rows=None):
+    """Returns per frame: dict(reservoirs=final (N,) RESERVOIR_DTYPE, initial=after restirOmni, rgba, rays)."""
+    po = oracle()
+    sc = oracle_scene(case.scene)
+    gb = case.gbuffers()
+    n = case.w * case.h
+    frame_bufs = [np.zeros(n, po.RESERVOIR_DTYPE), np.zeros(n, po.RESERVOIR_DTYPE)]  # app.h:264-284 zero-filled
+    out = []
+    for f in range(len(case.cameras)):
+        i, p = f & 1, (f & 1) ^ 1
+        u, lu = case.uniforms(f)
+        u = u.astype(po.UNIFORMS_DTYPE)
+        lu = lu.astype(po.LIGHTING_UNIFORMS_DTYPE)
+        cur = gb[f]
+        prev = gb[f - 1] if f > 0 else None
+        rays = 0
+        initial, r = po.restir_pass(sc, u, cur, prev, frame_bufs[p], rows)
+        rays += r
+        if case.unbiased:  # app.h:298-314
+            final, r = po.unbiased_pass(sc, u, cur, initial, case.unbiased_neighbors, rows)
+            rays += r
+            frame_bufs[i] = final
+        else:              # app.h:316-332: the previous frame's buffer is the scratch of the spatial passes
+            frame_bufs[i] = initial
+            for j in range(case.iterations):
+                frame_bufs[p] = po.spatial_pass(u, cur, frame_bufs[i], 2 * j, rows)
+                frame_bufs[i] = po.spatial_pass(u, cur, frame_bufs[p], 2 * j + 1, rows)
+        rgba = po.lighting_pass(sc, lu, cur, frame_bufs[i], rows)
+        out.append(dict(reservoirs=frame_bufs[i].copy(), initial=initial, rgba=rgba, rays=rays))
+    return out
+
+
+def make_context(scene, device=0):
+    ctx = capi.RestirContext(device)
+    ctx.upload_bvh(scene.nodes, scene.triangles)
+    ctx.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
+    return ctx
+
+
+def run_cuda(case, ctx=None):
+    import torch
+
+    own = ctx is None
+    if own:
+        ctx = make_context(case.scene)
+    ctx.resize(case.w, case.h)
+    ctx.set_unbiased_neighbors(case.unbiased_neighbors)
+    gb = case.gbuffers()
+    out_img = torch.zeros((case.h, case.w, 4), dtype=torch.float32, device="cuda")
+    out = []
+    ctx.counters(reset=True)
+    for f in range(len(case.cameras)):
+        i = f & 1
+        u, lu = case.uniforms(f)
+        ctx.upload_gbuffer(i, *gb[f].planes())
+        ctx.set_uniforms(u)
+        ctx.set_lighting_uniforms(lu)
+        # same order as restir_frame, split so the initial reservoirs can be inspected
+        if case.unbiased:
+            ctx.pass_restir(i, capi.RESTIR_BUF_TEMP, i ^ 1)
+            initial = ctx.download_reservoirs(capi.RESTIR_BUF_TEMP)
+            ctx.pass_unbiased(i, capi.RESTIR_BUF_TEMP, i)
+        else:
+            ctx.pass_restir(i, i, i ^ 1)
+            initial = ctx.download_reservoirs(i)
+            for j in range(case.iterations):
+                ctx.pass_spatial(i, i, i ^ 1, 2 * j)
+                ctx.pass_spatial(i, i ^ 1, i, 2 * j + 1)
+        ctx.pass_lighting(i, i, out_img, capi.RESTIR_OUT_RGBA32F)
+        ctx.synchronize()
+        c = ctx.counters(reset=True)
+        out.append(dict(reservoirs=ctx.download_reservoirs(i), initial=initial, rgba=out_img.cpu().numpy().copy(), rays=c["shadow_rays"],
+                        counters=c))
+    if own:
+        ctx.close()
+    return out
+
+
+# ---- comparison -------------------------------------------------------------------------------------
+
+FLOAT_FIELDS = ("position_emissionLum", "normal", "pHat", "sumWeights", "w")
+INT_FIELDS = ("lightIndex", "M")
+
+
+def bits_equal(a, b):
+    """Bitwise equality of float arrays, except that any NaN equals any NaN."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    same = a.view(np.uint32) == b.view(np.uint32)
+    return same | (np.isnan(a) & np.isnan(b))
+
+
+def compare_reservoirs(got, want, label=""):
+    """Returns the number of mismatching reservoirs; prints the first few."""
+    bad = np.zeros(got.shape[0], bool)
+    for f in INT_FIELDS:
+        bad |= got[f] != want[f]
+    for f in FLOAT_FIELDS:
+        eq = bits_equal(got[f], want[f])
+        bad |= ~(eq.reshape(got.shape[0], -1).all(axis=1))
+    n = int(bad.sum())
+    if n:
+        idx = np.flatnonzero(bad)[:5]
+        for k in idx:
+            print(f"[{label}] reservoir {k} differs:\n  cuda   {got[k]}\n  oracle {want[k]}")
+    return n
+
+
+def compare_rgb(got, want):
+    """(max relative error over compared pixels, PSNR in dB).  Non-finite pixels must match as such."""
+    g = got[..., :3].astype(np.float64)
+    w = want[..., :3].astype(np.float64)
+    finite = np.isfinite(g) & np.isfinite(w)
+    assert np.array_equal(np.isfinite(g), np.isfinite(w)), "non-finite pixels differ"
+    diff = np.abs(np.where(finite, g - w, 0.0))
+    rel = diff / np.maximum(np.abs(np.where(finite, w, 0.0)), RGB_ABS_FLOOR)
+    rel = np.where(diff <= RGB_ABS_FLOOR, 0.0, rel)
+    mse = float(np.mean(diff ** 2))
+    peak = max(float(np.max(np.abs(np.where(finite, w, 0.0)))), 1e-12)
+    psnr = float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+    return float(rel.max()), psnr
+
+
+def assert_frames_match(cuda_frames, oracle_frames, label=""):
+    for f, (c, o) in enumerate(zip(cuda_frames, oracle_frames)):
+        assert c["counters"]["stack_overflows"] == 0, f"{label} frame {f}: traversal stack overflow"
+        assert c["counters"]["halo_misses"] == 0, f"{label} frame {f}: halo miss"
+        n_init = compare_reservoirs(c["initial"], o["initial"], f"{label} frame {f} initial")
+        assert n_init == 0, f"{label} frame {f}: {n_init} reservoirs differ after restirOmni"
+        n_fin = compare_reservoirs(c["reservoirs"], o["reservoirs"], f"{label} frame {f} final")
+        assert n_fin == 0, f"{label} frame {f}: {n_fin} final reservoirs differ"
+        assert c["rays"] == o["rays"], f"{label} frame {f}: ray count {c['rays']} != {o['rays']}"
+        rel, psnr = compare_rgb(c["rgba"], o["rgba"])
+        assert rel <= RGB_REL_TOL and psnr >= PSNR_MIN_DB, f"{label} frame {f}: rgb rel {rel} psnr {psnr}"
+
+
+# ---- smoke (called by __graft_entry__.smoke on the GPU box) -------------------------------------------
+
+def smoke_case():
+    scene = fixtures.make_procedural(seed=3, grid=8, boxes=12, lights="point", n_point_lights=12)
+    cams = moving_cameras(2, (3.0, 3.5, 4.2), (0.0, -1.0, 0.0), 96 / 64)
+    return Case(scene, 96, 64, cams, candidates=8, unbiased=True)
+
+
+def run_smoke():
+    case = smoke_case()
+    got = run_cuda(case)
+    want = run_oracle(case)
+    assert_frames_match(got, want, "smoke")
+    print(f"smoke ok: {len(got)} unbiased frames of {case.w}x{case.h}, {got[-1]['rays']} shadow rays in the last frame, "
+          f"{got[-1]['counters']['kernel_launches']} kernel launches, bit-identical to the oracle")
