@@ -1,0 +1,122 @@
+"""Row-band data parallelism for the ReSTIR passes: one process per GPU, contiguous bands of rows, scene
+replicated, nearest-neighbour halo exchange of reservoir rows.
+
+The reference is single-GPU; this is the one subsystem the B200 build adds.  Pixels are independent except
+for (i) the spatial / unbiased neighbour gathers within spatialRadius (+1 for round()) rows and (ii) the
+temporal gather at the reprojected pixel, so the only communication is: before every pass that reads
+another pixel's reservoir, each rank sends the `halo` rows adjacent to each band edge of that pass's INPUT
+buffer to the rank on the other side of the edge.  RNG streams are keyed on global pixel coordinates, so
+the result is bit-identical to a single-GPU frame.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing for the point-to-point copies; there
+is no collective on the data path.
+"""
+import math
+
+
+def band_rows(height, world, rank):
+    """Contiguous, near-equal row bands: rank r owns [begin, end)."""
+    base, extra = divmod(height, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def halo_rows_for(spatial_radius):
+    """Rows a neighbour gather can reach: floor/round of radius*sin() is at most ceil(radius), +1 for round-to-even slack."""
+    return int(math.ceil(spatial_radius)) + 1
+
+
+def halo_plan(height, world, rank, halo):
+    """Messages of one exchange for `rank`: list of (peer, send_rows, recv_rows) with rows as global [lo, hi).
+
+    A rank sends the first/last `halo` rows it OWNS and receives the `halo` rows just outside its band, each
+    clipped to the peer's band (bands thinner than the halo would need a second hop: rejected).
+    """
+    begin, end = band_rows(height, world, rank)
+    plan = []
+    for peer in (rank - 1, rank + 1):
+        if peer < 0 or peer >= world:
+            continue
+        pb, pe = band_rows(height, world, peer)
+        if pe - pb < halo or end - begin < halo:
+            raise ValueError(f"band of {min(pe - pb, end - begin)} rows is thinner than the {halo}-row halo")
+        if peer < rank:
+            plan.append((peer, (begin, begin + halo), (begin - halo, begin)))
+        else:
+            plan.append((peer, (end - halo, end), (end, end + halo)))
+    return plan
+
+
+def exchange_halo(rows_tensor, alloc_begin, plan, dist, group=None):
+    """Run one halo exchange on `rows_tensor` (first dim = rows [alloc_begin, ...), any trailing dims).
+
+    Uses batched isend/irecv; works for CPU tensors over gloo and CUDA tensors over NCCL.  Returns after the
+    transfers are complete with respect to the caller's stream (NCCL) / the host (gloo).
+    """
+    ops, recvs = [], []
+    for peer, (s0, s1), (r0, r1) in plan:
+        send = rows_tensor[s0 - alloc_begin: s1 - alloc_begin].contiguous()
+        recv = rows_tensor[r0 - alloc_begin: r1 - alloc_begin]
+        tmp = recv if recv.is_contiguous() else recv.contiguous()
+        ops.append(dist.P2POp(dist.isend, send, peer, group))
+        ops.append(dist.P2POp(dist.irecv, tmp, peer, group))
+        recvs.append((recv, tmp))
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for recv, tmp in recvs:
+        if tmp is not recv:
+            recv.copy_(tmp)
+
+
+class _DeviceBytes:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def reservoir_rows_tensor(ctx, buffer, torch):
+    """The context's packed reservoir buffer `buffer` as a (rows, pitch_bytes) uint8 CUDA tensor (no copy)."""
+    ptr, pitch = ctx.reservoir_device_ptr(buffer)
+    rows = ctx.alloc_rows()
+    t = torch.as_tensor(_DeviceBytes(ptr, rows * pitch), device=f"cuda:{ctx.device}")
+    return t.view(rows, pitch)
+
+
+class BandRenderer:
+    """Drives one band context through App's pass order (src/app.h:212-262) with the halo exchanges between
+    the passes.  With world == 1 it degenerates to restir_frame + lighting."""
+
+    def __init__(self, ctx, height, world, rank, halo, torch, dist=None, group=None):
+        self.ctx, self.world, self.rank, self.torch, self.dist, self.group = ctx, world, rank, torch, dist, group
+        self.height, self.halo = height, halo
+        self.plan = halo_plan(height, world, rank, halo) if world > 1 else []
+        self.alloc_begin = ctx.band()[2]
+        self._views = {}
+
+    def _exchange(self, buffer):
+        if not self.plan:
+            return
+        if buffer not in self._views:
+            self._views[buffer] = reservoir_rows_tensor(self.ctx, buffer, self.torch)
+        exchange_halo(self._views[buffer], self.alloc_begin, self.plan, self.dist, self.group)
+
+    def frame(self, i, unbiased, spatial_iterations=1):
+        """One frame's resampling passes.  Leaves the final reservoirs (halo included) in FRAME[i]."""
+        from .capi import RESTIR_BUF_TEMP
+
+        ctx, p = self.ctx, i ^ 1
+        if unbiased:
+            ctx.pass_restir(i, RESTIR_BUF_TEMP, p)
+            self._exchange(RESTIR_BUF_TEMP)
+            ctx.pass_unbiased(i, RESTIR_BUF_TEMP, i)
+        else:
+            ctx.pass_restir(i, i, p)
+            for j in range(spatial_iterations):
+                self._exchange(i)
+                ctx.pass_spatial(i, i, p, 2 * j)
+                self._exchange(p)
+                ctx.pass_spatial(i, p, i, 2 * j + 1)
+        self._exchange(i)   # next frame's temporal reprojection reads FRAME[i] within the halo
