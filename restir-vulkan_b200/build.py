@@ -6,9 +6,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_capi.cu", "host/scene_build.cpp"]
+DRIVER_SOURCES = ["host/restir_driver.cpp", "host/passes.hpp"]
 HEADERS = ["csrc/restir_math.cuh", "csrc/restir_device.cuh", "csrc/restir_kernels.h", "../include/restir_b200.h",
            "../include/restir_layouts.h", "host/passes.hpp"]
 OUT = os.path.join(HERE, "librestir_b200.so")
+DRIVER = os.path.join(HERE, "restir_driver")
 
 # -fmad=false: no FMA contraction (arithmetic policy P1); division and sqrt stay IEEE (-prec-div/-prec-sqrt
 # default true), denormals are kept (-ftz default false).
@@ -23,10 +25,10 @@ def nvcc():
 
 
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(DRIVER):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.exists(os.path.join(HERE, s)) and os.path.getmtime(os.path.join(HERE, s)) > t for s in SOURCES + HEADERS + ["build.py"])
+    return any(os.path.exists(os.path.join(HERE, s)) and os.path.getmtime(os.path.join(HERE, s)) > t for s in SOURCES + HEADERS + DRIVER_SOURCES + ["build.py"])
 
 
 def build(force=False, verbose=False):
@@ -37,10 +39,11 @@ def build(force=False, verbose=False):
     if os.path.exists(ccbin):
         cmd[1:1] = ["-ccbin", ccbin]
     subprocess.check_call(cmd, cwd=HERE)
-    # the C++ mirror of the reference's pass classes is header-only: make sure it compiles against the ABI
-    example = os.path.join(HERE, "host", "passes_example.cpp")
-    if os.path.exists(example):
-        subprocess.check_call([ccbin if os.path.exists(ccbin) else "g++", "-std=c++17", "-fsyntax-only", "-Wall", example], cwd=HERE)
+    # the C++ host driver (mirror of the reference's pass classes + App main loop) links against the C ABI
+    drv = [nvcc()] + (["-ccbin", ccbin] if os.path.exists(ccbin) else []) + [
+        "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-Wall,-ffp-contract=off", "-o", DRIVER, os.path.join(HERE, "host", "restir_driver.cpp"),
+        "-L" + HERE, "-lrestir_b200", "-Xlinker", "-rpath,$ORIGIN"]
+    subprocess.check_call(drv, cwd=HERE)
     return OUT
 
 

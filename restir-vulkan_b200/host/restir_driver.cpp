@@ -1,0 +1,217 @@
+// restir_driver — C++ host program that drives the sm_100a kernels through the C ABI the way the
+// reference's App drives its passes: load scene data, build tree / lights / alias table, then per frame
+// patch the uniforms (src/app.cpp:775-826), record the ReSTIR passes (src/app.h:212-262) and the
+// lighting pass (src/app.cpp:861-862), flipping the G-buffer index (src/app.cpp:900).
+//
+//   restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors]
+//
+// <scene_dir> holds triangles.bin (n x 48), tri_material.i32, materials.f32 (m x 16), dims.f32 and
+// material_table.u32 (m x 4) — what scenes/_baked/<name>/ or restir-vulkan_b200/fixtures.py write.
+// Prints one JSON line: FNV-1a checksums of the final reservoirs (64-byte layout) and of the RGBA8 image,
+// ms per frame and ray count — tests compare the checksums with the same sequence driven from Python.
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "passes.hpp"
+
+namespace {
+
+template <typename T> std::vector<T> readFile(const std::string &path, bool required = true) {
+	std::ifstream f(path, std::ios::binary | std::ios::ate);
+	if (!f) {
+		if (required) {
+			std::cerr << "restir_driver: cannot read " << path << "\n";
+			std::exit(2);
+		}
+		return {};
+	}
+	std::streamsize bytes = f.tellg();
+	f.seekg(0);
+	std::vector<T> v((size_t)bytes / sizeof(T));
+	f.read(reinterpret_cast<char *>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+	return v;
+}
+
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+	const unsigned char *p = static_cast<const unsigned char *>(data);
+	for (size_t i = 0; i < bytes; ++i) {
+		h = (h ^ p[i]) * 1099511628211ull;
+	}
+	return h;
+}
+
+void cuda(cudaError_t e, const char *what) {
+	if (e != cudaSuccess) {
+		std::cerr << "restir_driver: " << what << ": " << cudaGetErrorString(e) << "\n";
+		std::exit(3);
+	}
+}
+
+struct DeviceGBuffer {
+	void *plane[5] = {};
+	void allocate(size_t pixels) {
+		const size_t bpp[5] = {4, 8, 4, 16, 4};
+		for (int k = 0; k < 5; ++k) {
+			cuda(cudaMalloc(&plane[k], pixels * bpp[k]), "cudaMalloc G-buffer plane");
+		}
+	}
+	restir_gbuffer_planes planes() const { return restir_gbuffer_planes{plane[0], plane[1], plane[2], plane[3], plane[4]}; }
+};
+
+} // namespace
+
+int main(int argc, char **argv) {
+	if (argc < 6) {
+		std::cerr << "usage: restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors]\n";
+		return 64;
+	}
+	const std::string dir = argv[1];
+	const uint32_t width = (uint32_t)std::atoi(argv[2]), height = (uint32_t)std::atoi(argv[3]);
+	const int frames = std::atoi(argv[4]);
+	const bool unbiased = std::atoi(argv[5]) != 0;
+	const uint32_t neighbors = argc > 6 ? (uint32_t)std::atoi(argv[6]) : (unbiased ? 3u : 4u);
+
+	try {
+		// ---- scene (App::App: loadScene, SceneBuffers::create, AabbTree::build; src/app.cpp:285-360) ----
+		auto triangles = readFile<restir_triangle>(dir + "/triangles.bin");
+		auto triMaterial = readFile<int32_t>(dir + "/tri_material.i32");
+		auto materials = readFile<float>(dir + "/materials.f32");
+		auto dims = readFile<float>(dir + "/dims.f32");
+		auto materialTable = readFile<uint32_t>(dir + "/material_table.u32");
+		auto filePointLights = readFile<unsigned char>(dir + "/gltf_point_lights.bin", false);
+		const uint32_t nMaterials = (uint32_t)(materials.size() / 16);
+		std::vector<float> emissive(nMaterials * 3);
+		for (uint32_t m = 0; m < nMaterials; ++m) {
+			std::memcpy(&emissive[m * 3], &materials[m * 16 + 8], 12);
+		}
+		std::vector<restir_point_light> point;
+		if (filePointLights.size() > RESTIR_BLOB_HEADER_BYTES) {
+			point.resize((filePointLights.size() - RESTIR_BLOB_HEADER_BYTES) / sizeof(restir_point_light));
+			std::memcpy(point.data(), filePointLights.data() + RESTIR_BLOB_HEADER_BYTES, point.size() * sizeof(restir_point_light));
+		}
+		std::vector<restir_tri_light> tri(triangles.size());
+		int64_t nTri = restir_collect_triangle_lights(triangles.data(), triMaterial.data(), (uint32_t)triangles.size(), emissive.data(),
+		                                              nMaterials, tri.data());
+		if (nTri < 0) {
+			throw restir::Error((int)nTri, "restir_collect_triangle_lights failed");
+		}
+		tri.resize((size_t)nTri);
+
+		restir::Device device(0);
+		restir::AabbTree tree = restir::AabbTree::build(triangles);
+		tree.upload(device);
+		restir::SceneLights lights = restir::SceneLights::create(point, tri, dims.data(), dims.data() + 3);
+		lights.upload(device);
+		device.check(restir_resize(device.get(), width, height)); // App::_updateRestirBuffers
+		device.check(restir_set_unbiased_neighbors(device.get(), unbiased ? neighbors : 3));
+
+		// ---- inputs: two G-buffers from two camera positions (fixture tool) ----------------------------
+		const size_t pixels = (size_t)width * height;
+		int32_t *dTriMaterial = nullptr;
+		uint32_t *dMaterialTable = nullptr;
+		cuda(cudaMalloc(&dTriMaterial, triMaterial.size() * 4), "cudaMalloc");
+		cuda(cudaMalloc(&dMaterialTable, materialTable.size() * 4), "cudaMalloc");
+		cuda(cudaMemcpy(dTriMaterial, triMaterial.data(), triMaterial.size() * 4, cudaMemcpyHostToDevice), "memcpy");
+		cuda(cudaMemcpy(dMaterialTable, materialTable.data(), materialTable.size() * 4, cudaMemcpyHostToDevice), "memcpy");
+		restir_camera cams[2];
+		for (int k = 0; k < 2; ++k) { // src/camera.h:7-13 defaults, nudged along +x for the second view
+			restir_camera c{};
+			auto cam = readFile<float>(dir + "/camera.f32", false); // optional: position xyz, lookAt xyz
+			float pos[3] = {3.0f, 4.0f, 5.0f}, look[3] = {0.0f, 0.0f, 0.0f};
+			if (cam.size() >= 6) {
+				std::memcpy(pos, cam.data(), 12);
+				std::memcpy(look, cam.data() + 3, 12);
+			}
+			c.position[0] = pos[0] + 0.05f * (float)k;
+			c.position[1] = pos[1];
+			c.position[2] = pos[2];
+			std::memcpy(c.lookAt, look, 12);
+			c.worldUp[1] = 1.0f;
+			c.zNear = 0.01f;
+			c.zFar = 1000.0f;
+			c.fovYRadians = 0.5f * 3.14159265358979f;
+			c.aspectRatio = (float)width / (float)height;
+			cams[k] = c;
+		}
+		DeviceGBuffer gbuf[2];
+		for (int k = 0; k < 2; ++k) {
+			gbuf[k].allocate(pixels);
+			device.check(restir_tools_raycast_gbuffer(device.get(), &cams[k], dTriMaterial, dMaterialTable, gbuf[k].plane[0], gbuf[k].plane[1],
+			                                          gbuf[k].plane[2], gbuf[k].plane[3], gbuf[k].plane[4]));
+			restir_gbuffer_planes p = gbuf[k].planes();
+			device.check(restir_bind_gbuffer(device.get(), k, RESTIR_GBUFFER_NVIDIA_DEFAULT, &p));
+		}
+		void *image = nullptr;
+		cuda(cudaMalloc(&image, pixels * 4), "cudaMalloc image");
+
+		// ---- main loop (App::mainLoop, src/app.cpp:690-902) ---------------------------------------------
+		restir_uniforms u{};
+		u.screenSize[0] = width;
+		u.screenSize[1] = height;
+		u.frame = 0;                          // app.cpp:421
+		u.spatialPosThreshold = 0.1f;         // app.h:150
+		u.spatialNormalThreshold = 25.0f;     // app.h:151
+		u.flags = RESTIR_VISIBILITY_REUSE_FLAG | RESTIR_TEMPORAL_REUSE_FLAG;
+		u.spatialNeighbors = unbiased ? 4u : neighbors; // app.cpp:430
+		u.spatialRadius = 30.0f;              // app.cpp:431
+		restir_lighting_uniforms lu{};
+		lu.bufferSize[0] = width;
+		lu.bufferSize[1] = height;
+		lu.debugMode = 0;
+		lu.gamma = 1.0f;
+
+		restir::FrameRecorder recorder;
+		recorder.unbiasedSpatialReuse = unbiased;
+		restir::LightingPass lighting;
+		lighting.outImage = image;
+		int currentGBufferFrame = 0;
+		restir_counters counters{};
+		device.check(restir_get_counters(device.get(), &counters, 1));
+		device.waitIdle();
+		auto t0 = std::chrono::steady_clock::now();
+		for (int f = 0; f < frames; ++f) {
+			const restir_camera &cam = cams[f & 1], &prevCam = cams[f > 0 ? ((f & 1) ^ 1) : 0];
+			++u.frame;                                   // app.cpp:776
+			u.initialLightSampleCount = 1u << 5;         // app.cpp:777, app.h:165
+			restir_camera_matrix(&prevCam, u.prevFrameProjectionViewMatrix); // app.cpp:778
+			u.temporalSampleCountMultiplier = 20;        // app.cpp:779, app.h:168
+			std::memcpy(u.cameraPos, cam.position, 12);  // app.cpp:795
+			u.cameraPos[3] = 1.0f;
+			std::memcpy(lu.cameraPos, u.cameraPos, 16);
+			std::memcpy(lu.prevFrameProjectionViewMatrix, u.prevFrameProjectionViewMatrix, 64);
+			device.check(restir_set_uniforms(device.get(), &u));
+			device.check(restir_set_lighting_uniforms(device.get(), &lu));
+			recorder.record(device, currentGBufferFrame); // app.cpp:828-832
+			lighting.gBuffer = currentGBufferFrame;
+			lighting.reservoirBuffer = currentGBufferFrame;
+			lighting.issueCommands(device);               // app.cpp:861-862
+			currentGBufferFrame ^= 1;                     // app.cpp:900
+		}
+		device.waitIdle();
+		double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		device.check(restir_get_counters(device.get(), &counters, 0));
+
+		std::vector<restir_reservoir> reservoirs(pixels);
+		device.check(restir_download_reservoirs(device.get(), currentGBufferFrame ^ 1, reservoirs.data()));
+		std::vector<unsigned char> rgba(pixels * 4);
+		cuda(cudaMemcpy(rgba.data(), image, rgba.size(), cudaMemcpyDeviceToHost), "memcpy image");
+		std::printf("{\"frames\": %d, \"ms_per_frame_wall\": %.4f, \"shadow_rays\": %llu, \"kernel_launches\": %llu, "
+		            "\"reservoir_fnv1a\": \"%016llx\", \"image_fnv1a\": \"%016llx\"}\n",
+		            frames, ms / frames, (unsigned long long)counters.shadow_rays, (unsigned long long)counters.kernel_launches,
+		            (unsigned long long)fnv1a(reservoirs.data(), reservoirs.size() * sizeof(restir_reservoir)),
+		            (unsigned long long)fnv1a(rgba.data(), rgba.size()));
+	} catch (const restir::Error &e) {
+		std::cerr << "restir_driver: error " << e.code << ": " << e.what() << "\n";
+		return 1;
+	}
+	return 0;
+}

@@ -1,0 +1,82 @@
+"""Host-side logic of the row-band multi-GPU path, on CPU: band partition, halo plan, and a
+real world_size-2 exchange over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import parity_harness as ph
+
+bands = __import__("restir_vulkan_b200.bands", fromlist=["bands"])
+
+
+def test_band_rows_partition_the_screen():
+    for h, world in [(1080, 1), (1080, 2), (1080, 8), (4320, 8), (1081, 4), (7, 3)]:
+        rows = [bands.band_rows(h, world, r) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == h
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in rows]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_halo_covers_the_neighbour_reach():
+    # floor(cos*r)/round(cos*r) with r <= spatialRadius = 30 reaches at most 30 rows; +1 slack
+    assert bands.halo_rows_for(30.0) == 31
+    assert bands.halo_rows_for(30.5) == 32
+
+
+def test_halo_plan_is_symmetric():
+    h, world, halo = 4320, 8, 31
+    plans = [bands.halo_plan(h, world, r, halo) for r in range(world)]
+    assert len(plans[0]) == 1 and len(plans[-1]) == 1 and all(len(p) == 2 for p in plans[1:-1])
+    for r, plan in enumerate(plans):
+        b, e = bands.band_rows(h, world, r)
+        for peer, send, recv in plan:
+            assert b <= send[0] < send[1] <= e                      # sends only rows it owns
+            assert recv[1] <= b or recv[0] >= e                     # receives only rows outside its band
+            back = [x for x in plans[peer] if x[0] == r][0]
+            assert back[1] == recv and back[2] == send              # the peer's message mirrors it
+    with pytest.raises(ValueError):
+        bands.halo_plan(100, 8, 3, 31)                              # bands thinner than the halo
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, h, w, halo, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = bands.band_rows(h, world, rank)
+    a0, a1 = max(0, b - halo), min(h, e + halo)
+    # every row carries its global row index and the owner's rank; halos start out as garbage
+    buf = torch.full((a1 - a0, w), -1.0)
+    for y in range(b, e):
+        buf[y - a0] = y * 1000.0 + rank
+    plan = bands.halo_plan(h, world, rank, halo)
+    bands.exchange_halo(buf, a0, plan, dist)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), buf.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_halo_over_gloo(world, tmp_path):
+    h, w, halo = 40 * world, 8, 5
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, h, w, halo, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        b, e = bands.band_rows(h, world, rank)
+        a0, a1 = max(0, b - halo), min(h, e + halo)
+        got = np.load(tmp_path / f"rank{rank}.npy")
+        for y in range(a0, a1):
+            owner = [r for r in range(world) if bands.band_rows(h, world, r)[0] <= y < bands.band_rows(h, world, r)[1]][0]
+            assert (got[y - a0] == y * 1000.0 + owner).all(), (rank, y)
