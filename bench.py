@@ -50,7 +50,7 @@ HALO = 31  # ceil(spatialRadius = 30) + 1
 
 # algorithmic bytes per pixel with the layout actually resident in HBM (32-byte packed reservoirs,
 # 36-byte G-buffer) — DESIGN.md §Kernels, SURVEY.md §8d
-BYTES_PER_PIXEL = {"restir": 124, "spatial": 100, "unbiased": 100, "lighting_rgba8": 68, "lighting_rgba32f": 80}
+BYTES_PER_PIXEL = {"spatial": 100, "lighting_rgba8": 68, "lighting_rgba32f": 80}
 
 
 def load_scene(fixtures, cfg):
@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--config", default="sponza_1080p_unbiased5", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--reference-rows", type=int, default=48, help="rows per step of the --impl reference arm")
+    ap.add_argument("--traversal", default="auto", choices=["auto", "reference-order"],
+                    help="reference-order: walk the 80-byte nodes in the shader's own order (A/B against the 4-wide re-layout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -274,6 +276,8 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)                          # NCCL p2p ops order against the current stream
     ctx = capi.RestirContext(local_rank, stream.cuda_stream)
+    if args.traversal == "reference-order":
+        ctx.set_traversal(capi.RESTIR_TRAVERSAL_REFERENCE_ORDER)
     ctx.upload_bvh(scene.nodes, scene.triangles)
     ctx.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
     if world > 1:
@@ -357,8 +361,9 @@ def main():
     ms_per_frame = dev_ms / args.steps
     mrays = rays_total / (dev_ms * 1e-3) / 1e6
 
-    # ---- per-pass breakdown + roofline of the dominant kernel (single kernel per bracket) ------------------
-    names = ["restir_omni_kernel", "unbiased_reuse_kernel" if cfg["unbiased"] else "spatial_reuse_kernel(x2)", "lighting_kernel"]
+    # ---- per-pass and per-kernel breakdown (CUDA events on the launching stream: pass brackets here, kernel
+    # brackets inside the library via restir_profile_begin/_end) + roofline of the dominant kernel ------------
+    names = ["restir pass", "unbiased pass" if cfg["unbiased"] else "spatial pass (x2)", "lighting pass"]
     pass_ms = np.zeros(3)
     reps = max(3, min(args.steps, 10))
     for _ in range(reps):
@@ -390,27 +395,53 @@ def main():
         pass_ms += [e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])]
         frame_no += 1
     pass_ms /= reps
+    kernel_ms, kernel_launches = {}, {}
+    ctx.counters(reset=True)
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.profile_begin()
+        device_step(frame_no)
+        for name, (n, ms) in ctx.profile_end().items():
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / reps
+            kernel_launches[name] = kernel_launches.get(name, 0) + n / reps
+        frame_no += 1
+    rays_prof = ctx.counters(reset=True)["shadow_rays"] / reps
     peak, peak_src = peaks()
-    scene_bytes = scene.nodes.size + scene.triangles.size
+    info = ctx.bvh_info()
+    bvh_bytes = (info["wide_nodes"] * 128 if info["wide_nodes"] else scene.nodes.size) + scene.triangles.size
     light_bytes = scene.point_blob.size + scene.tri_blob.size + scene.alias_blob.size
-    alg_bytes = [own_pixels * BYTES_PER_PIXEL["restir"] + scene_bytes + light_bytes,
-                 own_pixels * BYTES_PER_PIXEL["unbiased"] + scene_bytes + light_bytes if cfg["unbiased"]
-                 else 2 * (own_pixels * BYTES_PER_PIXEL["spatial"] + light_bytes),
-                 own_pixels * BYTES_PER_PIXEL["lighting_rgba8"] + light_bytes]
-    top = int(np.argmax(pass_ms))
-    launches_in_top = 2 if (top == 1 and not cfg["unbiased"]) else 1
-    achieved = alg_bytes[top] / (pass_ms[top] * 1e-3) / 1e9
+    k = cfg["neighbors"]
+    # algorithmic bytes per launch of each kernel: every input read once, every output written once
+    alg = {
+        "omni_candidates_kernel": own_pixels * (32 + 32) + light_bytes,
+        "omni_temporal_kernel": own_pixels * (32 + 1 + 32 + 28 + 32 + 32) + light_bytes,
+        "spatial_reuse_kernel": own_pixels * BYTES_PER_PIXEL["spatial"] + light_bytes,
+        "unbiased_merge_kernel": own_pixels * (32 + 32 + 32 + 4 * k) + light_bytes,
+        "unbiased_finalize_kernel": own_pixels * (16 + 16 + 16 + 4 * k + (k + 1)),
+        "lighting_kernel": own_pixels * BYTES_PER_PIXEL["lighting_rgba8"] + light_bytes,
+        # one ray = neighbour/own position 16 B + sample position 16 B + neighbour index 4 B + visibility byte; + the tree once per launch
+        "trace_kernel": None,
+    }
+    if "trace_kernel" in kernel_ms:
+        n_trace = max(kernel_launches["trace_kernel"], 1)
+        alg["trace_kernel"] = (rays_prof * 37 + n_trace * bvh_bytes) / n_trace
+    top = max(kernel_ms, key=kernel_ms.get)
+    top_ms = kernel_ms[top] / max(kernel_launches[top], 1)
+    achieved = alg[top] / (top_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.config, {}).get(names[top])
-    roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[top] / launches_in_top,
-                "kernel_ms": float(pass_ms[top]) / launches_in_top,
-                "note": "ray-bearing passes are L2-latency / divergence bound, not HBM bound (BVH and light tables are L2-resident); "
-                        "the frame-level fraction is in hbm_frame_frac"}
-    frame_bytes = sum(alg_bytes)
+        traffic = json.load(open(tpath)).get(args.config, {}).get(top)
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top], "kernel_ms": top_ms,
+                "launches_per_frame": kernel_launches[top],
+                "note": "the trace kernel is issue/L2-latency bound, not HBM bound (tree and light tables are L2-resident): its yardstick is "
+                        "Mrays/s and lanes per instruction (profiles/); the streaming kernels' HBM fractions are in kernel_hbm_frac"}
+    kernel_hbm_frac = {n: (alg[n] * kernel_launches[n] / (kernel_ms[n] * 1e-3) / 1e9 / peak) for n in kernel_ms if alg.get(n)}
+    frame_bytes = sum(alg[n] * kernel_launches[n] for n in kernel_ms if alg.get(n))
     hbm_frame_frac = frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak
+    trace_mrays = rays_prof / (kernel_ms["trace_kernel"] * 1e-3) / 1e6 if kernel_ms.get("trace_kernel") else None
 
     # ---- end to end through the C ABI: host G-buffers in (pinned), 8-bit image out, every step ---------------
     e2e = None
@@ -507,6 +538,8 @@ def main():
                        "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
                        "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world}, halo {HALO} rows"},
             "rays_per_frame": rays_total / args.steps, "pass_ms": dict(zip(names, [float(x) for x in pass_ms])),
+            "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac,
+            "trace_kernel_mrays_per_s": trace_mrays, "bvh": info,
             "hbm_frame_frac": hbm_frame_frac, "frame_algorithmic_bytes": frame_bytes,
             "gpu_launches": int(launches), "halo_misses": int(halo_misses), "stack_overflows": int(overflows),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity_sample": parity,

@@ -103,6 +103,27 @@ int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_unif
  * ignores uniforms.spatialNeighbors; this overrides it (1..16) for the north-star's 5-neighbour runs. */
 int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
 
+/* Shadow-ray traversal.  The uploaded tree is always the reference's (aabbTreeBuilder node / triangle
+ * layout).  AUTO (default): restir_upload_bvh also derives a 4-wide re-layout of the same tree and the trace
+ * kernel walks that — same visibility bits, see csrc/wide_bvh.h for why — unless the tree fails the checks
+ * that make it exact (then REFERENCE_ORDER is used and restir_get_bvh_info says so).  REFERENCE_ORDER: walk
+ * the 80-byte nodes in softwareRaytracing.glsl:39-85's own order, 32-entry stack, dropped pushes counted.
+ * Takes effect at the next restir_upload_bvh. */
+#define RESTIR_TRAVERSAL_AUTO 0
+#define RESTIR_TRAVERSAL_REFERENCE_ORDER 1
+#define RESTIR_TRAVERSAL_WIDE 2 /* reported by restir_get_bvh_info only */
+int restir_set_traversal(restir_context *ctx, int mode);
+
+typedef struct restir_bvh_info {
+	uint32_t nodes, triangles;
+	uint32_t wide_nodes, wide_depth;      /* 0 when the reference-order traversal is in use */
+	uint32_t folded_nodes, unfolded_nodes; /* binary nodes folded into their parent / kept because nesting failed */
+	uint32_t reference_stack_bound;        /* worst-case occupancy of the reference's 32-entry stack on this tree */
+	uint32_t wide_stack_bound;
+	int32_t traversal;                     /* RESTIR_TRAVERSAL_WIDE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
+} restir_bvh_info;
+int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
+
 /* ---- the passes ---------------------------------------------------------------------------------- */
 
 /* Replaces: RestirPass::issueCommands, software-ray-tracing pipeline (restirPass.h:36-62) running
@@ -156,6 +177,17 @@ typedef struct restir_counters {
 } restir_counters;
 /* Synchronises the stream. */
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset);
+
+/* Per-kernel device times (no reference equivalent: the reference has no GPU timestamps, only an FPS
+ * counter, src/fpsCounter.h).  Between _begin and _end every kernel the context launches is bracketed by
+ * CUDA events on the context's stream; _end synchronises and sums them by kernel name. */
+typedef struct restir_kernel_time {
+	char name[48];
+	uint32_t launches;
+	float total_ms;
+} restir_kernel_time;
+int restir_profile_begin(restir_context *ctx);
+int restir_profile_end(restir_context *ctx, restir_kernel_time *out, uint32_t capacity, uint32_t *count);
 
 /* ---- scene-side builders (host, once per scene) ------------------------------------------------ */
 

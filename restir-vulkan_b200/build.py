@@ -5,9 +5,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_capi.cu", "host/scene_build.cpp"]
+SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_trace.cu", "csrc/restir_capi.cu", "csrc/wide_bvh.cpp", "host/scene_build.cpp"]
 DRIVER_SOURCES = ["host/restir_driver.cpp", "host/passes.hpp"]
-HEADERS = ["csrc/restir_math.cuh", "csrc/restir_device.cuh", "csrc/restir_kernels.h", "../include/restir_b200.h",
+HEADERS = ["csrc/restir_math.cuh", "csrc/restir_device.cuh", "csrc/restir_kernels.h", "csrc/restir_trace.cuh", "csrc/wide_bvh.h", "../include/restir_b200.h",
            "../include/restir_layouts.h", "host/passes.hpp"]
 OUT = os.path.join(HERE, "librestir_b200.so")
 DRIVER = os.path.join(HERE, "restir_driver")
@@ -29,6 +29,13 @@ def needs_build():
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.exists(os.path.join(HERE, s)) and os.path.getmtime(os.path.join(HERE, s)) > t for s in SOURCES + HEADERS + DRIVER_SOURCES + ["build.py"])
+
+
+def build_variant(out, defines, verbose=False):
+    """Experiment builds (same sources, extra -D flags) loaded through RESTIR_B200_LIB; not part of build()."""
+    cmd = [nvcc(), "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(HERE, s) for s in SOURCES]
+    subprocess.check_call(cmd, cwd=HERE)
+    return out
 
 
 def build(force=False, verbose=False):

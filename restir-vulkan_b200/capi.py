@@ -10,11 +10,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librestir_b200.so")
+LIB_PATH = os.environ.get("RESTIR_B200_LIB") or os.path.join(_HERE, "librestir_b200.so")  # the env override is for A/B experiment builds
 
 RESTIR_BUF_FRAME0, RESTIR_BUF_FRAME1, RESTIR_BUF_TEMP = 0, 1, 2
 RESTIR_OUT_RGBA32F, RESTIR_OUT_RGBA8_SRGB = 0, 1
 RESTIR_VISIBILITY_REUSE_FLAG, RESTIR_TEMPORAL_REUSE_FLAG = 1, 2
+RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_WIDE = 0, 1, 2
 
 RESERVOIR_DTYPE = np.dtype(
     [
@@ -60,6 +61,7 @@ EXPORTS = [
     "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
+    "restir_set_traversal", "restir_get_bvh_info", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_collect_triangle_lights",
@@ -74,6 +76,15 @@ class GBufferPlanes(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches")]
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("nodes", "triangles", "wide_nodes", "wide_depth", "folded_nodes", "unfolded_nodes",
+                                          "reference_stack_bound", "wide_stack_bound")] + [("traversal", C.c_int32)]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint32), ("total_ms", C.c_float)]
 
 
 class Camera(C.Structure):
@@ -298,6 +309,24 @@ class RestirContext:
 
     def set_unbiased_neighbors(self, n):
         self._check(self.lib.restir_set_unbiased_neighbors(self._ctx, C.c_uint32(n)))
+
+    def set_traversal(self, mode):
+        """Takes effect at the next upload_bvh."""
+        self._check(self.lib.restir_set_traversal(self._ctx, C.c_int(mode)))
+
+    def bvh_info(self):
+        b = BvhInfo()
+        self._check(self.lib.restir_get_bvh_info(self._ctx, C.byref(b)))
+        return {n: getattr(b, n) for n, _ in BvhInfo._fields_}
+
+    def profile_begin(self):
+        self._check(self.lib.restir_profile_begin(self._ctx))
+
+    def profile_end(self):
+        """{kernel name: (launches, total ms)} of everything launched since profile_begin (CUDA events on the context's stream)."""
+        arr, n = (KernelTime * 32)(), C.c_uint32()
+        self._check(self.lib.restir_profile_end(self._ctx, arr, C.c_uint32(32), C.byref(n)))
+        return {arr[i].name.decode(): (arr[i].launches, float(arr[i].total_ms)) for i in range(n.value)}
 
     def pass_restir(self, gbuffer, out_buffer, prev_buffer):
         self._check(self.lib.restir_pass_restir(self._ctx, C.c_int(gbuffer), C.c_int(out_buffer), C.c_int(prev_buffer)))

@@ -13,6 +13,7 @@
 
 #include "../../include/restir_b200.h"
 #include "restir_kernels.h"
+#include "wide_bvh.h"
 
 using namespace restir;
 
@@ -25,7 +26,10 @@ struct restir_context {
 
 	// scene
 	float4 *nodes = nullptr, *tris = nullptr;
+	float4 *wide = nullptr; // 4-wide re-layout of `nodes` (wide_bvh.h); null => reference-order traversal
+	WideBvhInfo wideInfo;
 	uint32_t nNodes = 0, nTris = 0;
+	int smCount = 0;
 	unsigned char *pointBlob = nullptr, *triBlob = nullptr, *aliasBlob = nullptr;
 	float4 *pointPosLum = nullptr, *triAux = nullptr;
 	int pointCount = 0, triCount = 0, aliasCount = 0;
@@ -38,15 +42,29 @@ struct restir_context {
 	void *ownedPlanes[2][5] = {};
 	restir_reservoir *staging = nullptr; // device scratch for 64-byte <-> 32-byte conversion
 	size_t stagingPixels = 0;
+	// hand-over buffers between the halves of a cut pass and the trace kernel (restir_kernels.cu)
+	unsigned char *shadowed = nullptr; // [tile-ordered pixel id][rays per pixel]
+	size_t shadowedBytes = 0;
+	int *neighborPix = nullptr;        // [tile-ordered pixel id][unbiased neighbours]
+	size_t neighborPixCount = 0;
 
 	restir_uniforms uniforms{};
 	bool haveUniforms = false;
 	restir_lighting_uniforms lighting{};
 	bool haveLighting = false;
 	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
+	int traversal = RESTIR_TRAVERSAL_AUTO;
 
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
 	uint64_t launches = 0;
+
+	// optional per-kernel CUDA-event timing (restir_profile_begin / _end)
+	struct ProfRecord {
+		const char *name;
+		cudaEvent_t begin, end;
+	};
+	bool profiling = false;
+	std::vector<ProfRecord> prof;
 
 	size_t allocPixels() const { return (size_t)(band.allocEnd - band.allocBegin) * (size_t)band.W; }
 };
@@ -107,6 +125,7 @@ SceneView sceneView(const restir_context *ctx) {
 	SceneView v{};
 	v.nodes = ctx->nodes;
 	v.tris = ctx->tris;
+	v.wide = ctx->wide;
 	v.pointLights = ctx->pointBlob ? reinterpret_cast<const restir_point_light *>(ctx->pointBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.triLights = ctx->triBlob ? reinterpret_cast<const restir_tri_light *>(ctx->triBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.alias = ctx->aliasBlob ? reinterpret_cast<const restir_alias_column *>(ctx->aliasBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
@@ -157,12 +176,65 @@ int makeParams(restir_context *ctx, int gbuffer, bool needScene, bool needLights
 	return RESTIR_OK;
 }
 
+// Every kernel launch of a pass goes between beforeLaunch and afterLaunch: error check, launch count and,
+// when profiling is on, a pair of events on the launching stream.
+void beforeLaunch(restir_context *ctx, const char *what) {
+	if (ctx->profiling) {
+		restir_context::ProfRecord r{what, nullptr, nullptr};
+		if (cudaEventCreate(&r.begin) == cudaSuccess && cudaEventCreate(&r.end) == cudaSuccess) {
+			cudaEventRecord(r.begin, ctx->stream);
+			ctx->prof.push_back(r);
+		}
+	}
+}
 int afterLaunch(restir_context *ctx, const char *what) {
 	ctx->launches++;
+	if (ctx->profiling && !ctx->prof.empty() && ctx->prof.back().name == what) {
+		cudaEventRecord(ctx->prof.back().end, ctx->stream);
+	}
 	return cudaCheck(ctx, cudaGetLastError(), what);
+}
+void dropProfile(restir_context *ctx) {
+	for (auto &r : ctx->prof) {
+		if (r.begin) cudaEventDestroy(r.begin);
+		if (r.end) cudaEventDestroy(r.end);
+	}
+	ctx->prof.clear();
 }
 
 const size_t kPlaneBytes[5] = {4, 8, 4, 16, 4}; // albedo, normal, material, worldPos, depth
+
+// grow-only hand-over buffers: one visibility byte per ray, one neighbour index per unbiased neighbour slot
+int ensureHandOver(restir_context *ctx, const PassGrid &g, unsigned raysPerPixel, unsigned neighbors) {
+	size_t bytes = (size_t)g.pixelIds * raysPerPixel;
+	if (ctx->shadowedBytes < bytes) {
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		freeDev(ctx->shadowed);
+		ctx->shadowedBytes = 0;
+		CU(ctx, cudaMalloc(&ctx->shadowed, bytes));
+		ctx->shadowedBytes = bytes;
+	}
+	size_t count = (size_t)g.pixelIds * neighbors;
+	if (ctx->neighborPixCount < count) {
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		freeDev(ctx->neighborPix);
+		ctx->neighborPixCount = 0;
+		CU(ctx, cudaMalloc(&ctx->neighborPix, count * sizeof(int)));
+		ctx->neighborPixCount = count;
+	}
+	return RESTIR_OK;
+}
+
+TraceParams traceParams(const restir_context *ctx) {
+	TraceParams tp{};
+	tp.nodes = ctx->nodes;
+	tp.tris = ctx->tris;
+	tp.wide = ctx->wide;
+	tp.band = ctx->band;
+	tp.shadowed = ctx->shadowed;
+	tp.counters = ctx->counters;
+	return tp;
+}
 
 } // namespace
 
@@ -186,6 +258,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 	int rc = RESTIR_OK;
 	do {
 		if ((rc = cudaCheck(ctx, cudaSetDevice(device), "cudaSetDevice")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute")) != RESTIR_OK) break;
 		if (stream != nullptr) {
 			ctx->stream = static_cast<cudaStream_t>(stream);
 		} else {
@@ -220,8 +293,12 @@ void restir_destroy(restir_context *ctx) {
 		cudaStreamSynchronize(ctx->stream);
 	}
 	dropGBuffers(ctx);
+	dropProfile(ctx);
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
+	freeDev(ctx->wide);
+	freeDev(ctx->shadowed);
+	freeDev(ctx->neighborPix);
 	freeDev(ctx->pointBlob);
 	freeDev(ctx->triBlob);
 	freeDev(ctx->aliasBlob);
@@ -252,16 +329,31 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	if (nodes == nullptr || triangles == nullptr || n_nodes == 0 || n_triangles == 0) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: empty tree");
 	}
+	// Child indices are checked here (the kernels trust them) and the traversal image is derived: the same
+	// tree, 4 wide, only where the nesting that makes the fold exact holds (wide_bvh.h).
+	std::vector<WideNode> wide;
+	WideBvhInfo info;
+	std::string why;
+	if (!build_wide_bvh(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, wide, info, why)) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: %s", why.c_str());
+	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
+	freeDev(ctx->wide);
+	ctx->nNodes = ctx->nTris = 0;
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
 	CU(ctx, cudaMalloc(&ctx->tris, (size_t)n_triangles * sizeof(restir_triangle)));
 	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
 	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, (size_t)n_triangles * sizeof(restir_triangle), cudaMemcpyHostToDevice, ctx->stream));
+	if (info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER) {
+		CU(ctx, cudaMalloc(&ctx->wide, wide.size() * sizeof(WideNode)));
+		CU(ctx, cudaMemcpyAsync(ctx->wide, wide.data(), wide.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
+	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->nNodes = n_nodes;
 	ctx->nTris = n_triangles;
+	ctx->wideInfo = info;
 	return RESTIR_OK;
 }
 
@@ -424,6 +516,32 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count) {
 	return RESTIR_OK;
 }
 
+int restir_set_traversal(restir_context *ctx, int mode) {
+	ENTER(ctx);
+	if (mode != RESTIR_TRAVERSAL_AUTO && mode != RESTIR_TRAVERSAL_REFERENCE_ORDER) {
+		return fail(ctx, RESTIR_E_INVALID, "unknown traversal mode %d", mode);
+	}
+	ctx->traversal = mode;
+	return RESTIR_OK;
+}
+
+int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out) {
+	if (ctx == nullptr || out == nullptr) {
+		return RESTIR_E_INVALID;
+	}
+	std::memset(out, 0, sizeof(*out));
+	out->nodes = ctx->nNodes;
+	out->triangles = ctx->nTris;
+	out->wide_nodes = ctx->wide ? ctx->wideInfo.wideNodes : 0;
+	out->wide_depth = ctx->wide ? (uint32_t)ctx->wideInfo.wideDepth : 0;
+	out->folded_nodes = ctx->wide ? ctx->wideInfo.foldedNodes : 0;
+	out->unfolded_nodes = ctx->wide ? ctx->wideInfo.keptUnfolded : 0;
+	out->reference_stack_bound = (uint32_t)ctx->wideInfo.referenceStackBound;
+	out->wide_stack_bound = (uint32_t)ctx->wideInfo.wideStackBound;
+	out->traversal = ctx->wide ? RESTIR_TRAVERSAL_WIDE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	return RESTIR_OK;
+}
+
 int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int prev_buffer) {
 	ENTER(ctx);
 	PassParams p;
@@ -434,8 +552,31 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	if (out_buffer == prev_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "restir pass: out and prev buffers must differ");
 	}
-	launch_restir_omni(p, ctx->reservoirs[out_buffer], ctx->reservoirs[prev_buffer], ctx->stream);
-	return afterLaunch(ctx, "restir_omni_kernel");
+	// restirOmni.glsl cut at its testVisibility call (:148-160): candidates | shadow rays | visibility + temporal
+	const PassGrid g = pass_grid(ctx->band);
+	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0, temporal = (p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0;
+	if ((rc = ensureHandOver(ctx, g, 1, 0)) != RESTIR_OK) return rc;
+	PackedReservoir *out = ctx->reservoirs[out_buffer];
+	beforeLaunch(ctx, "omni_candidates_kernel");
+	launch_omni_candidates(p, out, ctx->stream);
+	if ((rc = afterLaunch(ctx, "omni_candidates_kernel")) != RESTIR_OK) return rc;
+	if (vis) {
+		TraceParams tp = traceParams(ctx);
+		tp.tilesX = g.tilesX;
+		tp.slots = 1;
+		tp.nItems = g.pixelIds;
+		tp.worldPos = p.cur.worldPos;
+		tp.reservoirs = out;
+		beforeLaunch(ctx, "trace_kernel");
+		CU(ctx, launch_trace(tp, kTracePixel, ctx->smCount, ctx->stream));
+		if ((rc = afterLaunch(ctx, "trace_kernel")) != RESTIR_OK) return rc;
+	}
+	if (vis || temporal) {
+		beforeLaunch(ctx, "omni_temporal_kernel");
+		launch_omni_temporal(p, out, ctx->reservoirs[prev_buffer], ctx->shadowed, ctx->stream);
+		if ((rc = afterLaunch(ctx, "omni_temporal_kernel")) != RESTIR_OK) return rc;
+	}
+	return RESTIR_OK;
 }
 
 int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter) {
@@ -448,6 +589,7 @@ int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out
 	if (in_buffer == out_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "spatial pass: in and out buffers must differ");
 	}
+	beforeLaunch(ctx, "spatial_reuse_kernel");
 	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, ctx->stream);
 	return afterLaunch(ctx, "spatial_reuse_kernel");
 }
@@ -462,8 +604,31 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	if (in_buffer == out_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "unbiased pass: in and out buffers must differ");
 	}
-	launch_unbiased_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], (int)ctx->unbiasedNeighbors, ctx->stream);
-	return afterLaunch(ctx, "unbiased_reuse_kernel");
+	// unbiasedReuse.glsl cut at its testVisibility calls (:139-166): merge | shadow rays | normalisation
+	const PassGrid g = pass_grid(ctx->band);
+	const unsigned k = ctx->unbiasedNeighbors;
+	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
+	if ((rc = ensureHandOver(ctx, g, k + 1, k)) != RESTIR_OK) return rc;
+	const PackedReservoir *in = ctx->reservoirs[in_buffer];
+	PackedReservoir *out = ctx->reservoirs[out_buffer];
+	beforeLaunch(ctx, "unbiased_merge_kernel");
+	launch_unbiased_merge(p, in, out, (int)k, ctx->neighborPix, ctx->stream);
+	if ((rc = afterLaunch(ctx, "unbiased_merge_kernel")) != RESTIR_OK) return rc;
+	if (vis) {
+		TraceParams tp = traceParams(ctx);
+		tp.tilesX = g.tilesX;
+		tp.slots = k + 1;
+		tp.nItems = g.pixelIds * (k + 1);
+		tp.worldPos = p.cur.worldPos;
+		tp.reservoirs = out;
+		tp.neighborPix = ctx->neighborPix;
+		beforeLaunch(ctx, "trace_kernel");
+		CU(ctx, launch_trace(tp, kTraceUnbiased, ctx->smCount, ctx->stream));
+		if ((rc = afterLaunch(ctx, "trace_kernel")) != RESTIR_OK) return rc;
+	}
+	beforeLaunch(ctx, "unbiased_finalize_kernel");
+	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
+	return afterLaunch(ctx, "unbiased_finalize_kernel");
 }
 
 int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out_device, int out_format) {
@@ -481,6 +646,7 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
 	if ((int)ctx->lighting.bufferSize[0] != ctx->band.W || (int)ctx->lighting.bufferSize[1] != ctx->band.H) {
 		return fail(ctx, RESTIR_E_INVALID, "lighting uniforms bufferSize does not match restir_resize");
 	}
+	beforeLaunch(ctx, "lighting_kernel");
 	launch_lighting(p, ctx->lighting, ctx->reservoirs[buffer], out_device, out_format, ctx->stream);
 	return afterLaunch(ctx, "lighting_kernel");
 }
@@ -570,8 +736,14 @@ int restir_trace_segments(restir_context *ctx, const float *p1, const float *p2,
 	if (n == 0) {
 		return RESTIR_OK;
 	}
-	launch_trace_segments(sceneView(ctx), p1, p2, n, shadowed, ctx->counters, ctx->stream);
-	return afterLaunch(ctx, "trace_segments_kernel");
+	TraceParams tp = traceParams(ctx);
+	tp.nItems = n;
+	tp.segP1 = p1;
+	tp.segP2 = p2;
+	tp.shadowed = shadowed;
+	beforeLaunch(ctx, "trace_kernel");
+	CU(ctx, launch_trace(tp, kTraceSegments, ctx->smCount, ctx->stream));
+	return afterLaunch(ctx, "trace_kernel");
 }
 
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
@@ -589,6 +761,39 @@ int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
 		CU(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(h), ctx->stream));
 		ctx->launches = 0;
 	}
+	return RESTIR_OK;
+}
+
+int restir_profile_begin(restir_context *ctx) {
+	ENTER(ctx);
+	dropProfile(ctx);
+	ctx->profiling = true;
+	return RESTIR_OK;
+}
+
+int restir_profile_end(restir_context *ctx, restir_kernel_time *out, uint32_t capacity, uint32_t *count) {
+	ENTER(ctx);
+	ctx->profiling = false;
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	uint32_t n = 0;
+	for (auto &r : ctx->prof) {
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, r.begin, r.end) != cudaSuccess) {
+			continue;
+		}
+		uint32_t k = 0;
+		while (k < n && std::strcmp(out[k].name, r.name) != 0) ++k;
+		if (k == n) {
+			if (n == capacity) continue;
+			std::memset(&out[n], 0, sizeof(out[n]));
+			std::strncpy(out[n].name, r.name, sizeof(out[n].name) - 1);
+			++n;
+		}
+		out[k].launches++;
+		out[k].total_ms += ms;
+	}
+	dropProfile(ctx);
+	if (count) *count = n;
 	return RESTIR_OK;
 }
 

@@ -24,6 +24,7 @@ static_assert(sizeof(PackedReservoir) == 32, "packed reservoir is 32 bytes");
 struct SceneView {
 	const float4 *nodes;       // reference layout, 5 x float4 per node (80 B)
 	const float4 *tris;        // reference layout, 3 x float4 per triangle (48 B)
+	const float4 *wide;        // derived at upload (wide_bvh.h): 8 x float4 per 4-wide node (128 B); null => reference-order traversal
 	const restir_point_light *pointLights;
 	const restir_tri_light *triLights;
 	const restir_alias_column *alias;
@@ -50,7 +51,8 @@ struct Band {
 	int allocBegin, allocEnd;
 };
 
-enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterCount = 4 };
+enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterWork = 3, kCounterCount = 4 };
+// kCounterWork is the persistent trace kernel's work cursor (zeroed before every trace launch).
 
 struct PassParams {
 	SceneView scene;

@@ -1,16 +1,22 @@
-// restir_kernels.cu — hand-written sm_100a kernels of the ReSTIR resampling path.
+// restir_kernels.cu — hand-written sm_100a per-pixel kernels of the ReSTIR resampling path.
 //
-//   restir_omni_kernel      <- src/shaders/restirOmni.glsl:86-212   (RIS + visibility reuse + temporal reuse)
-//   spatial_reuse_kernel    <- src/shaders/spatialReuse.comp:30-86
-//   unbiased_reuse_kernel   <- src/shaders/unbiasedReuse.glsl:50-185
-//   lighting_kernel         <- src/shaders/lighting.frag:43-71,103  (debugMode 0)
-//   trace_segments_kernel   <- src/shaders/include/visibilityTest.glsl:1-4,27-28 + softwareRaytracing.glsl
-//   raycast_gbuffer_kernel  fixture tool (primary visibility through the same tree)
+//   omni_candidates_kernel    <- src/shaders/restirOmni.glsl:86-145   (RIS over the alias table)
+//   omni_temporal_kernel      <- src/shaders/restirOmni.glsl:148-212  (apply the visibility bit, temporal reuse)
+//   spatial_reuse_kernel      <- src/shaders/spatialReuse.comp:30-86
+//   unbiased_merge_kernel     <- src/shaders/unbiasedReuse.glsl:50-124
+//   unbiased_finalize_kernel  <- src/shaders/unbiasedReuse.glsl:126-185
+//   lighting_kernel           <- src/shaders/lighting.frag:43-71,103  (debugMode 0)
+//   raycast_gbuffer_kernel    fixture tool (primary visibility through the same tree)
+//
+// The reference traces its shadow rays inline in restirOmni / unbiasedReuse.  Here each of those shaders is
+// cut at its testVisibility calls: the part before writes the (not yet visibility-tested) reservoir, the
+// persistent trace kernel (restir_trace.cu) answers every ray of the pass with full warps, and the part
+// after consumes one byte per ray.  The RNG stream of a pixel continues across the cut by an LCG jump.
 //
 // One thread shades one pixel, as in the reference, but a CTA covers a 32x8 screen tile made of
-// eight 8x4 warp tiles (the reference uses 64x1 workgroups, restirStructs.glsl:10-14): rays of a warp
-// start from a compact screen patch and the G-buffer / reservoir rows a warp touches are whole 32-byte
-// sectors.  Reservoirs live in HBM as 32-byte PackedReservoir records.
+// eight 8x4 warp tiles (the reference uses 64x1 workgroups, restirStructs.glsl:10-14): the G-buffer /
+// reservoir rows a warp touches are whole 32-byte sectors and the rays of a tile are neighbours in the trace
+// kernel's work list.  Reservoirs live in HBM as 32-byte PackedReservoir records.
 
 #include "restir_device.cuh"
 #include "restir_kernels.h"
@@ -26,6 +32,13 @@ __device__ __forceinline__ bool pixel_of_thread(const Band &b, int &x, int &y) {
 	x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
 	y = b.rowBegin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
 	return x < b.W && y < b.rowEnd;
+}
+// Tile-ordered pixel id of this thread: (8x4 tile index, lane).  The trace kernel numbers its work items the
+// same way (restir_trace.cu item_pixel).
+__device__ __forceinline__ unsigned long long tile_pixel_id() {
+	unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned tileX = blockIdx.x * 4u + (warp & 3u), tileY = blockIdx.y * 2u + (warp >> 2);
+	return ((unsigned long long)tileY * (gridDim.x * 4u) + tileX) * 32ull + lane;
 }
 __device__ __forceinline__ size_t local_index(const Band &b, int x, int y) {
 	return (size_t)(y - b.allocBegin) * (size_t)b.W + (size_t)x;
@@ -67,6 +80,15 @@ __device__ __forceinline__ f3 fetch_world_pos(const GBufferView &g, size_t i) {
 __device__ __forceinline__ PackedReservoir load_reservoir(const PackedReservoir *buf, size_t i) {
 	const float4 *p = reinterpret_cast<const float4 *>(buf + i);
 	float4 a = __ldg(p), b = __ldg(p + 1);
+	PackedReservoir r;
+	r.px = a.x; r.py = a.y; r.pz = a.z; r.lightIndex = __float_as_int(a.w);
+	r.pHat = b.x; r.sumWeights = b.y; r.w = b.z; r.M = __float_as_uint(b.w);
+	return r;
+}
+// same, through the coherent path: for a buffer this pass's earlier kernel wrote
+__device__ __forceinline__ PackedReservoir load_reservoir_plain(const PackedReservoir *buf, size_t i) {
+	const float4 *p = reinterpret_cast<const float4 *>(buf + i);
+	float4 a = p[0], b = p[1];
 	PackedReservoir r;
 	r.px = a.x; r.py = a.y; r.pz = a.z; r.lightIndex = __float_as_int(a.w);
 	r.pHat = b.x; r.sumWeights = b.y; r.w = b.z; r.M = __float_as_uint(b.w);
@@ -130,87 +152,6 @@ __device__ __forceinline__ void combine_reservoirs(PackedReservoir &self, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// shadow rays: softwareRaytracing.glsl + visibilityTest.glsl (software branch)
-
-// softwareRaytracing.glsl:9-14 with the division hoisted (P3): inv = 1/dir once per ray.
-__device__ __forceinline__ bool ray_box(f3 o, f3 inv, float4 bmin, float4 bmax) {
-	float t1x = (bmin.x - o.x) * inv.x, t1y = (bmin.y - o.y) * inv.y, t1z = (bmin.z - o.z) * inv.z;
-	float t2x = (bmax.x - o.x) * inv.x, t2y = (bmax.y - o.y) * inv.y, t2z = (bmax.z - o.z) * inv.z;
-	float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
-	float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
-	return rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
-}
-// softwareRaytracing.glsl:15-37
-__device__ __forceinline__ bool ray_triangle(const float4 *tris, int id, f3 o, f3 d) {
-	const float4 *t = tris + (size_t)id * 3;
-	float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-	f3 p1 = mk3(a.x, a.y, a.z);
-	f3 e1 = mk3(b.x, b.y, b.z) - p1;
-	f3 e2 = mk3(c.x, c.y, c.z) - p1;
-	f3 p = cross3(d, e2);
-	float f = 1.0f / dot3(e1, p);
-	f3 s = o - p1;
-	float baryX = f * dot3(s, p);
-	if (baryX < 0.0f || baryX > 1.0f) {
-		return false;
-	}
-	f3 q = cross3(s, e1);
-	float baryY = f * dot3(d, q);
-	if (baryY < 0.0f || baryY + baryX > 1.0f) {
-		return false;
-	}
-	f = f * dot3(e2, q);
-	return f > 0.0f && f < 1.0f;
-}
-
-// softwareRaytracing.glsl:39-85.  Any-hit: the answer does not depend on the order in which nodes and
-// triangles are visited, only on which boxes / triangles the segment intersects, so triangles are tested
-// as soon as their leaf box is hit instead of being deferred in batches of 8 node visits.  The stack is
-// the reference's 32 entries with its push order (left, then right); a push onto a full stack is dropped
-// and counted (UB in the reference).  Returns true when nothing is hit.
-__device__ bool trace_any(const SceneView &sc, f3 o, f3 d, unsigned &overflow) {
-	int stack[32];
-	int top = 1;
-	stack[0] = 0;
-	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-	while (top > 0) {
-		const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
-		float4 lmin = __ldg(n), lmax = __ldg(n + 1), rmin = __ldg(n + 2), rmax = __ldg(n + 3);
-		float4 ch = __ldg(n + 4);
-		int left = __float_as_int(ch.x), right = __float_as_int(ch.y);
-		if (ray_box(o, inv, lmin, lmax)) {
-			if (left < 0) {
-				if (ray_triangle(sc.tris, ~left, o, d)) {
-					return false;
-				}
-			} else if (top < 32) {
-				stack[top++] = left;
-			} else {
-				overflow++;
-			}
-		}
-		if (ray_box(o, inv, rmin, rmax)) {
-			if (right < 0) {
-				if (ray_triangle(sc.tris, ~right, o, d)) {
-					return false;
-				}
-			} else if (top < 32) {
-				stack[top++] = right;
-			} else {
-				overflow++;
-			}
-		}
-	}
-	return true;
-}
-
-// visibilityTest.glsl:1-4, 27-28.  Returns SHADOWED.
-__device__ __forceinline__ bool test_visibility(const SceneView &sc, f3 p1, f3 p2, unsigned &overflow) {
-	f3 dir = p2 - p1;
-	f3 offset = normalize3(dir) * 0.001f;
-	return !trace_any(sc, p1 + offset, dir - offset * 2.0f, overflow);
-}
-
 __device__ __forceinline__ void add_counter(unsigned long long *counters, int slot, unsigned v) {
 	// one atomic per warp
 	unsigned total = __reduce_add_sync(0xffffffffu, v);
@@ -233,82 +174,140 @@ __device__ __forceinline__ void alias_sample(const SceneView &sc, float r1, floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// restirOmni.glsl:86-212
-__global__ void __launch_bounds__(kThreads) restir_omni_kernel(PassParams p, PackedReservoir *__restrict__ out,
-                                                              const PackedReservoir *__restrict__ prevReservoirs) {
+// PCG32 stream position after n draws: state_n = A_n * state + G_n * inc (LCG jump-ahead), with A_n, G_n
+// computed once per launch on the host (lcg_jump).  Lets the second half of a cut shader continue the
+// pixel's RNG stream (rand.glsl:12-18) without storing it.
+struct LcgJump {
+	uint64_t A, G;
+};
+static LcgJump lcg_jump(uint64_t n) {
+	uint64_t accA = 1, accG = 0, curA = 6364136223846793005ull, curG = 1;
+	while (n) {
+		if (n & 1) {
+			accG = accG * curA + curG;
+			accA = accA * curA;
+		}
+		curG = (curA + 1) * curG;
+		curA = curA * curA;
+		n >>= 1;
+	}
+	return LcgJump{accA, accG};
+}
+
+// draws consumed by restirOmni.glsl:108-142 per candidate: 2 (alias table) [+ 2 (point on triangle)] + 1 (reservoir update)
+__host__ __device__ inline uint32_t draws_per_candidate(bool pointMode) { return pointMode ? 3u : 5u; }
+
+// ------------------------------------------------------------------------------------------------
+// restirOmni.glsl:86-145: candidate generation and streaming RIS.  Writes the reservoir BEFORE the
+// visibility test (:148-160) and temporal reuse (:163-209), which omni_temporal_kernel applies.
+//
+// Exact shortcuts (same bits as the straightforward evaluation, tests/test_gpu_parity.py):
+//   * `w` of addSampleToReservoir (reservoir.glsl:33) is only observable for the candidate that ends up
+//     selected, so the division is done once after the loop from the (sumWeights, M) recorded at selection;
+//   * a point light behind the surface has pHat = +0 (restirUtils.glsl:8-10) and, for prob > 0, weight +0:
+//     sumWeights and the selection are unchanged and only M and the RNG advance (reservoir.glsl:6-26).
+__global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
+	int x, y;
+	if (!pixel_of_thread(p.band, x, y)) {
+		return;
+	}
+	const SceneView &sc = p.scene;
+	size_t pix = local_index(p.band, x, y);
+	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
+	f3 normal = fetch_normal(p.cur, pix);
+	float roughness, metallic;
+	fetch_material(p.cur, pix, roughness, metallic);
+	f3 worldPos = fetch_world_pos(p.cur, pix);
+	float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
+	f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+
+	PackedReservoir res;                                                      // :105
+	res.px = res.py = res.pz = 0.0f;
+	res.lightIndex = 0;
+	res.pHat = res.sumWeights = res.w = 0.0f;
+	res.M = 0u;
+	if (dot3(normal, normal) != 0.0f) {                                       // :107
+		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
+		const uint32_t count = p.u.initialLightSampleCount;
+		const bool pointMode = sc.pointCount != 0;
+		float selSum = 0.0f;
+		uint32_t selM = 0u;
+		for (uint32_t i = 0; i < count; ++i) {                                // :108-142
+			float r1 = pcg_float(rng);
+			float r2 = pcg_float(rng);
+			int idx;
+			float prob;
+			alias_sample(sc, r1, r2, idx, prob);
+			f3 lpos, ln;
+			float lum;
+			int lightIndex;
+			if (pointMode) {                                                  // :116-122
+				float4 pl = __ldg(sc.pointPosLum + idx);
+				lpos = mk3(pl.x, pl.y, pl.z);
+				lum = pl.w;
+				lightIndex = idx;
+				ln = mk3(0.0f, 0.0f, 0.0f);
+				if (dot3(lpos - worldPos, normal) < 0.0f && prob > 0.0f) {    // pHat = +0, weight = +0: nothing but M and the RNG move
+					res.M += 1u;
+					pcg_next(rng);
+					continue;
+				}
+			} else {                                                          // :123-133
+				const float4 *tl = reinterpret_cast<const float4 *>(sc.triLights + idx);
+				float4 a = __ldg(tl), b = __ldg(tl + 1), c = __ldg(tl + 2), em = __ldg(tl + 3), na = __ldg(tl + 4);
+				float r3 = pcg_float(rng);
+				float r4 = pcg_float(rng);
+				float sq = sqrtf(r3);                                          // pickPointOnTriangle :68-71
+				lpos = (mk3(a.x, a.y, a.z) * (1.0f - sq) + mk3(b.x, b.y, b.z) * (sq * (1.0f - r4))) + mk3(c.x, c.y, c.z) * (r4 * sq);
+				lum = em.w;
+				lightIndex = -1 - idx;
+				f3 wi = normalize3(worldPos - lpos);
+				ln = mk3(na.x, na.y, na.z);
+				prob = prob / (fabsf(dot3(wi, ln)) * na.w);
+			}
+			float pHat = evaluate_phat(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
+			// addSampleToReservoir + updateReservoirAt, reservoir.glsl:28-42, 6-26
+			float weight = pHat / prob;
+			res.M += 1u;
+			res.sumWeights = res.sumWeights + weight;
+			float replacePossibility = weight / res.sumWeights;
+			if (pcg_float(rng) < replacePossibility) {
+				res.px = lpos.x; res.py = lpos.y; res.pz = lpos.z;
+				res.lightIndex = lightIndex;
+				res.pHat = pHat;
+				selSum = res.sumWeights;
+				selM = res.M;
+			}
+		}
+		if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
+			res.w = selSum / ((float)selM * res.pHat);
+		}
+	}
+	store_reservoir(out, pix, res);                                           // handed to the trace kernel and omni_temporal_kernel
+}
+
+// restirOmni.glsl:148-212 on the reservoir omni_candidates_kernel wrote.
+__global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, PackedReservoir *__restrict__ out,
+                                                                const PackedReservoir *__restrict__ prevReservoirs,
+                                                                const unsigned char *__restrict__ shadowed, LcgJump jump) {
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
-	unsigned rays = 0, overflow = 0, haloMiss = 0;
+	unsigned haloMiss = 0;
 	if (active) {
 		const SceneView &sc = p.scene;
 		size_t pix = local_index(p.band, x, y);
-		f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
-		f3 normal = fetch_normal(p.cur, pix);
-		float roughness, metallic;
-		fetch_material(p.cur, pix, roughness, metallic);
-		f3 worldPos = fetch_world_pos(p.cur, pix);
-		float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
-		f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
-		Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
-
-		PackedReservoir res;                                                      // :105
-		res.px = res.py = res.pz = 0.0f;
-		res.lightIndex = 0;
-		res.pHat = res.sumWeights = res.w = 0.0f;
-		res.M = 0u;
-		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
-		if (dot3(normal, normal) != 0.0f) {                                       // :107
-			const uint32_t count = p.u.initialLightSampleCount;
-			const bool pointMode = sc.pointCount != 0;
-			for (uint32_t i = 0; i < count; ++i) {                                // :108-142
-				float r1 = pcg_float(rng);
-				float r2 = pcg_float(rng);
-				int idx;
-				float prob;
-				alias_sample(sc, r1, r2, idx, prob);
-				f3 lpos, ln;
-				float lum;
-				int lightIndex;
-				if (pointMode) {                                                  // :116-122
-					float4 pl = __ldg(sc.pointPosLum + idx);
-					lpos = mk3(pl.x, pl.y, pl.z);
-					lum = pl.w;
-					lightIndex = idx;
-					ln = mk3(0.0f, 0.0f, 0.0f);
-				} else {                                                          // :123-133
-					const float4 *tl = reinterpret_cast<const float4 *>(sc.triLights + idx);
-					float4 a = __ldg(tl), b = __ldg(tl + 1), c = __ldg(tl + 2), em = __ldg(tl + 3), na = __ldg(tl + 4);
-					float r3 = pcg_float(rng);
-					float r4 = pcg_float(rng);
-					float sq = sqrtf(r3);                                          // pickPointOnTriangle :68-71
-					lpos = (mk3(a.x, a.y, a.z) * (1.0f - sq) + mk3(b.x, b.y, b.z) * (sq * (1.0f - r4))) + mk3(c.x, c.y, c.z) * (r4 * sq);
-					lum = em.w;
-					lightIndex = -1 - idx;
-					f3 wi = normalize3(worldPos - lpos);
-					ln = mk3(na.x, na.y, na.z);
-					prob = prob / (fabsf(dot3(wi, ln)) * na.w);
-				}
-				float pHat = evaluate_phat(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
-				// addSampleToReservoir, reservoir.glsl:28-42
-				float weight = pHat / prob;
-				res.M += 1u;
-				float w = (res.sumWeights + weight) / ((float)res.M * pHat);
-				update_reservoir(res, weight, lpos, lightIndex, pHat, w, rng);
-			}
-		}
-
+		PackedReservoir res = load_reservoir_plain(out, pix);
+		bool dirty = false;
 		// visibility reuse, :148-160 (M is kept)
-		if ((p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0) {
-			bool shadowed = test_visibility(sc, worldPos, mk3(res.px, res.py, res.pz), overflow);
-			rays = 1;
-			if (shadowed) {
-				res.w = 0.0f;
-				res.sumWeights = 0.0f;
-			}
+		if ((p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0 && shadowed[tile_pixel_id()] != 0) {
+			res.w = 0.0f;
+			res.sumWeights = 0.0f;
+			dirty = true;
 		}
-
 		// temporal reuse, :163-209
 		if ((p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0) {
+			f3 worldPos = fetch_world_pos(p.cur, pix);
 			const float *M = p.u.prevFrameProjectionViewMatrix;
 			float px = ((M[0] * worldPos.x + M[4] * worldPos.y) + M[8] * worldPos.z) + M[12] * 1.0f;
 			float py = ((M[1] * worldPos.x + M[5] * worldPos.y) + M[9] * worldPos.z) + M[13] * 1.0f;
@@ -326,23 +325,36 @@ __global__ void __launch_bounds__(kThreads) restir_omni_kernel(PassParams p, Pac
 					size_t ppix = local_index(p.band, fx, fy);
 					f3 dp = worldPos - fetch_world_pos(p.prev, ppix);
 					if (dot3(dp, dp) < 0.01f) {
+						f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
 						f3 da = albedo - fetch_albedo(p.prev, sc.srgbLut, ppix, nullptr);
 						if (dot3(da, da) < 0.01f) {
+							f3 normal = fetch_normal(p.cur, pix);
 							float nd = dot3(normal, fetch_normal(p.prev, ppix));
 							if (nd > 0.5f) {
+								float roughness, metallic;
+								fetch_material(p.cur, pix, roughness, metallic);
+								float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);
+								f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+								Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+								// the pixel's RNG stream, advanced past the candidate loop's draws (:106-142)
+								Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);
+								if (dot3(normal, normal) != 0.0f) {
+									rng.state = jump.A * rng.state + jump.G * rng.inc;
+								}
 								PackedReservoir prevRes = load_reservoir(prevReservoirs, ppix);
 								prevRes.M = min(prevRes.M, p.u.temporalSampleCountMultiplier * res.M); // :189-191
 								combine_reservoirs(res, prevRes, sc, sf, albedoLum, rng);
+								dirty = true;
 							}
 						}
 					}
 				}
 			}
 		}
-		store_reservoir(out, pix, res);                                           // :211
+		if (dirty) {
+			store_reservoir(out, pix, res);                                       // :211
+		}
 	}
-	add_counter(p.counters, kCounterRays, rays);
-	add_counter(p.counters, kCounterOverflow, overflow);
 	add_counter(p.counters, kCounterHaloMiss, haloMiss);
 }
 
@@ -398,14 +410,18 @@ __global__ void __launch_bounds__(kThreads) spatial_reuse_kernel(PassParams p, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// unbiasedReuse.glsl:50-185
+// unbiasedReuse.glsl:50-124: merge the neighbours' reservoirs (no rejection), then decide which neighbours
+// take part in the normalisation (:135-138, sample in front of the neighbour's surface).  Writes the merged
+// reservoir and, per neighbour slot, the neighbour's local pixel index (< 0: contributes nothing and needs no
+// ray).  The rays themselves (:139-166) are the trace kernel's, the normalisation unbiased_finalize_kernel's.
 constexpr int kMaxUnbiasedNeighbors = 16;
 
-__global__ void __launch_bounds__(kThreads) unbiased_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
-                                                                 PackedReservoir *__restrict__ out, int numNeighbors) {
+__global__ void __launch_bounds__(kThreads) unbiased_merge_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+                                                                 PackedReservoir *__restrict__ out, int numNeighbors,
+                                                                 int *__restrict__ neighborPix) {
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
-	unsigned rays = 0, overflow = 0, haloMiss = 0;
+	unsigned haloMiss = 0;
 	if (active) {
 		const SceneView &sc = p.scene;
 		size_t pix = local_index(p.band, x, y);
@@ -420,9 +436,7 @@ __global__ void __launch_bounds__(kThreads) unbiased_reuse_kernel(PassParams p, 
 
 		PackedReservoir res = load_reservoir(in, pix);
 		Pcg32 rng = pcg_seed(p.u.frame * 17u, (uint32_t)y * 10007u + (uint32_t)x); // :72
-		uint32_t originalM = res.M;
 		int npx[kMaxUnbiasedNeighbors];
-		uint32_t nM[kMaxUnbiasedNeighbors];
 #pragma unroll 1
 		for (int i = 0; i < numNeighbors; ++i) {                                  // :84-124
 			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;
@@ -435,13 +449,11 @@ __global__ void __launch_bounds__(kThreads) unbiased_reuse_kernel(PassParams p, 
 			if (ny < p.band.allocBegin || ny >= p.band.allocEnd) {
 				haloMiss = 1;
 				npx[i] = -1;
-				nM[i] = 0;
 				continue;
 			}
 			size_t npix = local_index(p.band, nx, ny);
 			PackedReservoir other = load_reservoir(in, npix);
 			npx[i] = (int)npix;
-			nM[i] = other.M;
 			res.M += other.M;                                                     // :104
 			if (other.w != 0.0f && other.M != 0u) {                               // see combine_reservoirs
 				f3 n; bool useN; float lum;
@@ -453,45 +465,62 @@ __global__ void __launch_bounds__(kThreads) unbiased_reuse_kernel(PassParams p, 
 				}
 			}
 		}
-		// :126-182
+		store_reservoir(out, pix, res);
+		// :135-138
 		f3 lightPos = mk3(res.px, res.py, res.pz);
-		uint32_t numSamples = originalM;
-		const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
+		int *slots = neighborPix + tile_pixel_id() * (unsigned long long)numNeighbors;
 #pragma unroll 1
 		for (int j = 0; j < numNeighbors; ++j) {
-			if (npx[j] < 0) {
-				continue;
-			}
-			f3 nPos = fetch_world_pos(p.cur, (size_t)npx[j]);
-			f3 nNor = fetch_normal(p.cur, (size_t)npx[j]);
-			if (dot3(lightPos - nPos, nNor) < 0.0f) {
-				continue;
-			}
-			if (vis) {
-				rays++;
-				if (test_visibility(sc, nPos, lightPos, overflow)) {
-					continue;
+			int n = npx[j];
+			if (n >= 0) {
+				f3 nPos = fetch_world_pos(p.cur, (size_t)n);
+				f3 nNor = fetch_normal(p.cur, (size_t)n);
+				if (dot3(lightPos - nPos, nNor) < 0.0f) {
+					n = -1;
 				}
 			}
-			numSamples += nM[j];
+			slots[j] = n;
 		}
-		if (vis) {
-			rays++;
-			if (test_visibility(sc, worldPos, lightPos, overflow)) {
-				numSamples = 0;
-			}
-		}
-		if (numSamples > 0) {
-			res.w = res.sumWeights / ((float)numSamples * res.pHat);
-		} else {
-			res.w = 0.0f;
-			res.sumWeights = 0.0f;
-		}
-		store_reservoir(out, pix, res);
 	}
-	add_counter(p.counters, kCounterRays, rays);
-	add_counter(p.counters, kCounterOverflow, overflow);
 	add_counter(p.counters, kCounterHaloMiss, haloMiss);
+}
+
+// unbiasedReuse.glsl:126-182 given the visibility bytes: Z = own M + the M of every participating, unshadowed
+// neighbour; everything is dropped when the pixel itself is shadowed.
+__global__ void __launch_bounds__(kThreads) unbiased_finalize_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+                                                                    PackedReservoir *__restrict__ out, int numNeighbors,
+                                                                    const int *__restrict__ neighborPix,
+                                                                    const unsigned char *__restrict__ shadowed) {
+	int x, y;
+	if (!pixel_of_thread(p.band, x, y)) {
+		return;
+	}
+	size_t pix = local_index(p.band, x, y);
+	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
+	unsigned long long id = tile_pixel_id();
+	const int *slots = neighborPix + id * (unsigned long long)numNeighbors;
+	const unsigned char *bits = shadowed + id * (unsigned long long)(numNeighbors + 1);
+	float4 *o = reinterpret_cast<float4 *>(out + pix);
+	float4 b = o[1]; // pHat, sumWeights, w, M of the merged reservoir
+	uint32_t numSamples = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(in + pix) + 1).w); // own M before the merge, :126
+#pragma unroll 1
+	for (int j = 0; j < numNeighbors; ++j) {
+		int n = __ldg(slots + j);
+		if (n < 0 || (vis && bits[j] != 0)) {
+			continue;
+		}
+		numSamples += __float_as_uint(__ldg(reinterpret_cast<const float4 *>(in + n) + 1).w);
+	}
+	if (vis && bits[numNeighbors] != 0) {                                         // :157-166
+		numSamples = 0;
+	}
+	if (numSamples > 0) {                                                         // :171-181
+		b.z = b.y / ((float)numSamples * b.x);
+	} else {
+		b.z = 0.0f;
+		b.y = 0.0f;
+	}
+	o[1] = b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,23 +580,6 @@ __global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir
 		q.w = 255;
 		reinterpret_cast<uchar4 *>(outPixels)[pix] = q;
 	}
-}
-
-// ------------------------------------------------------------------------------------------------
-// stand-alone testVisibility over a list of segments
-__global__ void __launch_bounds__(kThreads) trace_segments_kernel(SceneView sc, const float *__restrict__ p1, const float *__restrict__ p2,
-                                                                 unsigned long long n, unsigned char *__restrict__ shadowed,
-                                                                 unsigned long long *counters) {
-	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned overflow = 0, rays = 0;
-	if (i < n) {
-		f3 a = mk3(p1[i * 3], p1[i * 3 + 1], p1[i * 3 + 2]);
-		f3 b = mk3(p2[i * 3], p2[i * 3 + 1], p2[i * 3 + 2]);
-		shadowed[i] = test_visibility(sc, a, b, overflow) ? 1 : 0;
-		rays = 1;
-	}
-	add_counter(counters, kCounterRays, rays);
-	add_counter(counters, kCounterOverflow, overflow);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,25 +735,30 @@ static dim3 tile_grid(const Band &b) {
 	return dim3((unsigned)((b.W + kTileW - 1) / kTileW), (unsigned)((b.rowEnd - b.rowBegin + kTileH - 1) / kTileH), 1);
 }
 
-void launch_restir_omni(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, cudaStream_t s) {
-	restir_omni_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out, prev);
+PassGrid pass_grid(const Band &b) {
+	dim3 g = tile_grid(b);
+	return PassGrid{g.x, g.y, g.x * 4u, 256ull * g.x * g.y};
+}
+
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s) {
+	omni_candidates_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
+}
+void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s) {
+	LcgJump jump = lcg_jump((uint64_t)p.u.initialLightSampleCount * draws_per_candidate(p.scene.pointCount != 0));
+	omni_temporal_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out, prev, shadowed, jump);
 }
 void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s) {
 	spatial_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter);
 }
-void launch_unbiased_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, cudaStream_t s) {
-	unbiased_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors);
+void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix, cudaStream_t s) {
+	unbiased_merge_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix);
+}
+void launch_unbiased_finalize(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, const int *neighborPix,
+                              const unsigned char *shadowed, cudaStream_t s) {
+	unbiased_finalize_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix, shadowed);
 }
 void launch_lighting(const PassParams &p, const restir_lighting_uniforms &lu, const PackedReservoir *res, void *out, int fmt, cudaStream_t s) {
 	lighting_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, lu, res, out, fmt);
-}
-void launch_trace_segments(const SceneView &sc, const float *p1, const float *p2, unsigned long long n, unsigned char *shadowed,
-                           unsigned long long *counters, cudaStream_t s) {
-	if (n == 0) {
-		return;
-	}
-	unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
-	trace_segments_kernel<<<blocks, kThreads, 0, s>>>(sc, p1, p2, n, shadowed, counters);
 }
 void launch_raycast_gbuffer(const SceneView &sc, const Band &band, const RaycastCamera &cam, const int *triMaterial, const uint4 *materialTable,
                             void *albedo, void *normal, void *material, void *worldPos, void *depth, cudaStream_t s) {

@@ -12,12 +12,47 @@ struct RaycastCamera {
 	float pv[16];
 };
 
-void launch_restir_omni(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, cudaStream_t s);
+// ---- the persistent shadow-ray kernel (restir_trace.cu) ---------------------------------------------------
+enum TraceMode {
+	kTracePixel = 0,    // one ray per pixel: G-buffer position -> reservoir sample (restirOmni.glsl:148-160)
+	kTraceUnbiased = 1, // `slots` rays per pixel: slots-1 neighbour positions and the pixel itself -> sample (unbiasedReuse.glsl:126-166)
+	kTraceSegments = 2, // explicit segments (restir_trace_segments)
+};
+struct TraceParams {
+	const float4 *nodes, *tris, *wide; // wide == null: reference-order traversal only
+	Band band;
+	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)
+	unsigned slots;
+	unsigned long long nItems;
+	const float4 *worldPos;
+	const PackedReservoir *reservoirs; // sample positions = ray targets
+	const int *neighborPix;            // [pixel id][slots-1]: local pixel index of the neighbour, < 0 = no ray
+	const float *segP1, *segP2;
+	unsigned char *shadowed;           // [item]: 1 = shadowed
+	unsigned long long *counters;
+};
+cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);
+
+// ---- per-pixel kernels (restir_kernels.cu) ---------------------------------------------------------------
+// Grid geometry shared by every per-pixel kernel and the trace kernel's item numbering.
+struct PassGrid {
+	unsigned gx, gy;     // CTAs (32x8 pixels each)
+	unsigned tilesX;     // 8x4 tiles per tile row = 4 * gx
+	unsigned long long pixelIds; // tile-ordered pixel ids = 256 * gx * gy (ids past the band edge are holes)
+};
+PassGrid pass_grid(const Band &b);
+
+// restirOmni.glsl:108-142 (candidates) and :148-209 (apply visibility, temporal reuse); between the two the
+// trace kernel runs in kTracePixel mode on `out`.
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s);
+void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s);
 void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s);
-void launch_unbiased_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, cudaStream_t s);
+// unbiasedReuse.glsl:84-124 (merge) and :126-182 (normalisation from the visibility bits); the trace kernel
+// runs in kTraceUnbiased mode between them.
+void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix, cudaStream_t s);
+void launch_unbiased_finalize(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, const int *neighborPix,
+                              const unsigned char *shadowed, cudaStream_t s);
 void launch_lighting(const PassParams &p, const restir_lighting_uniforms &lu, const PackedReservoir *res, void *out, int fmt, cudaStream_t s);
-void launch_trace_segments(const SceneView &sc, const float *p1, const float *p2, unsigned long long n, unsigned char *shadowed,
-                           unsigned long long *counters, cudaStream_t s);
 void launch_raycast_gbuffer(const SceneView &sc, const Band &band, const RaycastCamera &cam, const int *triMaterial, const uint4 *materialTable,
                             void *albedo, void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
 void launch_unpack_reservoirs(const SceneView &sc, const PackedReservoir *in, restir_reservoir *out, size_t n, cudaStream_t s);

@@ -87,6 +87,44 @@ def test_shadow_rays_bit_exact(name, n_rays):
     ctx.close()
 
 
+def test_traversal_modes_agree_and_report():
+    """The 4-wide re-layout and the reference-order walk of the same uploaded tree give the same bits; a tree
+    whose child indices are out of range is rejected at upload instead of being traversed."""
+    torch = _torch()
+    scene = _scene("procedural:tri")
+    rng = np.random.default_rng(5)
+    n = 200_000
+    lo, hi = scene.dims[:3], scene.dims[3:]
+    p1 = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    p2 = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    outs = []
+    for mode in (capi.RESTIR_TRAVERSAL_AUTO, capi.RESTIR_TRAVERSAL_REFERENCE_ORDER):
+        ctx = capi.RestirContext(0)
+        ctx.set_traversal(mode)
+        ctx.upload_bvh(scene.nodes, scene.triangles)
+        info = ctx.bvh_info()
+        if mode == capi.RESTIR_TRAVERSAL_AUTO:
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE and info["unfolded_nodes"] == 0
+            assert info["wide_nodes"] + info["folded_nodes"] == scene.nodes.shape[0]
+        else:
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_REFERENCE_ORDER and info["wide_nodes"] == 0
+        out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ctx.trace_segments(d1, d2, n, out)
+        ctx.synchronize()
+        outs.append(out.cpu().numpy())
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1])
+    want = ph.oracle().trace_segments(ph.oracle_scene(scene), p1, p2)
+    assert np.array_equal(outs[0], want)
+    bad = scene.nodes.copy()
+    bad.view(np.int32).reshape(-1, 20)[0, 16] = bad.shape[0] + 7
+    ctx = capi.RestirContext(0)
+    with pytest.raises(capi.RestirError, match="out of range"):
+        ctx.upload_bvh(bad, scene.triangles)
+    ctx.close()
+
+
 # ---- fixture tool ---------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("name", ["procedural:tri", "cornellBox", "sponza"])
