@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--reference-rows", type=int, default=48, help="rows per step of the --impl reference arm")
     ap.add_argument("--traversal", default="auto", choices=["auto", "reference-order"],
-                    help="reference-order: walk the 80-byte nodes in the shader's own order (A/B against the 4-wide re-layout)")
+                    help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -409,7 +409,7 @@ def main():
     rays_prof = ctx.counters(reset=True)["shadow_rays"] / reps
     peak, peak_src = peaks()
     info = ctx.bvh_info()
-    bvh_bytes = (info["wide_nodes"] * 128 if info["wide_nodes"] else scene.nodes.size) + scene.triangles.size
+    bvh_bytes = (info["nodes"] * 64 if info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE else scene.nodes.size) + scene.triangles.size
     light_bytes = scene.point_blob.size + scene.tri_blob.size + scene.alias_blob.size
     k = cfg["neighbors"]
     # algorithmic bytes per launch of each kernel: every input read once, every output written once

@@ -104,25 +104,31 @@ int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_unif
 int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
 
 /* Shadow-ray traversal.  The uploaded tree is always the reference's (aabbTreeBuilder node / triangle
- * layout).  AUTO (default): restir_upload_bvh also derives a 4-wide re-layout of the same tree and the trace
- * kernel walks that — same visibility bits, see csrc/wide_bvh.h for why — unless the tree fails the checks
- * that make it exact (then REFERENCE_ORDER is used and restir_get_bvh_info says so).  REFERENCE_ORDER: walk
- * the 80-byte nodes in softwareRaytracing.glsl:39-85's own order, 32-entry stack, dropped pushes counted.
- * Takes effect at the next restir_upload_bvh. */
+ * layout) and is always walked in softwareRaytracing.glsl:39-85's own order.  AUTO (default):
+ * restir_upload_bvh keeps a device copy of the same nodes re-strided to 64 bytes (four 16-byte loads from one
+ * line instead of five that straddle lines) and, having checked that the reference's 32-entry stack cannot
+ * overflow on this tree, drops the per-push bound check.  REFERENCE_ORDER: walk the 80-byte nodes literally,
+ * dropped pushes counted — also what AUTO falls back to when the stack could overflow
+ * (restir_get_bvh_info tells).  Takes effect at the next restir_upload_bvh.  Uploads whose child indices are
+ * out of range or that are not trees are rejected with RESTIR_E_INVALID. */
 #define RESTIR_TRAVERSAL_AUTO 0
 #define RESTIR_TRAVERSAL_REFERENCE_ORDER 1
-#define RESTIR_TRAVERSAL_WIDE 2 /* reported by restir_get_bvh_info only */
+#define RESTIR_TRAVERSAL_IMAGE 2 /* reported by restir_get_bvh_info only */
 int restir_set_traversal(restir_context *ctx, int mode);
 
 typedef struct restir_bvh_info {
 	uint32_t nodes, triangles;
-	uint32_t wide_nodes, wide_depth;      /* 0 when the reference-order traversal is in use */
-	uint32_t folded_nodes, unfolded_nodes; /* binary nodes folded into their parent / kept because nesting failed */
-	uint32_t reference_stack_bound;        /* worst-case occupancy of the reference's 32-entry stack on this tree */
-	uint32_t wide_stack_bound;
-	int32_t traversal;                     /* RESTIR_TRAVERSAL_WIDE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
+	uint32_t reachable_nodes, depth;
+	uint32_t reference_stack_bound; /* worst-case occupancy of the reference's 32-entry stack on this tree */
+	int32_t traversal;              /* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
 } restir_bvh_info;
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
+/* The same checks restir_upload_bvh runs, on the host and without a context (no GPU needed): RESTIR_E_INVALID
+ * and a message for an upload that would be rejected; otherwise RESTIR_OK, `out` filled (traversal says which
+ * walk such an upload would get) and, for the reference-order fallback, the reason in `message`.  The
+ * reference itself checks nothing (its only assert is dummyRoot == 0, src/aabbTreeBuilder.cpp:212). */
+int restir_check_aabb_tree(const void *nodes, uint32_t n_nodes, uint32_t n_triangles, restir_bvh_info *out, char *message,
+                           size_t message_bytes);
 
 /* ---- the passes ---------------------------------------------------------------------------------- */
 

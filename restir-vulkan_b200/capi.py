@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RESTIR_B200_LIB") or os.path.join(_HERE, "librestir_b
 RESTIR_BUF_FRAME0, RESTIR_BUF_FRAME1, RESTIR_BUF_TEMP = 0, 1, 2
 RESTIR_OUT_RGBA32F, RESTIR_OUT_RGBA8_SRGB = 0, 1
 RESTIR_VISIBILITY_REUSE_FLAG, RESTIR_TEMPORAL_REUSE_FLAG = 1, 2
-RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_WIDE = 0, 1, 2
+RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_IMAGE = 0, 1, 2
 
 RESERVOIR_DTYPE = np.dtype(
     [
@@ -61,7 +61,7 @@ EXPORTS = [
     "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
-    "restir_set_traversal", "restir_get_bvh_info", "restir_profile_begin", "restir_profile_end",
+    "restir_set_traversal", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_collect_triangle_lights",
@@ -79,8 +79,7 @@ class Counters(C.Structure):
 
 
 class BvhInfo(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("nodes", "triangles", "wide_nodes", "wide_depth", "folded_nodes", "unfolded_nodes",
-                                          "reference_stack_bound", "wide_stack_bound")] + [("traversal", C.c_int32)]
+    _fields_ = [(n, C.c_uint32) for n in ("nodes", "triangles", "reachable_nodes", "depth", "reference_stack_bound")] + [("traversal", C.c_int32)]
 
 
 class KernelTime(C.Structure):
@@ -159,6 +158,14 @@ def build_aabb_tree(triangles):
     if rc != 0:
         raise RestirError(f"restir_build_aabb_tree failed ({rc})")
     return nodes
+
+
+def check_aabb_tree(nodes, n_triangles):
+    """restir_check_aabb_tree: (rc, info dict, message).  Host only."""
+    nodes = np.ascontiguousarray(nodes).view(np.uint8).reshape(-1, 80)
+    info, msg = BvhInfo(), C.create_string_buffer(256)
+    rc = load_library().restir_check_aabb_tree(_hp(nodes), C.c_uint32(nodes.shape[0]), C.c_uint32(n_triangles), C.byref(info), msg, C.c_size_t(256))
+    return rc, {n: getattr(info, n) for n, _ in BvhInfo._fields_}, msg.value.decode()
 
 
 def collect_triangle_lights(triangles, tri_material, material_emissive):

@@ -13,7 +13,7 @@
 
 #include "../../include/restir_b200.h"
 #include "restir_kernels.h"
-#include "wide_bvh.h"
+#include "traversal_image.h"
 
 using namespace restir;
 
@@ -26,8 +26,8 @@ struct restir_context {
 
 	// scene
 	float4 *nodes = nullptr, *tris = nullptr;
-	float4 *wide = nullptr; // 4-wide re-layout of `nodes` (wide_bvh.h); null => reference-order traversal
-	WideBvhInfo wideInfo;
+	float4 *image = nullptr; // 64-byte re-stride of `nodes` (traversal_image.h); null => literal 80-byte walk
+	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
 	int smCount = 0;
 	unsigned char *pointBlob = nullptr, *triBlob = nullptr, *aliasBlob = nullptr;
@@ -125,7 +125,7 @@ SceneView sceneView(const restir_context *ctx) {
 	SceneView v{};
 	v.nodes = ctx->nodes;
 	v.tris = ctx->tris;
-	v.wide = ctx->wide;
+	v.image = ctx->image;
 	v.pointLights = ctx->pointBlob ? reinterpret_cast<const restir_point_light *>(ctx->pointBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.triLights = ctx->triBlob ? reinterpret_cast<const restir_tri_light *>(ctx->triBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.alias = ctx->aliasBlob ? reinterpret_cast<const restir_alias_column *>(ctx->aliasBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
@@ -229,7 +229,7 @@ TraceParams traceParams(const restir_context *ctx) {
 	TraceParams tp{};
 	tp.nodes = ctx->nodes;
 	tp.tris = ctx->tris;
-	tp.wide = ctx->wide;
+	tp.image = ctx->image;
 	tp.band = ctx->band;
 	tp.shadowed = ctx->shadowed;
 	tp.counters = ctx->counters;
@@ -296,7 +296,7 @@ void restir_destroy(restir_context *ctx) {
 	dropProfile(ctx);
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
-	freeDev(ctx->wide);
+	freeDev(ctx->image);
 	freeDev(ctx->shadowed);
 	freeDev(ctx->neighborPix);
 	freeDev(ctx->pointBlob);
@@ -330,30 +330,30 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: empty tree");
 	}
 	// Child indices are checked here (the kernels trust them) and the traversal image is derived: the same
-	// tree, 4 wide, only where the nesting that makes the fold exact holds (wide_bvh.h).
-	std::vector<WideNode> wide;
-	WideBvhInfo info;
+	// tree at a 64-byte stride (traversal_image.h).
+	std::vector<Node64> image;
+	TraversalImageInfo info;
 	std::string why;
-	if (!build_wide_bvh(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, wide, info, why)) {
+	if (!build_traversal_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, image, info, why)) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: %s", why.c_str());
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
-	freeDev(ctx->wide);
+	freeDev(ctx->image);
 	ctx->nNodes = ctx->nTris = 0;
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
 	CU(ctx, cudaMalloc(&ctx->tris, (size_t)n_triangles * sizeof(restir_triangle)));
 	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
 	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, (size_t)n_triangles * sizeof(restir_triangle), cudaMemcpyHostToDevice, ctx->stream));
 	if (info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER) {
-		CU(ctx, cudaMalloc(&ctx->wide, wide.size() * sizeof(WideNode)));
-		CU(ctx, cudaMemcpyAsync(ctx->wide, wide.data(), wide.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
+		CU(ctx, cudaMalloc(&ctx->image, image.size() * sizeof(Node64)));
+		CU(ctx, cudaMemcpyAsync(ctx->image, image.data(), image.size() * sizeof(Node64), cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->nNodes = n_nodes;
 	ctx->nTris = n_triangles;
-	ctx->wideInfo = info;
+	ctx->imageInfo = info;
 	return RESTIR_OK;
 }
 
@@ -532,14 +532,37 @@ int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out) {
 	std::memset(out, 0, sizeof(*out));
 	out->nodes = ctx->nNodes;
 	out->triangles = ctx->nTris;
-	out->wide_nodes = ctx->wide ? ctx->wideInfo.wideNodes : 0;
-	out->wide_depth = ctx->wide ? (uint32_t)ctx->wideInfo.wideDepth : 0;
-	out->folded_nodes = ctx->wide ? ctx->wideInfo.foldedNodes : 0;
-	out->unfolded_nodes = ctx->wide ? ctx->wideInfo.keptUnfolded : 0;
-	out->reference_stack_bound = (uint32_t)ctx->wideInfo.referenceStackBound;
-	out->wide_stack_bound = (uint32_t)ctx->wideInfo.wideStackBound;
-	out->traversal = ctx->wide ? RESTIR_TRAVERSAL_WIDE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	out->reachable_nodes = ctx->imageInfo.reachableNodes;
+	out->depth = (uint32_t)ctx->imageInfo.depth;
+	out->reference_stack_bound = (uint32_t)ctx->imageInfo.referenceStackBound;
+	out->traversal = ctx->image ? RESTIR_TRAVERSAL_IMAGE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
 	return RESTIR_OK;
+}
+
+int restir_check_aabb_tree(const void *nodes, uint32_t n_nodes, uint32_t n_triangles, restir_bvh_info *out, char *message, size_t message_bytes) {
+	if (message && message_bytes) message[0] = 0;
+	if (nodes == nullptr || n_nodes == 0 || n_triangles == 0) {
+		return RESTIR_E_INVALID;
+	}
+	std::vector<Node64> image;
+	TraversalImageInfo info;
+	std::string why;
+	bool ok = build_traversal_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, image, info, why);
+	const std::string &text = ok ? info.why : why;
+	if (message && message_bytes) {
+		std::strncpy(message, text.c_str(), message_bytes - 1);
+		message[message_bytes - 1] = 0;
+	}
+	if (out) {
+		std::memset(out, 0, sizeof(*out));
+		out->nodes = n_nodes;
+		out->triangles = n_triangles;
+		out->reachable_nodes = info.reachableNodes;
+		out->depth = (uint32_t)info.depth;
+		out->reference_stack_bound = (uint32_t)info.referenceStackBound;
+		out->traversal = info.usable ? RESTIR_TRAVERSAL_IMAGE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	}
+	return ok ? RESTIR_OK : RESTIR_E_INVALID;
 }
 
 int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int prev_buffer) {
@@ -608,6 +631,9 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	const PassGrid g = pass_grid(ctx->band);
 	const unsigned k = ctx->unbiasedNeighbors;
 	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
+	if (g.pixelIds * (k + 1) >= (1ull << 32)) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "unbiased pass: %llu rays exceed the trace kernel's 32-bit work list; use row bands", (unsigned long long)(g.pixelIds * (k + 1)));
+	}
 	if ((rc = ensureHandOver(ctx, g, k + 1, k)) != RESTIR_OK) return rc;
 	const PackedReservoir *in = ctx->reservoirs[in_buffer];
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
@@ -736,14 +762,20 @@ int restir_trace_segments(restir_context *ctx, const float *p1, const float *p2,
 	if (n == 0) {
 		return RESTIR_OK;
 	}
-	TraceParams tp = traceParams(ctx);
-	tp.nItems = n;
-	tp.segP1 = p1;
-	tp.segP2 = p2;
-	tp.shadowed = shadowed;
-	beforeLaunch(ctx, "trace_kernel");
-	CU(ctx, launch_trace(tp, kTraceSegments, ctx->smCount, ctx->stream));
-	return afterLaunch(ctx, "trace_kernel");
+	// the kernel numbers its work items with 32 bits: longer lists go in slices
+	const uint64_t slice = 1ull << 31;
+	for (uint64_t first = 0; first < n; first += slice) {
+		TraceParams tp = traceParams(ctx);
+		tp.nItems = n - first < slice ? n - first : slice;
+		tp.segP1 = p1 + first * 3;
+		tp.segP2 = p2 + first * 3;
+		tp.shadowed = shadowed + first;
+		beforeLaunch(ctx, "trace_kernel");
+		CU(ctx, launch_trace(tp, kTraceSegments, ctx->smCount, ctx->stream));
+		int rc = afterLaunch(ctx, "trace_kernel");
+		if (rc != RESTIR_OK) return rc;
+	}
+	return RESTIR_OK;
 }
 
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {

@@ -24,7 +24,7 @@ static_assert(sizeof(PackedReservoir) == 32, "packed reservoir is 32 bytes");
 struct SceneView {
 	const float4 *nodes;       // reference layout, 5 x float4 per node (80 B)
 	const float4 *tris;        // reference layout, 3 x float4 per triangle (48 B)
-	const float4 *wide;        // derived at upload (wide_bvh.h): 8 x float4 per 4-wide node (128 B); null => reference-order traversal
+	const float4 *image;       // derived at upload (traversal_image.h): the same nodes re-strided to 4 x float4 (64 B); null => literal 80-byte walk
 	const restir_point_light *pointLights;
 	const restir_tri_light *triLights;
 	const restir_alias_column *alias;

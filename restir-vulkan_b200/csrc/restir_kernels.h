@@ -19,7 +19,7 @@ enum TraceMode {
 	kTraceSegments = 2, // explicit segments (restir_trace_segments)
 };
 struct TraceParams {
-	const float4 *nodes, *tris, *wide; // wide == null: reference-order traversal only
+	const float4 *nodes, *tris, *image; // image == null: literal walk of the 80-byte nodes (restir_trace.cuh)
 	Band band;
 	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)
 	unsigned slots;

@@ -3,7 +3,7 @@
 //   segment_setup / test_visibility   <- src/shaders/include/visibilityTest.glsl:1-4, 27-28 (software branch)
 //   ray_box_reference, ray_triangle   <- src/shaders/include/softwareRaytracing.glsl:9-14, 15-37
 //   trace_any_reference               <- softwareRaytracing.glsl:39-85, in the reference's node order
-//   wide_step                         one visit of the 4-wide re-layout (wide_bvh.h) — same answer, see there
+//   trace_any_image                   the same walk over the 64-byte re-stride of the same tree (traversal_image.h)
 #pragma once
 
 #include "restir_device.cuh"
@@ -47,8 +47,8 @@ __device__ __forceinline__ bool ray_triangle(const float4 *__restrict__ tris, in
 // triangles the segment intersects, so triangles are tested as soon as their leaf box is hit instead of
 // being deferred in batches of 8 node visits.  The stack is the reference's 32 entries with its push order
 // (left, then right); a push onto a full stack is dropped and counted (UB in the reference).  Returns true
-// when nothing is hit.  This is the path for rays whose 1/dir is not finite and for trees the 4-wide
-// re-layout does not cover.
+// when nothing is hit.  This literal path serves trees whose worst-case stack occupancy exceeds 32
+// (traversal_image.h) and RESTIR_TRAVERSAL_REFERENCE_ORDER.
 static __device__ __noinline__ bool trace_any_reference(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, f3 o, f3 d, unsigned &overflow) {
 	int stack[32];
 	int top = 1;
@@ -102,73 +102,52 @@ __device__ __forceinline__ bool test_visibility_reference(const SceneView &sc, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// 4-wide traversal state of one lane.
-constexpr int kWideStack = 32;
-
-struct WideRay {
-	f3 o, d, inv;
-	int nearX, nearY, nearZ; // float4 index of the near plane set per axis inside a WideNode (axis + 3 * (inv < 0))
-};
-
-__device__ __forceinline__ void wide_ray_init(WideRay &r, f3 o, f3 d, f3 inv) {
-	r.o = o;
-	r.d = d;
-	r.inv = inv;
-	r.nearX = inv.x < 0.0f ? 3 : 0;
-	r.nearY = inv.y < 0.0f ? 4 : 1;
-	r.nearZ = inv.z < 0.0f ? 5 : 2;
-}
-
-// With finite non-zero 1/dir and lo <= hi the reference's min(t1,t2) / max(t1,t2) are the near / far plane
-// distances selected by the sign of 1/dir — bit for bit, since (b - o) * inv is monotone in b.
-__device__ __forceinline__ bool wide_slab(const WideRay &r, float nx, float ny, float nz, float fx, float fy, float fz) {
-	float tn = fmaxf((nx - r.o.x) * r.inv.x, fmaxf((ny - r.o.y) * r.inv.y, (nz - r.o.z) * r.inv.z));
-	float tf = fminf((fx - r.o.x) * r.inv.x, fminf((fy - r.o.y) * r.inv.y, (fz - r.o.z) * r.inv.z));
-	return tn < 1.0f && tf >= tn && tf > 0.0f;
-}
-
-enum WideStepResult { kWideContinue = 0, kWideMiss = 1, kWideHit = 2, kWideStackFull = 3 };
-
-// Visits wide node `cur`: tests its four boxes, tests the triangles of hit leaf slots at once, makes the
-// first hit inner slot the next node and pushes the others.
-__device__ __forceinline__ int wide_step(const float4 *__restrict__ wide, const float4 *__restrict__ tris, const WideRay &r, int &cur, int *stack,
-                                         int &top) {
-	const float4 *n = wide + (size_t)cur * 8;
-	float4 nx = __ldg(n + r.nearX), ny = __ldg(n + r.nearY), nz = __ldg(n + r.nearZ);
-	float4 fx = __ldg(n + (3 - r.nearX)), fy = __ldg(n + (5 - r.nearY)), fz = __ldg(n + (7 - r.nearZ));
-	int4 ch = __ldg(reinterpret_cast<const int4 *>(n + 6));
-	unsigned hit = 0;
-	hit |= wide_slab(r, nx.x, ny.x, nz.x, fx.x, fy.x, fz.x) ? 1u : 0u;
-	hit |= wide_slab(r, nx.y, ny.y, nz.y, fx.y, fy.y, fz.y) ? 2u : 0u;
-	hit |= wide_slab(r, nx.z, ny.z, nz.z, fx.z, fy.z, fz.z) ? 4u : 0u;
-	hit |= wide_slab(r, nx.w, ny.w, nz.w, fx.w, fy.w, fz.w) ? 8u : 0u;
-	unsigned leaf = (ch.x < 0 ? 1u : 0u) | (ch.y < 0 ? 2u : 0u) | (ch.z < 0 ? 4u : 0u) | (ch.w < 0 ? 8u : 0u);
-	unsigned lh = hit & leaf;
-	while (lh) {
-		int c = __ffs(lh) - 1;
-		lh &= lh - 1;
-		int id = c == 0 ? ch.x : (c == 1 ? ch.y : (c == 2 ? ch.z : ch.w));
-		if (ray_triangle(tris, ~id, r.o, r.d)) {
-			return kWideHit;
+// The same walk over the 64-byte re-stride of the same tree (traversal_image.h): four 16-byte loads per node
+// from one 128-byte line.  Only used when the tree's worst-case stack occupancy is <= 32 (checked at upload),
+// so no push can be dropped and the stack needs no bound checks; the node about to be visited stays in a
+// register instead of going through the stack.  Order of visits and triangle tests is the reference's: left
+// box, right box, then the right child before the left one.  Returns true when nothing is hit.
+__device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image, const float4 *__restrict__ tris, f3 o, f3 d) {
+	int stack[32];
+	int top = 0, cur = 0;
+	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	for (;;) {
+		const float4 *n = image + (unsigned)cur * 4u;
+		float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
+		int4 ch = __ldg(reinterpret_cast<const int4 *>(n + 3));
+		bool hl = ray_box_reference(o, inv, make_float4(a.x, a.y, a.z, 0.0f), make_float4(a.w, b.x, b.y, 0.0f));
+		bool hr = ray_box_reference(o, inv, make_float4(b.z, b.w, c.x, 0.0f), make_float4(c.y, c.z, c.w, 0.0f));
+		// hit leaves: left first, then right (most visits have none: one branch skips the whole block)
+		int t0 = (hl && ch.x < 0) ? ~ch.x : -1, t1 = (hr && ch.y < 0) ? ~ch.y : -1;
+		if ((t0 & t1) >= 0) { // at least one of them is a triangle index
+			if (t0 < 0) {
+				t0 = t1;
+				t1 = -1;
+			}
+#pragma unroll 1
+			do {
+				if (ray_triangle(tris, t0, o, d)) {
+					return false;
+				}
+				t0 = t1;
+				t1 = -1;
+			} while (t0 >= 0);
+		}
+		bool il = hl && ch.x >= 0, ir = hr && ch.y >= 0;
+		if (ir) {
+			if (il) {
+				stack[top++] = ch.x;
+			}
+			cur = ch.y;
+		} else if (il) {
+			cur = ch.x;
+		} else {
+			if (top == 0) {
+				return true;
+			}
+			cur = stack[--top];
 		}
 	}
-	unsigned ih = hit & ~leaf;
-	if (ih == 0) {
-		if (top == 0) {
-			return kWideMiss;
-		}
-		cur = stack[--top];
-		return kWideContinue;
-	}
-	if (top + 3 > kWideStack) {
-		return kWideStackFull;
-	}
-	bool first = true;
-	if (ih & 1u) { cur = ch.x; first = false; }
-	if (ih & 2u) { if (first) { cur = ch.y; first = false; } else { stack[top++] = ch.y; } }
-	if (ih & 4u) { if (first) { cur = ch.z; first = false; } else { stack[top++] = ch.z; } }
-	if (ih & 8u) { if (first) { cur = ch.w; } else { stack[top++] = ch.w; } }
-	return kWideContinue;
 }
 
 } // namespace restir

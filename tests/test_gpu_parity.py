@@ -88,7 +88,7 @@ def test_shadow_rays_bit_exact(name, n_rays):
 
 
 def test_traversal_modes_agree_and_report():
-    """The 4-wide re-layout and the reference-order walk of the same uploaded tree give the same bits; a tree
+    """The 64-byte re-stride and the literal 80-byte walk of the same uploaded tree give the same bits; a tree
     whose child indices are out of range is rejected at upload instead of being traversed."""
     torch = _torch()
     scene = _scene("procedural:tri")
@@ -105,10 +105,10 @@ def test_traversal_modes_agree_and_report():
         ctx.upload_bvh(scene.nodes, scene.triangles)
         info = ctx.bvh_info()
         if mode == capi.RESTIR_TRAVERSAL_AUTO:
-            assert info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE and info["unfolded_nodes"] == 0
-            assert info["wide_nodes"] + info["folded_nodes"] == scene.nodes.shape[0]
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE
+            assert info["reachable_nodes"] == scene.nodes.shape[0] and info["reference_stack_bound"] <= 32
         else:
-            assert info["traversal"] == capi.RESTIR_TRAVERSAL_REFERENCE_ORDER and info["wide_nodes"] == 0
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_REFERENCE_ORDER
         out = torch.zeros(n, dtype=torch.uint8, device="cuda")
         ctx.trace_segments(d1, d2, n, out)
         ctx.synchronize()
