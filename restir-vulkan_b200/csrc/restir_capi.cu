@@ -590,9 +590,9 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 		tp.nItems = g.pixelIds;
 		tp.worldPos = p.cur.worldPos;
 		tp.reservoirs = out;
-		beforeLaunch(ctx, "trace_kernel");
+		beforeLaunch(ctx, "trace_kernel<pixel>");
 		CU(ctx, launch_trace(tp, kTracePixel, ctx->smCount, ctx->stream));
-		if ((rc = afterLaunch(ctx, "trace_kernel")) != RESTIR_OK) return rc;
+		if ((rc = afterLaunch(ctx, "trace_kernel<pixel>")) != RESTIR_OK) return rc;
 	}
 	if (vis || temporal) {
 		beforeLaunch(ctx, "omni_temporal_kernel");
@@ -648,9 +648,9 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 		tp.worldPos = p.cur.worldPos;
 		tp.reservoirs = out;
 		tp.neighborPix = ctx->neighborPix;
-		beforeLaunch(ctx, "trace_kernel");
+		beforeLaunch(ctx, "trace_kernel<unbiased>");
 		CU(ctx, launch_trace(tp, kTraceUnbiased, ctx->smCount, ctx->stream));
-		if ((rc = afterLaunch(ctx, "trace_kernel")) != RESTIR_OK) return rc;
+		if ((rc = afterLaunch(ctx, "trace_kernel<unbiased>")) != RESTIR_OK) return rc;
 	}
 	beforeLaunch(ctx, "unbiased_finalize_kernel");
 	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
@@ -770,9 +770,9 @@ int restir_trace_segments(restir_context *ctx, const float *p1, const float *p2,
 		tp.segP1 = p1 + first * 3;
 		tp.segP2 = p2 + first * 3;
 		tp.shadowed = shadowed + first;
-		beforeLaunch(ctx, "trace_kernel");
+		beforeLaunch(ctx, "trace_kernel<segments>");
 		CU(ctx, launch_trace(tp, kTraceSegments, ctx->smCount, ctx->stream));
-		int rc = afterLaunch(ctx, "trace_kernel");
+		int rc = afterLaunch(ctx, "trace_kernel<segments>");
 		if (rc != RESTIR_OK) return rc;
 	}
 	return RESTIR_OK;
