@@ -187,6 +187,7 @@ def run_reference_arm(args):
     pkg = graft.load_package()
     capi, fixtures = pkg.capi, pkg.fixtures
     po = graft.load_oracle()
+    po.set_num_threads(os.cpu_count() or 1)               # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
     cfg = CONFIGS[args.config]
     scene, cam_key, label = load_scene(fixtures, cfg)
     w, h = cfg["size"]
@@ -252,6 +253,12 @@ def main():
         if rank == 0:
             run_reference_arm(args)
         return 0
+
+    # fd 1 carries exactly one JSON line: everything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
 
     import torch
     import torch.distributed as dist
@@ -547,7 +554,8 @@ def main():
             "gpu_launches": int(launches), "halo_misses": int(halo_misses), "stack_overflows": int(overflows),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity_sample": parity,
         }
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -263,3 +263,7 @@ def raycast_gbuffer(scene, tri_material, material_table, cam, w, h, rows=None):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(C.c_int(int(n)))

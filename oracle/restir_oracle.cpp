@@ -1037,6 +1037,13 @@ void oracle_raycast_gbuffer(const oracle_scene *s, const int32_t *triMaterial, c
 	}
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py asks for every host core explicitly
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
 	return omp_get_max_threads();
