@@ -10,11 +10,17 @@
 //   src/shaders/include/structs/*.glsl (layouts: include/restir_layouts.h)
 // Each function cites the lines it restates.
 //
-// PARITY STATUS.  The reference has no tests, golden vectors or dump facility for this path
-//  and GLSL cannot be executed in this image, so the shader arithmetic below is
-// "parity unpinned" by the reference itself, except for: PCG32 (canonical pcg32 demo stream),
-// struct layouts, and — via oracle/_ref/scene_baker, which runs the reference's real C++ — the
-// BVH / light / alias-table inputs.  See DESIGN.md §Oracle.
+// PARITY STATUS: PINNED BY THE REFERENCE'S OWN SOURCE.  The reference has no tests, golden vectors or dump
+// facility for this path and no Vulkan/GLSL toolchain exists in this image, so the pin is
+// built here: oracle/ref_build compiles the reference's shader sources themselves (restirOmni.glsl,
+// spatialReuse.comp, unbiasedReuse.glsl, lighting.frag and their includes, from where they lie) as C++ into
+// oracle/_ref/libglslref.so, and tests/test_oracle_vs_glsl.py demands that this file reproduces that build bit
+// for bit — every reservoir field of every pixel over multi-frame sequences of cornellBox, Sponza, office and
+// procedural scenes, every visibility bit, every output colour.  Frame sequences made by that build are committed
+// as tests/golden/frames_*.npz (tests/make_golden_frames.py).  Also pinned: PCG32 (canonical pcg32 demo
+// stream), struct layouts, and — via oracle/_ref/scene_baker, which runs the reference's real C++ — the BVH /
+// light / alias-table inputs.  What stays a stated choice rather than a measured fact is the precision of the
+// GLSL built-ins a driver is free to pick (below); the shader build and this file share that one reading.
 //
 // ARITHMETIC POLICY (DESIGN.md §Arithmetic policy).  GLSL leaves the precision of '/', sqrt, pow,
 // sin, cos, normalize and FMA contraction to the driver.  This oracle fixes one IEEE-754 binary32

@@ -33,6 +33,21 @@ def oracle():
     return graft.load_oracle()
 
 
+def glsl_reference():
+    """TEST INFRASTRUCTURE: the reference's own shader sources compiled as C++ (oracle/pyglslref.py); None where
+    oracle/_ref/libglslref.so was never built (it is built wherever /root/reference exists and travels from there)."""
+    graft.load_oracle()
+    import importlib.util
+
+    if "pyglslref" not in sys.modules:
+        spec = importlib.util.spec_from_file_location("pyglslref", os.path.join(ROOT, "oracle", "pyglslref.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["pyglslref"] = mod
+        spec.loader.exec_module(mod)
+    mod = sys.modules["pyglslref"]
+    return mod if mod.available() else None
+
+
 def oracle_scene(scene):
     po = oracle()
     return po.Scene(scene.nodes, scene.triangles, scene.point_blob, scene.tri_blob, scene.alias_blob)
@@ -93,13 +108,15 @@ def to_capi_camera(cam):
 
 # ---- running both sides -----------------------------------------------------------------------------
 
-def run_oracle(case, rows=None):
-    """Returns per frame: dict(reservoirs=final (N,) RESERVOIR_DTYPE, initial=after restirOmni, rgba, rays)."""
+def run_oracle(case, rows=None, passes=None):
+    """Returns per frame: dict(reservoirs=final (N,) RESERVOIR_DTYPE, initial=after restirOmni, rgba, rays).
+    passes: the module providing the four passes — the oracle (default) or glsl_reference()."""
     po = oracle()
     sc = oracle_scene(case.scene)
+    data_po, po = po, (passes or po)
     gb = case.gbuffers()
     n = case.w * case.h
-    frame_bufs = [np.zeros(n, po.RESERVOIR_DTYPE), np.zeros(n, po.RESERVOIR_DTYPE)]  # app.h:264-284 zero-filled
+    frame_bufs = [np.zeros(n, data_po.RESERVOIR_DTYPE), np.zeros(n, data_po.RESERVOIR_DTYPE)]  # app.h:264-284 zero-filled
     out = []
     for f in range(len(case.cameras)):
         i, p = f & 1, (f & 1) ^ 1
@@ -110,10 +127,10 @@ def run_oracle(case, rows=None):
         prev = gb[f - 1] if f > 0 else None
         rays = 0
         initial, r = po.restir_pass(sc, u, cur, prev, frame_bufs[p], rows)
-        rays += r
+        rays += r or 0
         if case.unbiased:  # app.h:298-314
             final, r = po.unbiased_pass(sc, u, cur, initial, case.unbiased_neighbors, rows)
-            rays += r
+            rays += r or 0
             frame_bufs[i] = final
         else:              # app.h:316-332: the previous frame's buffer is the scratch of the spatial passes
             frame_bufs[i] = initial
