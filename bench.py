@@ -127,8 +127,12 @@ class ClockSampler:
 # the CPU arm: the oracle (a restatement of the reference's shaders; Vulkan/lavapipe does not exist in
 # this image) on all host cores, on a bounded row sample of the same workload
 
-def oracle_rows_sample(po, scene, cfg, cams, frame_inputs, target_seconds, rows_hint=None):
-    """Time the oracle's passes on a centred band of rows of frame index 1 (temporal active).
+def oracle_rows_sample(po, scene, cfg, cams, frame_inputs, target_seconds, rows_hint=None, passes=None):
+    """Time the CPU passes on a centred band of rows of frame index 1 (temporal active).
+
+    passes: the module whose passes are timed — the oracle port (default) or oracle/pyglslref.py, the reference's
+    own shader sources compiled for the CPU (then the rays are counted by the oracle afterwards, untimed: the two
+    are bit-identical, tests/test_oracle_vs_glsl.py).
 
     frame_inputs: dict(g_cur, g_prev, prev_reservoirs (64-byte, full frame), uniforms, lighting_uniforms).
     Returns dict with per-pass seconds scaled to the full frame, rays, rows, and the sampled reservoirs.
@@ -142,18 +146,23 @@ def oracle_rows_sample(po, scene, cfg, cams, frame_inputs, target_seconds, rows_
         y0 = max(0, h // 2 - rows // 2)
         y1 = min(h, y0 + rows)
         a0, a1 = max(0, y0 - HALO), min(h, y1 + HALO)
+        pm = passes or po
         t0 = time.perf_counter()
-        initial, rays_a = po.restir_pass(sc, u, frame_inputs["g_cur"], frame_inputs["g_prev"], frame_inputs["prev_reservoirs"], (a0, a1))
+        initial, rays_a = pm.restir_pass(sc, u, frame_inputs["g_cur"], frame_inputs["g_prev"], frame_inputs["prev_reservoirs"], (a0, a1))
         t1 = time.perf_counter()
         if cfg["unbiased"]:
-            final, rays_b = po.unbiased_pass(sc, u, frame_inputs["g_cur"], initial, cfg["neighbors"], (y0, y1))
+            final, rays_b = pm.unbiased_pass(sc, u, frame_inputs["g_cur"], initial, cfg["neighbors"], (y0, y1))
         else:
-            mid = po.spatial_pass(u, frame_inputs["g_cur"], initial, 0, (a0, a1))
-            final = po.spatial_pass(u, frame_inputs["g_cur"], mid, 1, (y0, y1))
+            mid = pm.spatial_pass(u, frame_inputs["g_cur"], initial, 0, (a0, a1))
+            final = pm.spatial_pass(u, frame_inputs["g_cur"], mid, 1, (y0, y1))
             rays_b = 0
         t2 = time.perf_counter()
-        po.lighting_pass(sc, lu, frame_inputs["g_cur"], final, (y0, y1))
+        pm.lighting_pass(sc, lu, frame_inputs["g_cur"], final, (y0, y1))
         t3 = time.perf_counter()
+        if pm is not po:                                   # count the rays of the same rows, untimed
+            _, rays_a = po.restir_pass(sc, u, frame_inputs["g_cur"], frame_inputs["g_prev"], frame_inputs["prev_reservoirs"], (a0, a1))
+            if cfg["unbiased"]:
+                _, rays_b = po.unbiased_pass(sc, u, frame_inputs["g_cur"], initial, cfg["neighbors"], (y0, y1))
         # scale each pass by the rows it actually covered
         t_restir = (t1 - t0) * h / (a1 - a0)
         if cfg["unbiased"]:
@@ -182,12 +191,28 @@ def make_uniform_blocks(capi, po_or_capi_matrix, cfg, w, h, cams, f):
     return u, lu
 
 
+def load_glsl_reference(cfg):
+    """oracle/_ref/libglslref.so (the reference's own shader sources compiled for the CPU, oracle/ref_build), or None
+    where it was never built or was not compiled for this neighbour count."""
+    import importlib.util
+    graft.load_oracle()
+    spec = importlib.util.spec_from_file_location("pyglslref", os.path.join(ROOT, "oracle", "pyglslref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules.setdefault("pyglslref", mod)
+    spec.loader.exec_module(mod)
+    if not mod.available() or (cfg["unbiased"] and cfg["neighbors"] not in (3, 5)):
+        return None
+    return mod
+
+
 def run_reference_arm(args):
-    """--impl reference: the CPU restatement alone, no CUDA code on the path."""
+    """--impl reference: the reference's CPU arm alone, no CUDA code on the path — its own shader sources compiled
+    for the host (oracle/_ref/libglslref.so) when that was built, else the oracle port."""
     pkg = graft.load_package()
     capi, fixtures = pkg.capi, pkg.fixtures
     po = graft.load_oracle()
     po.set_num_threads(os.cpu_count() or 1)               # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
+    gl = load_glsl_reference(CONFIGS[args.config])
     cfg = CONFIGS[args.config]
     scene, cam_key, label = load_scene(fixtures, cfg)
     w, h = cfg["size"]
@@ -207,7 +232,7 @@ def run_reference_arm(args):
         u, lu = make_uniform_blocks(capi, po.camera_matrix, cfg, w, h, cams, f)
         inputs = dict(g_cur=gbufs[f & 1], g_prev=gbufs[(f & 1) ^ 1] if f > 0 else None, prev_reservoirs=prev,
                       uniforms=u.astype(po.UNIFORMS_DTYPE), lighting_uniforms=lu.astype(po.LIGHTING_UNIFORMS_DTYPE))
-        r = oracle_rows_sample(po, scene, cfg, cams, inputs, 0.0, rows_hint=rows)
+        r = oracle_rows_sample(po, scene, cfg, cams, inputs, 0.0, rows_hint=rows, passes=gl)
         prev = r["final"]    # valid on the sampled rows, which is where the next step reprojects to
         if step >= args.warmup:
             times.append(r["frame_seconds"])
@@ -219,9 +244,11 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": mrays, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "ms_per_frame": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"{args.config}: {label} {w}x{h}", "note": "CPU restatement of the compute-shader path "
-                                        "(oracle/restir_oracle.cpp, OpenMP) — not lavapipe: no Vulkan in this image"},
-        "cpu_baseline": {"value": mrays, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_frame": ms},
+        "data": "synthetic", "config": {"workload": f"{args.config}: {label} {w}x{h}", "note": (
+            "the reference's own shader sources (restirOmni.glsl, unbiasedReuse.glsl / spatialReuse.comp, lighting.frag) compiled for "
+            "the host by g++ with OpenMP (oracle/_ref/libglslref.so)" if gl else "CPU restatement of the compute-shader path "
+            "(oracle/restir_oracle.cpp, OpenMP)") + " — not lavapipe: no Vulkan in this image"},
+        "cpu_baseline": {"value": mrays, "unit": UNIT, "cores": cores, "kind": "reference" if gl else "port", "sample": sample, "ms_per_frame": ms},
         "e2e": {"value": mrays, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
