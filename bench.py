@@ -484,17 +484,35 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_gb = [[p.cpu().pin_memory() for p in planes] for planes in gb]
-        host_out = torch.empty((rows_alloc, w, 4), dtype=torch.uint8).pin_memory()
+        # two images in flight: the device->host read of frame f runs on a side stream under frame f+1's passes, as the
+        # upload of frame f+1's G-buffer (the library's copy stream) runs under frame f's reuse pass
+        out_imgs = [out_rgba8, torch.zeros_like(out_rgba8)]
+        host_outs = [torch.empty((rows_alloc, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        side = torch.cuda.Stream()
+        copy_done = [None, None]
         h2d = sum(p.numel() * p.element_size() for p in host_gb[0])
-        d2h = host_out.numel()
+        d2h = host_outs[0].numel()
 
         def e2e_step(f):
             i = f & 1
-            ctx.upload_gbuffer(i, *host_gb[i])          # cudaMemcpyAsync x5 on the context's stream
+            ctx.upload_gbuffer(i, *host_gb[i])          # cudaMemcpyAsync x5 on the context's copy stream
             set_frame(f)
             renderer.frame(i, cfg["unbiased"], 1)
-            ctx.pass_lighting(i, i, out_rgba8, capi.RESTIR_OUT_RGBA8_SRGB)
-            host_out.copy_(out_rgba8, non_blocking=True)
+            if copy_done[i] is not None:
+                stream.wait_event(copy_done[i])           # image i's previous read-back is done before it is overwritten
+            ctx.pass_lighting(i, i, out_imgs[i], capi.RESTIR_OUT_RGBA8_SRGB)
+            lit = torch.cuda.Event()
+            lit.record(stream)
+            side.wait_event(lit)
+            with torch.cuda.stream(side):
+                host_outs[i].copy_(out_imgs[i], non_blocking=True)
+                copy_done[i] = torch.cuda.Event()
+                copy_done[i].record(side)
+
+        def e2e_drain():
+            for e_ in copy_done:
+                if e_ is not None:
+                    stream.wait_event(e_)
 
         for _ in range(3):
             e2e_step(frame_no)
@@ -507,6 +525,7 @@ def main():
         for _ in range(args.steps):
             e2e_step(frame_no)
             frame_no += 1
+        e2e_drain()                                       # the last image has reached the host inside the timed region
         b.record(stream)
         barrier()
         c2 = ctx.counters(reset=True)

@@ -88,8 +88,13 @@ int restir_get_band(const restir_context *ctx, uint32_t *row_begin, uint32_t *ro
  * (unbiasedReusePass.h:111-161) and LightingPass (lightingPass.h:48-96).  slot is the G-buffer index
  * (0/1, src/app.h numGBuffers).  Planes are DEVICE pointers that must stay valid while bound. */
 int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *device_planes);
-/* Same, from HOST memory (pinned or pageable): copies the planes into context-owned device memory on the
- * context's stream (asynchronous when the host memory is pinned) and binds them. */
+/* Same, from HOST memory (pinned or pageable): copies the planes into context-owned device memory and binds
+ * them.  The copy runs on a copy stream the context owns (asynchronous when the host memory is pinned, which
+ * must then stay untouched until restir_synchronize or the first pass that reads the slot has been waited
+ * for): it starts as soon as the last pass that read this slot has finished — for frame f+1 that is frame
+ * f's restir pass (restirOmni.glsl:163-209 is the only reader of the previous G-buffer), so the upload is
+ * hidden under frame f's reuse and lighting passes — and every later pass that reads the slot waits for it.
+ * The observable order is the in-order one. */
 int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *host_planes);
 
 /* ---- uniforms ------------------------------------------------------------------------------------ */

@@ -40,6 +40,12 @@ struct restir_context {
 	PackedReservoir *reservoirs[3] = {nullptr, nullptr, nullptr};
 	GBufferView gbuf[2] = {};
 	void *ownedPlanes[2][5] = {};
+	// restir_upload_gbuffer copies on its own stream, so the upload of frame f+1 runs under the reuse and
+	// lighting passes of frame f: `uploaded[s]` orders the passes after the copy into slot s, `lastRead[s]`
+	// orders the next copy into slot s after the last kernel that read it.
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t uploaded[2] = {nullptr, nullptr}, lastRead[2] = {nullptr, nullptr};
+	bool uploadPending[2] = {false, false}, readRecorded[2] = {false, false};
 	restir_reservoir *staging = nullptr; // device scratch for 64-byte <-> 32-byte conversion
 	size_t stagingPixels = 0;
 	// hand-over buffers between the halves of a cut pass and the trace kernel (restir_kernels.cu)
@@ -204,6 +210,32 @@ void dropProfile(restir_context *ctx) {
 
 const size_t kPlaneBytes[5] = {4, 8, 4, 16, 4}; // albedo, normal, material, worldPos, depth
 
+// The passes about to read G-buffer slot `slot` wait for an upload into it that is still in flight.
+int waitUpload(restir_context *ctx, int slot) {
+	if (ctx->uploadPending[slot]) {
+		CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->uploaded[slot], 0));
+		ctx->uploadPending[slot] = false;
+	}
+	return RESTIR_OK;
+}
+// Marks the point on the compute stream after which slot `slot` may be overwritten by the next upload
+// (only slots whose planes restir_upload_gbuffer owns take part).
+int markRead(restir_context *ctx, int slot);
+int markReadIfOwned(restir_context *ctx, int slot) {
+	if (ctx->ownedPlanes[slot][3] != nullptr && ctx->gbuf[slot].worldPos == ctx->ownedPlanes[slot][3]) {
+		return markRead(ctx, slot);
+	}
+	return RESTIR_OK;
+}
+int markRead(restir_context *ctx, int slot) {
+	if (ctx->lastRead[slot] == nullptr) {
+		CU(ctx, cudaEventCreateWithFlags(&ctx->lastRead[slot], cudaEventDisableTiming));
+	}
+	CU(ctx, cudaEventRecord(ctx->lastRead[slot], ctx->stream));
+	ctx->readRecorded[slot] = true;
+	return RESTIR_OK;
+}
+
 // grow-only hand-over buffers: one visibility byte per ray, one neighbour index per unbiased neighbour slot
 int ensureHandOver(restir_context *ctx, const PassGrid &g, unsigned raysPerPixel, unsigned neighbors) {
 	size_t bytes = (size_t)g.pixelIds * raysPerPixel;
@@ -289,8 +321,18 @@ void restir_destroy(restir_context *ctx) {
 		return;
 	}
 	cudaSetDevice(ctx->device);
+	if (ctx->copyStream) {
+		cudaStreamSynchronize(ctx->copyStream);
+	}
 	if (ctx->stream) {
 		cudaStreamSynchronize(ctx->stream);
+	}
+	for (int s = 0; s < 2; ++s) {
+		if (ctx->uploaded[s]) cudaEventDestroy(ctx->uploaded[s]);
+		if (ctx->lastRead[s]) cudaEventDestroy(ctx->lastRead[s]);
+	}
+	if (ctx->copyStream) {
+		cudaStreamDestroy(ctx->copyStream);
 	}
 	dropGBuffers(ctx);
 	dropProfile(ctx);
@@ -320,6 +362,9 @@ const char *restir_last_error(const restir_context *ctx) { return ctx ? ctx->err
 
 int restir_synchronize(restir_context *ctx) {
 	ENTER(ctx);
+	if (ctx->copyStream) {
+		CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	return RESTIR_OK;
 }
@@ -402,8 +447,14 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 	if (width == 0 || height == 0 || row_begin >= row_end || row_end > height || width > (1u << 20) || height > (1u << 20)) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_resize: bad geometry %ux%u rows [%u,%u)", width, height, row_begin, row_end);
 	}
+	if (ctx->copyStream) {
+		CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	dropGBuffers(ctx);
+	for (int s = 0; s < 2; ++s) {
+		ctx->uploadPending[s] = ctx->readRecorded[s] = false;
+	}
 	for (auto &r : ctx->reservoirs) {
 		freeDev(r);
 	}
@@ -457,6 +508,7 @@ int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format for
 	v.worldPos = static_cast<const float4 *>(pl->worldPos);
 	v.depth = static_cast<const float *>(pl->depth);
 	ctx->gbuf[slot] = v;
+	ctx->uploadPending[slot] = false;
 	return RESTIR_OK;
 }
 
@@ -474,14 +526,37 @@ int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format f
 		if (src[k] == nullptr) {
 			return fail(ctx, RESTIR_E_INVALID, "restir_upload_gbuffer: all five planes are required");
 		}
+	}
+	if (ctx->copyStream == nullptr) {
+		CU(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	}
+	if (ctx->uploaded[slot] == nullptr) {
+		CU(ctx, cudaEventCreateWithFlags(&ctx->uploaded[slot], cudaEventDisableTiming));
+	}
+	// the copy waits for the last kernel that read this slot (for frame f+1 that is frame f's temporal kernel,
+	// restirOmni.glsl:163-209: the reuse and lighting passes of frame f only read the other slot), not for the
+	// whole compute stream
+	const bool ownedBefore = ctx->gbuf[slot].worldPos != nullptr && ctx->gbuf[slot].worldPos == ctx->ownedPlanes[slot][3];
+	if (ownedBefore && ctx->readRecorded[slot]) {
+		CU(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->lastRead[slot], 0));
+	} else if (ctx->ownedPlanes[slot][0] != nullptr) {
+		// planes exist but the slot was rebound in between: order after everything issued so far
+		int rc = markRead(ctx, slot);
+		if (rc != RESTIR_OK) return rc;
+		CU(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->lastRead[slot], 0));
+	}
+	for (int k = 0; k < 5; ++k) {
 		if (ctx->ownedPlanes[slot][k] == nullptr) {
 			CU(ctx, cudaMalloc(&ctx->ownedPlanes[slot][k], px * kPlaneBytes[k]));
 		}
-		CU(ctx, cudaMemcpyAsync(ctx->ownedPlanes[slot][k], src[k], px * kPlaneBytes[k], cudaMemcpyHostToDevice, ctx->stream));
+		CU(ctx, cudaMemcpyAsync(ctx->ownedPlanes[slot][k], src[k], px * kPlaneBytes[k], cudaMemcpyHostToDevice, ctx->copyStream));
 	}
+	CU(ctx, cudaEventRecord(ctx->uploaded[slot], ctx->copyStream));
 	restir_gbuffer_planes dev{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],
 	                          ctx->ownedPlanes[slot][4]};
-	return restir_bind_gbuffer(ctx, slot, format, &dev);
+	int rc = restir_bind_gbuffer(ctx, slot, format, &dev);
+	ctx->uploadPending[slot] = rc == RESTIR_OK;
+	return rc;
 }
 
 int restir_set_uniforms(restir_context *ctx, const restir_uniforms *u) {
@@ -579,6 +654,8 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	const PassGrid g = pass_grid(ctx->band);
 	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0, temporal = (p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0;
 	if ((rc = ensureHandOver(ctx, g, 1, 0)) != RESTIR_OK) return rc;
+	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+	if (temporal && (rc = waitUpload(ctx, gbuffer ^ 1)) != RESTIR_OK) return rc;
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "omni_candidates_kernel");
 	launch_omni_candidates(p, out, ctx->stream);
@@ -599,7 +676,8 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 		launch_omni_temporal(p, out, ctx->reservoirs[prev_buffer], ctx->shadowed, ctx->stream);
 		if ((rc = afterLaunch(ctx, "omni_temporal_kernel")) != RESTIR_OK) return rc;
 	}
-	return RESTIR_OK;
+	if ((rc = markReadIfOwned(ctx, gbuffer)) != RESTIR_OK) return rc;
+	return markReadIfOwned(ctx, gbuffer ^ 1); // the previous frame's G-buffer is not read after this pass
 }
 
 int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter) {
@@ -612,9 +690,11 @@ int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out
 	if (in_buffer == out_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "spatial pass: in and out buffers must differ");
 	}
+	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	beforeLaunch(ctx, "spatial_reuse_kernel");
 	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, ctx->stream);
-	return afterLaunch(ctx, "spatial_reuse_kernel");
+	if ((rc = afterLaunch(ctx, "spatial_reuse_kernel")) != RESTIR_OK) return rc;
+	return markReadIfOwned(ctx, gbuffer);
 }
 
 int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer) {
@@ -635,6 +715,7 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 		return fail(ctx, RESTIR_E_UNSUPPORTED, "unbiased pass: %llu rays exceed the trace kernel's 32-bit work list; use row bands", (unsigned long long)(g.pixelIds * (k + 1)));
 	}
 	if ((rc = ensureHandOver(ctx, g, k + 1, k)) != RESTIR_OK) return rc;
+	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	const PackedReservoir *in = ctx->reservoirs[in_buffer];
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "unbiased_merge_kernel");
@@ -654,7 +735,8 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	}
 	beforeLaunch(ctx, "unbiased_finalize_kernel");
 	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
-	return afterLaunch(ctx, "unbiased_finalize_kernel");
+	if ((rc = afterLaunch(ctx, "unbiased_finalize_kernel")) != RESTIR_OK) return rc;
+	return markReadIfOwned(ctx, gbuffer);
 }
 
 int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out_device, int out_format) {
@@ -672,9 +754,11 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
 	if ((int)ctx->lighting.bufferSize[0] != ctx->band.W || (int)ctx->lighting.bufferSize[1] != ctx->band.H) {
 		return fail(ctx, RESTIR_E_INVALID, "lighting uniforms bufferSize does not match restir_resize");
 	}
+	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	beforeLaunch(ctx, "lighting_kernel");
 	launch_lighting(p, ctx->lighting, ctx->reservoirs[buffer], out_device, out_format, ctx->stream);
-	return afterLaunch(ctx, "lighting_kernel");
+	if ((rc = afterLaunch(ctx, "lighting_kernel")) != RESTIR_OK) return rc;
+	return markReadIfOwned(ctx, gbuffer);
 }
 
 int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations) {
