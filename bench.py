@@ -267,6 +267,8 @@ def main():
     ap.add_argument("--reference-rows", type=int, default=48, help="rows per step of the --impl reference arm")
     ap.add_argument("--traversal", default="auto", choices=["auto", "reference-order"],
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -301,7 +303,10 @@ def main():
     cfg = CONFIGS[args.config]
     scene, cam_key, label = load_scene(fixtures, cfg)
     w, band_h = cfg["size"]
-    h = band_h * world                                    # weak scaling: one config-sized band per rank
+    if args.scaling == "strong":                          # the configuration's own frame, split into N row bands
+        h, band_h = band_h, (band_h + world - 1) // world
+    else:
+        h = band_h * world                                # weak scaling: one config-sized band per rank
     row_begin, row_end = bands.band_rows(h, world, rank)
     pos, look = CAMERAS[cam_key]
     cams = [capi.make_camera(position=pos, look_at=look, aspect=w / h),
@@ -440,7 +445,8 @@ def main():
             kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / reps
             kernel_launches[name] = kernel_launches.get(name, 0) + n / reps
         frame_no += 1
-    rays_prof = ctx.counters(reset=True)["shadow_rays"] / reps
+    c_prof = ctx.counters(reset=True)
+    rays_prof, traced_prof = c_prof["shadow_rays"] / reps, c_prof["shadow_rays_traced"] / reps
     peak, peak_src = peaks()
     info = ctx.bvh_info()
     bvh_bytes = (info["nodes"] * 64 if info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE else scene.nodes.size) + scene.triangles.size
@@ -459,8 +465,11 @@ def main():
     rays_pixel = own_pixels if "trace_kernel<pixel>" in kernel_ms else 0
     if "trace_kernel<pixel>" in kernel_ms:
         alg["trace_kernel<pixel>"] = rays_pixel * 33 + bvh_bytes
-    if "trace_kernel<unbiased>" in kernel_ms:
-        alg["trace_kernel<unbiased>"] = (rays_prof - rays_pixel) * 37 + bvh_bytes
+    if "trace_kernel<own>" in kernel_ms:
+        alg["trace_kernel<own>"] = own_pixels * 33 + bvh_bytes
+    if "trace_kernel<neighbours>" in kernel_ms:
+        # every neighbour slot is looked at (index 4 B + own visibility byte), the traced ones read two positions and write a byte
+        alg["trace_kernel<neighbours>"] = own_pixels * k * 5 + max(traced_prof - rays_pixel - own_pixels, 0) * 33 + bvh_bytes
     top = max(kernel_ms, key=kernel_ms.get)
     top_ms = kernel_ms[top] / max(kernel_launches[top], 1)
     achieved = alg[top] / (top_ms * 1e-3) / 1e9
@@ -479,6 +488,7 @@ def main():
     hbm_frame_frac = frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak
     trace_ms = sum(v for k_, v in kernel_ms.items() if k_.startswith("trace_kernel"))
     trace_mrays = rays_prof / (trace_ms * 1e-3) / 1e6 if trace_ms else None
+    trace_mrays_walked = traced_prof / (trace_ms * 1e-3) / 1e6 if trace_ms else None
 
     # ---- end to end through the C ABI: host G-buffers in (pinned), 8-bit image out, every step ---------------
     e2e = None
@@ -586,16 +596,19 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": mrays, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_frame, "ms_per_frame": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_frame, "ms_per_frame": ms_per_frame, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {label}, {w}x{h} frame ({w}x{band_h} band per GPU), {cfg['candidates']} candidates, "
                                    f"{'unbiased reuse, ' + str(cfg['neighbors']) + ' neighbours' if cfg['unbiased'] else 'biased reuse 2 passes x ' + str(cfg['neighbors']) + ' neighbours'}, "
                                    f"temporal reuse on, software shadow rays, lights: {scene.light_counts()}",
                        "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
                        "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world}, halo {HALO} rows"},
-            "rays_per_frame": rays_total / args.steps, "pass_ms": dict(zip(names, [float(x) for x in pass_ms])),
+            "rays_per_frame": rays_total / args.steps, "rays_walked_per_frame": traced_prof,
+            "rays_note": "value counts the reference's testVisibility calls answered per second (the same unit of work as the --impl reference "
+                         "arm); rays_walked_per_frame of them needed a walk of the tree, the rest are answered exactly without one",
+            "pass_ms": dict(zip(names, [float(x) for x in pass_ms])),
             "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac,
-            "trace_kernel_mrays_per_s": trace_mrays, "bvh": info,
+            "trace_kernel_mrays_per_s": trace_mrays, "trace_kernel_mrays_walked_per_s": trace_mrays_walked, "bvh": info,
             "hbm_frame_frac": hbm_frame_frac, "frame_algorithmic_bytes": frame_bytes,
             "gpu_launches": int(launches), "halo_misses": int(halo_misses), "stack_overflows": int(overflows),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity_sample": parity,

@@ -181,10 +181,13 @@ int restir_trace_segments(restir_context *ctx, const float *p1_device, const flo
 /* ---- counters --------------------------------------------------------------------------------- */
 
 typedef struct restir_counters {
-	uint64_t shadow_rays;       /* testVisibility calls executed since the last reset */
+	uint64_t shadow_rays;       /* the reference's testVisibility calls answered since the last reset */
 	uint64_t stack_overflows;   /* pushes dropped on a full 32-entry traversal stack (UB in the reference) */
 	uint64_t halo_misses;       /* band mode: neighbour / reprojection reads outside [alloc_begin, alloc_end) */
 	uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
+	uint64_t shadow_rays_traced; /* of shadow_rays, the ones that needed a walk of the tree: the rest were answered exactly
+	                              * without one (neighbour rays of a pixel whose own ray is shadowed, unbiasedReuse.glsl:157-166;
+	                              * neighbour rays bit-identical to the neighbour's own ray) */
 } restir_counters;
 /* Synchronises the stream. */
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset);

@@ -75,7 +75,7 @@ class GBufferPlanes(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches")]
+    _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches", "shadow_rays_traced")]
 
 
 class BvhInfo(C.Structure):
@@ -372,7 +372,7 @@ class RestirContext:
         c = Counters()
         self._check(self.lib.restir_get_counters(self._ctx, C.byref(c), C.c_int(1 if reset else 0)))
         return {"shadow_rays": c.shadow_rays, "stack_overflows": c.stack_overflows, "halo_misses": c.halo_misses,
-                "kernel_launches": c.kernel_launches}
+                "kernel_launches": c.kernel_launches, "shadow_rays_traced": c.shadow_rays_traced}
 
     def raycast_gbuffer(self, cam, tri_material, material_table, albedo, normal, material, world_pos, depth):
         self._check(self.lib.restir_tools_raycast_gbuffer(self._ctx, C.byref(cam), _dp(tri_material), _dp(material_table), _dp(albedo),

@@ -664,6 +664,8 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 		TraceParams tp = traceParams(ctx);
 		tp.tilesX = g.tilesX;
 		tp.slots = 1;
+		tp.outStride = 1;
+		tp.outOffset = 0;
 		tp.nItems = g.pixelIds;
 		tp.worldPos = p.cur.worldPos;
 		tp.reservoirs = out;
@@ -722,16 +724,25 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	launch_unbiased_merge(p, in, out, (int)k, ctx->neighborPix, ctx->stream);
 	if ((rc = afterLaunch(ctx, "unbiased_merge_kernel")) != RESTIR_OK) return rc;
 	if (vis) {
+		// the pixels' own rays first (:157-166): a shadowed pixel needs none of its neighbour rays, and a neighbour ray
+		// whose segment is bit-identical to the neighbour's own ray is answered from it (restir_trace.cu item_resolve)
 		TraceParams tp = traceParams(ctx);
 		tp.tilesX = g.tilesX;
-		tp.slots = k + 1;
-		tp.nItems = g.pixelIds * (k + 1);
+		tp.slots = 1;
+		tp.outStride = k + 1;
+		tp.outOffset = k;
+		tp.nItems = g.pixelIds;
 		tp.worldPos = p.cur.worldPos;
 		tp.reservoirs = out;
+		beforeLaunch(ctx, "trace_kernel<own>");
+		CU(ctx, launch_trace(tp, kTracePixel, ctx->smCount, ctx->stream));
+		if ((rc = afterLaunch(ctx, "trace_kernel<own>")) != RESTIR_OK) return rc;
+		tp.slots = k;
+		tp.nItems = g.pixelIds * k;
 		tp.neighborPix = ctx->neighborPix;
-		beforeLaunch(ctx, "trace_kernel<unbiased>");
+		beforeLaunch(ctx, "trace_kernel<neighbours>");
 		CU(ctx, launch_trace(tp, kTraceUnbiased, ctx->smCount, ctx->stream));
-		if ((rc = afterLaunch(ctx, "trace_kernel<unbiased>")) != RESTIR_OK) return rc;
+		if ((rc = afterLaunch(ctx, "trace_kernel<neighbours>")) != RESTIR_OK) return rc;
 	}
 	beforeLaunch(ctx, "unbiased_finalize_kernel");
 	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
@@ -869,6 +880,7 @@ int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	if (out) {
 		out->shadow_rays = h[kCounterRays];
+		out->shadow_rays_traced = h[kCounterTraced];
 		out->stack_overflows = h[kCounterOverflow];
 		out->halo_misses = h[kCounterHaloMiss];
 		out->kernel_launches = ctx->launches;

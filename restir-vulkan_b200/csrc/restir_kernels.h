@@ -14,8 +14,8 @@ struct RaycastCamera {
 
 // ---- the persistent shadow-ray kernel (restir_trace.cu) ---------------------------------------------------
 enum TraceMode {
-	kTracePixel = 0,    // one ray per pixel: G-buffer position -> reservoir sample (restirOmni.glsl:148-160)
-	kTraceUnbiased = 1, // `slots` rays per pixel: slots-1 neighbour positions and the pixel itself -> sample (unbiasedReuse.glsl:126-166)
+	kTracePixel = 0,    // one ray per pixel: G-buffer position -> reservoir sample (restirOmni.glsl:148-160, unbiasedReuse.glsl:157-166)
+	kTraceUnbiased = 1, // `slots` neighbour rays per pixel: neighbour position -> the pixel's sample (unbiasedReuse.glsl:139-156)
 	kTraceSegments = 2, // explicit segments (restir_trace_segments)
 };
 struct TraceParams {
@@ -28,7 +28,9 @@ struct TraceParams {
 	const PackedReservoir *reservoirs; // sample positions = ray targets
 	const int *neighborPix;            // [pixel id][slots-1]: local pixel index of the neighbour, < 0 = no ray
 	const float *segP1, *segP2;
-	unsigned char *shadowed;           // [item]: 1 = shadowed
+	unsigned char *shadowed;           // 1 = shadowed.  kTracePixel: [pixel id * outStride + outOffset]; kTraceUnbiased:
+	                                   // [pixel id * (slots + 1) + slot], the pixel's own ray (traced before, kTracePixel) at slot `slots`
+	unsigned outStride, outOffset;
 	unsigned long long *counters;
 };
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);

@@ -36,6 +36,9 @@ constexpr int kChunk = RESTIR_TRACE_CHUNK; // items per warp fetch (power of two
 #ifndef RESTIR_TRACE_SORT
 #define RESTIR_TRACE_SORT 1
 #endif
+#ifndef RESTIR_TRACE_SHARE
+#define RESTIR_TRACE_SHARE 1 // answer a neighbour ray from the neighbour's own ray when the two segments are identical
+#endif
 constexpr unsigned kInvalidKey = 0xffffffffu;
 
 // ---- item -> pixel, key, segment ---------------------------------------------------------------------------
@@ -54,56 +57,114 @@ __device__ __forceinline__ bool item_pixel(const TraceParams &tp, unsigned p, si
 	return true;
 }
 
-// Resolves an item to (pixel holding the sample, pixel the ray starts from); false = no ray for this item.
-template <int MODE> __device__ __forceinline__ bool item_pixels(const TraceParams &tp, unsigned item, size_t &pix, size_t &opix) {
-	unsigned p = item, slot = 0;
-	if (MODE == kTraceUnbiased) {
-		p = item / tp.slots;
-		slot = item - p * tp.slots;
-	}
-	if (!item_pixel(tp, p, pix)) {
+// Tile-ordered pixel id of local pixel index n (the inverse of item_pixel); false outside the band's own rows.
+__device__ __forceinline__ bool pixel_id_of_local(const TraceParams &tp, unsigned n, unsigned &id) {
+	unsigned W = (unsigned)tp.band.W;
+	unsigned yl = n / W, x = n - yl * W;
+	int y = (int)yl + tp.band.allocBegin;
+	if (y < tp.band.rowBegin || y >= tp.band.rowEnd) {
 		return false;
 	}
-	opix = pix;
-	if (MODE == kTraceUnbiased && slot + 1 < tp.slots) { // neighbour ray: starts at the neighbour's surface point
-		int n = tp.neighborPix[(size_t)p * (tp.slots - 1) + slot];
-		if (n < 0) {
-			return false;
-		}
-		opix = (size_t)n;
-	}
+	unsigned ry = (unsigned)(y - tp.band.rowBegin);
+	id = (((ry >> 2) * tp.tilesX + (x >> 3)) << 5) | ((ry & 3u) << 3) | (x & 7u);
 	return true;
 }
 
-// Sort key of an item: (light the ray is aimed at, position in the chunk); kInvalidKey = no ray.
-template <int MODE> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local) {
+// What the reference does for an item, and what is left of it here.
+enum ItemState {
+	kItemNone = 0,     // the reference makes no testVisibility call for this item
+	kItemAnswered = 1, // it does, and the answer is known without walking the tree (see item_resolve)
+	kItemRay = 2,      // it does, and the segment has to be traced
+};
+
+// Resolves an item to its state, the pixel holding the sample (pix), the pixel the ray starts from (opix) and
+// the index of its visibility byte (out).
+//
+// kTraceUnbiased items are the NEIGHBOUR rays of unbiasedReuse.glsl:139-156; the pixels' own rays (:157-166)
+// were traced by the kTracePixel launch before this one.  Two exact shortcuts:
+//   * the pixel's own ray is shadowed: the reference zeroes numSamples after the neighbour loop (:160-165), so
+//     no neighbour ray of that pixel can change the result;
+//   * the neighbour's own merged sample sits at the same position, bit for bit, as this pixel's (spatial reuse
+//     makes neighbours share samples; with point lights every reservoir holding light k does): the segment
+//     neighbour -> sample IS the neighbour's own ray (same p1, same p2 => same segment_setup, same walk), whose
+//     answer the kTracePixel launch already wrote.
+template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParams &tp, unsigned item, size_t &pix, size_t &opix, size_t &out, bool answer) {
+	if (MODE == kTracePixel) {
+		if (!item_pixel(tp, item, pix)) {
+			return kItemNone;
+		}
+		opix = pix;
+		out = (size_t)item * tp.outStride + tp.outOffset;
+		return kItemRay;
+	}
+	unsigned p = item / tp.slots, slot = item - p * tp.slots;
+	if (!item_pixel(tp, p, pix)) {
+		return kItemNone;
+	}
+	int n = tp.neighborPix[(size_t)p * tp.slots + slot];
+	if (n < 0) {
+		return kItemNone;
+	}
+	opix = (size_t)n;
+	const size_t row = (size_t)p * (tp.slots + 1);
+	out = row + slot;
+	if (tp.shadowed[row + tp.slots] != 0) {
+		return kItemAnswered; // the byte is never read (unbiased_finalize_kernel drops the pixel)
+	}
+	unsigned nid;
+	if (RESTIR_TRACE_SHARE && pixel_id_of_local(tp, (unsigned)n, nid)) {
+		float4 a = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+		float4 b = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + opix));
+		if (__float_as_uint(a.x) == __float_as_uint(b.x) && __float_as_uint(a.y) == __float_as_uint(b.y) && __float_as_uint(a.z) == __float_as_uint(b.z)) {
+			if (answer) {
+				tp.shadowed[out] = tp.shadowed[(size_t)nid * (tp.slots + 1) + tp.slots];
+			}
+			return kItemAnswered;
+		}
+	}
+	return kItemRay;
+}
+
+// Sort key of an item: (light the ray is aimed at, position in the chunk); kInvalidKey = nothing to trace.
+template <int MODE> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local, unsigned &answered) {
 	if (item >= tp.nItems) {
 		return kInvalidKey;
 	}
 	if (MODE == kTraceSegments) {
 		return local;
 	}
-	size_t pix, opix;
-	if (!item_pixels<MODE>(tp, item, pix, opix)) {
+	size_t pix, opix, out;
+	int state = item_resolve<MODE>(tp, item, pix, opix, out, true);
+	if (state != kItemRay) {
+		answered += state == kItemAnswered ? 1u : 0u;
 		return kInvalidKey;
 	}
 	unsigned light = RESTIR_TRACE_SORT ? (unsigned)__ldg(reinterpret_cast<const int *>(tp.reservoirs + pix) + 3) : 0u; // PackedReservoir::lightIndex
 	return ((light & 0x7fffffu) << 8) | local;
 }
 
-template <int MODE> __device__ __forceinline__ void item_segment(const TraceParams &tp, unsigned item, f3 &p1, f3 &p2) {
+// Segment of an item item_key found to be a ray; returns the index of its visibility byte.
+template <int MODE> __device__ __forceinline__ size_t item_segment(const TraceParams &tp, unsigned item, f3 &p1, f3 &p2) {
 	if (MODE == kTraceSegments) {
 		const float *a = tp.segP1 + (size_t)item * 3, *b = tp.segP2 + (size_t)item * 3;
 		p1 = mk3(a[0], a[1], a[2]);
 		p2 = mk3(b[0], b[1], b[2]);
-		return;
+		return item;
 	}
-	size_t pix, opix;
-	item_pixels<MODE>(tp, item, pix, opix);
+	size_t pix, opix, out;
+	if (MODE == kTracePixel) {
+		item_resolve<MODE>(tp, item, pix, opix, out, false);
+	} else {
+		unsigned p = item / tp.slots, slot = item - p * tp.slots;
+		item_pixel(tp, p, pix);
+		opix = (size_t)tp.neighborPix[(size_t)p * tp.slots + slot];
+		out = (size_t)p * (tp.slots + 1) + slot;
+	}
 	float4 w = __ldg(tp.worldPos + opix);
 	float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
 	p1 = mk3(w.x, w.y, w.z);
 	p2 = mk3(t.x, t.y, t.z);
+	return out;
 }
 
 // bitonic sort of kChunk keys in shared memory by one warp
@@ -129,12 +190,15 @@ __device__ __forceinline__ void warp_sort(unsigned *keys, unsigned lane) {
 
 // ---- the kernel ------------------------------------------------------------------------------------------
 
-template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_constant__ TraceParams tp) {
+#ifndef RESTIR_TRACE_MIN_BLOCKS
+#define RESTIR_TRACE_MIN_BLOCKS 1
+#endif
+template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
 	__shared__ unsigned allKeys[kTraceWarps][kChunk];
 	const unsigned lane = threadIdx.x & 31u;
 	unsigned *keys = allKeys[threadIdx.x >> 5];
 	const unsigned full = 0xffffffffu;
-	unsigned rays = 0, overflow = 0;
+	unsigned rays = 0, answered = 0, overflow = 0;
 
 	for (;;) {
 		unsigned base = 0;
@@ -148,7 +212,7 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads)
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)kChunk / 32; ++r) {
 			unsigned local = r * 32u + lane;
-			keys[local] = item_key<MODE>(tp, base + local, local);
+			keys[local] = item_key<MODE>(tp, base + local, local, answered);
 		}
 		__syncwarp();
 		if (MODE != kTraceSegments && RESTIR_TRACE_SORT) {
@@ -164,10 +228,10 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads)
 			if (key != kInvalidKey) {
 				unsigned item = base + (key & 255u);
 				f3 p1, p2, o, d;
-				item_segment<MODE>(tp, item, p1, p2);
+				size_t out = item_segment<MODE>(tp, item, p1, p2);
 				segment_setup(p1, p2, o, d);
 				bool clear = IMAGE ? trace_any_image(tp.image, tp.tris, o, d) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
-				tp.shadowed[item] = clear ? 0 : 1;
+				tp.shadowed[out] = clear ? 0 : 1;
 				rays++;
 			}
 		}
@@ -175,9 +239,11 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads)
 	}
 	// one atomic per warp
 	rays = __reduce_add_sync(full, rays);
+	answered = __reduce_add_sync(full, answered);
 	overflow = __reduce_add_sync(full, overflow);
 	if (lane == 0) {
-		if (rays) atomicAdd(tp.counters + kCounterRays, (unsigned long long)rays);
+		if (rays + answered) atomicAdd(tp.counters + kCounterRays, (unsigned long long)(rays + answered));
+		if (rays) atomicAdd(tp.counters + kCounterTraced, (unsigned long long)rays);
 		if (overflow) atomicAdd(tp.counters + kCounterOverflow, (unsigned long long)overflow);
 	}
 }
