@@ -191,7 +191,7 @@ __device__ __forceinline__ void warp_sort(unsigned *keys, unsigned lane) {
 // ---- the kernel ------------------------------------------------------------------------------------------
 
 #ifndef RESTIR_TRACE_MIN_BLOCKS
-#define RESTIR_TRACE_MIN_BLOCKS 1
+#define RESTIR_TRACE_MIN_BLOCKS 5
 #endif
 template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
 	__shared__ unsigned allKeys[kTraceWarps][kChunk];

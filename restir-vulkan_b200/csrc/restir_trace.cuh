@@ -102,7 +102,7 @@ __device__ __forceinline__ bool test_visibility_reference(const SceneView &sc, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same walk over the 64-byte re-stride of the same tree (traversal_image.h): four 16-byte loads per node
+// The same walk over the 64-byte image of the same tree (traversal_image.h): four 16-byte loads per node
 // from one 128-byte line.  Only used when the tree's worst-case stack occupancy is <= 32 (checked at upload),
 // so no push can be dropped and the stack needs no bound checks; the node about to be visited stays in a
 // register instead of going through the stack.  Order of visits and triangle tests is the reference's: left
@@ -111,12 +111,24 @@ __device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image
 	int stack[32];
 	int top = 0, cur = 0;
 	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	// both boxes of a node at once: (b - o) * inv as FADD2 (b + (-o), the same IEEE operation) and FMUL2, the
+	// left box in the low half and the right box in the high half of every pair
+	const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+	const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
 	for (;;) {
 		const float4 *n = image + (unsigned)cur * 4u;
-		float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
-		int4 ch = __ldg(reinterpret_cast<const int4 *>(n + 3));
-		bool hl = ray_box_reference(o, inv, make_float4(a.x, a.y, a.z, 0.0f), make_float4(a.w, b.x, b.y, 0.0f));
-		bool hr = ray_box_reference(o, inv, make_float4(b.z, b.w, c.x, 0.0f), make_float4(c.y, c.z, c.w, 0.0f));
+		float4 qx = __ldg(n), qy = __ldg(n + 1), qz = __ldg(n + 2);
+		int2 ch = __ldg(reinterpret_cast<const int2 *>(n + 3));
+		float2 t1x = __fmul2_rn(__fadd2_rn(make_float2(qx.x, qx.y), nox), ivx), t2x = __fmul2_rn(__fadd2_rn(make_float2(qx.z, qx.w), nox), ivx);
+		float2 t1y = __fmul2_rn(__fadd2_rn(make_float2(qy.x, qy.y), noy), ivy), t2y = __fmul2_rn(__fadd2_rn(make_float2(qy.z, qy.w), noy), ivy);
+		float2 t1z = __fmul2_rn(__fadd2_rn(make_float2(qz.x, qz.y), noz), ivz), t2z = __fmul2_rn(__fadd2_rn(make_float2(qz.z, qz.w), noz), ivz);
+		// softwareRaytracing.glsl:11-13 per box
+		float lmin = fmaxf(fminf(t1x.x, t2x.x), fmaxf(fminf(t1y.x, t2y.x), fminf(t1z.x, t2z.x)));
+		float lmax = fminf(fmaxf(t1x.x, t2x.x), fminf(fmaxf(t1y.x, t2y.x), fmaxf(t1z.x, t2z.x)));
+		float rmin = fmaxf(fminf(t1x.y, t2x.y), fmaxf(fminf(t1y.y, t2y.y), fminf(t1z.y, t2z.y)));
+		float rmax = fminf(fmaxf(t1x.y, t2x.y), fminf(fmaxf(t1y.y, t2y.y), fmaxf(t1z.y, t2z.y)));
+		bool hl = lmin < 1.0f && lmax >= lmin && lmax > 0.0f;
+		bool hr = rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
 		// hit leaves: left first, then right (most visits have none: one branch skips the whole block)
 		int t0 = (hl && ch.x < 0) ? ~ch.x : -1, t1 = (hr && ch.y < 0) ? ~ch.y : -1;
 		if ((t0 & t1) >= 0) { // at least one of them is a triangle index

@@ -72,16 +72,16 @@ bool build_traversal_image(const restir_aabb_node *nodes, uint32_t nNodes, uint3
 		return true; // usable stays false
 	}
 
-	// ---- the 64-byte re-stride: same index, same boxes, same children -------------------------------------
+	// ---- the 64-byte image: same index, same boxes, same children, planes grouped per axis (traversal_image.h) -------------------------------------
 	out.resize(nNodes);
 	for (uint32_t i = 0; i < nNodes; ++i) {
 		const restir_aabb_node &n = nodes[i];
 		Node64 &o = out[i];
 		for (int k = 0; k < 3; ++k) {
-			o.box[k] = n.leftAabbMin[k];
-			o.box[3 + k] = n.leftAabbMax[k];
-			o.box[6 + k] = n.rightAabbMin[k];
-			o.box[9 + k] = n.rightAabbMax[k];
+			o.box[4 * k + 0] = n.leftAabbMin[k];
+			o.box[4 * k + 1] = n.rightAabbMin[k];
+			o.box[4 * k + 2] = n.leftAabbMax[k];
+			o.box[4 * k + 3] = n.rightAabbMax[k];
 		}
 		o.left = n.leftChild;
 		o.right = n.rightChild;

@@ -21,7 +21,9 @@
 
 namespace restir {
 
-// 4 x float4: (Lmin.xyz, Lmax.x) (Lmax.yz, Rmin.xy) (Rmin.z, Rmax.xyz) (left, right, -, -)
+// 4 x float4, one per axis then the children: (Lmin.a, Rmin.a, Lmax.a, Rmax.a) for a = x, y, z; (left, right, -, -).
+// The left and the right box sit side by side so that one packed instruction (sm_100 FADD2 / FMUL2: two
+// IEEE binary32 operations per issue slot, each rounded like the scalar one) serves both.
 struct alignas(64) Node64 {
 	float box[12];
 	int32_t left, right; // reference encoding: >= 0 node index, < 0 ~triangleIndex
