@@ -416,9 +416,13 @@ __global__ void __launch_bounds__(kThreads) spatial_reuse_kernel(PassParams p, c
 // ray).  The rays themselves (:139-166) are the trace kernel's, the normalisation unbiased_finalize_kernel's.
 constexpr int kMaxUnbiasedNeighbors = 16;
 
+// K > 0: the neighbour count is the compile-time K (the reference's NUM_NEIGHBORS 3 and the north-star's 5): the
+// neighbour loops unroll and the neighbour indices stay in registers; K == 0: any count up to kMaxUnbiasedNeighbors.
+template <int K>
 __global__ void __launch_bounds__(kThreads) unbiased_merge_kernel(PassParams p, const PackedReservoir *__restrict__ in,
-                                                                 PackedReservoir *__restrict__ out, int numNeighbors,
+                                                                 PackedReservoir *__restrict__ out, int numNeighborsArg,
                                                                  int *__restrict__ neighborPix) {
+	const int numNeighbors = K ? K : numNeighborsArg;
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
 	unsigned haloMiss = 0;
@@ -436,8 +440,8 @@ __global__ void __launch_bounds__(kThreads) unbiased_merge_kernel(PassParams p, 
 
 		PackedReservoir res = load_reservoir(in, pix);
 		Pcg32 rng = pcg_seed(p.u.frame * 17u, (uint32_t)y * 10007u + (uint32_t)x); // :72
-		int npx[kMaxUnbiasedNeighbors];
-#pragma unroll 1
+		int npx[K ? K : kMaxUnbiasedNeighbors];
+#pragma unroll(K ? K : 1)
 		for (int i = 0; i < numNeighbors; ++i) {                                  // :84-124
 			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;
 			float radius = sqrtf(pcg_float(rng)) * p.u.spatialRadius;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(kThreads) unbiased_merge_kernel(PassParams p, 
 		// :135-138
 		f3 lightPos = mk3(res.px, res.py, res.pz);
 		int *slots = neighborPix + tile_pixel_id() * (unsigned long long)numNeighbors;
-#pragma unroll 1
+#pragma unroll(K ? K : 1)
 		for (int j = 0; j < numNeighbors; ++j) {
 			int n = npx[j];
 			if (n >= 0) {
@@ -751,7 +755,11 @@ void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, Packed
 	spatial_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter);
 }
 void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix, cudaStream_t s) {
-	unbiased_merge_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix);
+	switch (numNeighbors) {
+	case 3: unbiased_merge_kernel<3><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
+	case 5: unbiased_merge_kernel<5><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
+	default: unbiased_merge_kernel<0><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
+	}
 }
 void launch_unbiased_finalize(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, const int *neighborPix,
                               const unsigned char *shadowed, cudaStream_t s) {

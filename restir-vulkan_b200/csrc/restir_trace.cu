@@ -32,7 +32,15 @@ constexpr int kTraceWarps = kTraceThreads / 32;
 #ifndef RESTIR_TRACE_CHUNK
 #define RESTIR_TRACE_CHUNK 128
 #endif
-constexpr int kChunk = RESTIR_TRACE_CHUNK; // items per warp fetch (power of two, <= 256: the local id is 8 bits of the sort key)
+// items per warp fetch (power of two, <= 256: the local id is 8 bits of the sort key).  Neighbour rays: about half of the
+// items of a chunk are answered without a ray (item_resolve), so the chunk is twice as long to keep the batches full.
+constexpr int kChunk = RESTIR_TRACE_CHUNK;
+#ifndef RESTIR_TRACE_CHUNK_NEIGHBOURS
+#define RESTIR_TRACE_CHUNK_NEIGHBOURS 256
+#endif
+template <int MODE> struct ChunkOf {
+	static constexpr int value = MODE == kTraceUnbiased ? RESTIR_TRACE_CHUNK_NEIGHBOURS : kChunk;
+};
 #ifndef RESTIR_TRACE_SORT
 #define RESTIR_TRACE_SORT 1
 #endif
@@ -167,14 +175,14 @@ template <int MODE> __device__ __forceinline__ size_t item_segment(const TracePa
 	return out;
 }
 
-// bitonic sort of kChunk keys in shared memory by one warp
-__device__ __forceinline__ void warp_sort(unsigned *keys, unsigned lane) {
+// bitonic sort of CHUNK keys in shared memory by one warp
+template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, unsigned lane) {
 #pragma unroll 1
-	for (unsigned k = 2; k <= (unsigned)kChunk; k <<= 1) {
+	for (unsigned k = 2; k <= (unsigned)CHUNK; k <<= 1) {
 #pragma unroll 1
 		for (unsigned j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-			for (unsigned t = lane; t < (unsigned)kChunk / 2; t += 32) {
+			for (unsigned t = lane; t < (unsigned)CHUNK / 2; t += 32) {
 				unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
 				unsigned a = keys[i], b = keys[i + j];
 				bool ascending = (i & k) == 0u;
@@ -194,7 +202,8 @@ __device__ __forceinline__ void warp_sort(unsigned *keys, unsigned lane) {
 #define RESTIR_TRACE_MIN_BLOCKS 5
 #endif
 template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
-	__shared__ unsigned allKeys[kTraceWarps][kChunk];
+	constexpr int CHUNK = ChunkOf<MODE>::value;
+	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
 	const unsigned lane = threadIdx.x & 31u;
 	unsigned *keys = allKeys[threadIdx.x >> 5];
 	const unsigned full = 0xffffffffu;
@@ -203,23 +212,23 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 	for (;;) {
 		unsigned base = 0;
 		if (lane == 0) {
-			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)kChunk), 0xffffffffull);
+			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)CHUNK), 0xffffffffull);
 		}
 		base = __shfl_sync(full, base, 0);
 		if (base >= tp.nItems) {
 			break;
 		}
 #pragma unroll 1
-		for (unsigned r = 0; r < (unsigned)kChunk / 32; ++r) {
+		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned local = r * 32u + lane;
 			keys[local] = item_key<MODE>(tp, base + local, local, answered);
 		}
 		__syncwarp();
 		if (MODE != kTraceSegments && RESTIR_TRACE_SORT) {
-			warp_sort(keys, lane);
+			warp_sort<CHUNK>(keys, lane);
 		}
 #pragma unroll 1
-		for (unsigned r = 0; r < (unsigned)kChunk / 32; ++r) {
+		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned key = keys[r * 32u + lane];
 			if (__ballot_sync(full, key != kInvalidKey) == 0u) {
 				if (MODE != kTraceSegments && RESTIR_TRACE_SORT) break; // sorted: only holes follow
@@ -260,7 +269,8 @@ template <int MODE, bool IMAGE> static cudaError_t launch_mode(const TraceParams
 		if (blocksPerSm < 1) blocksPerSm = 1;
 	}
 	// items are numbered with 32 bits inside the kernel; restir_capi.cu splits longer segment lists
-	unsigned long long chunks = (tp.nItems + kChunk - 1) / kChunk;
+	constexpr int CHUNK = ChunkOf<MODE>::value;
+	unsigned long long chunks = (tp.nItems + CHUNK - 1) / CHUNK;
 	unsigned long long wanted = (chunks + kTraceWarps - 1) / kTraceWarps;
 	unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)smCount * blocksPerSm, std::max<unsigned long long>(wanted, 1));
 	trace_kernel<MODE, IMAGE><<<grid, kTraceThreads, 0, s>>>(tp);

@@ -19,6 +19,19 @@ __device__ __forceinline__ bool ray_box_reference(f3 o, f3 inv, float4 bmin, flo
 	return rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
 }
 
+// One 32-byte read-only load (sm_100 LDG.E.256): a 64-byte node is two of them instead of four 16-byte loads —
+// half the requests on the L1 tag stage this kernel is bound by.  p must be 32-byte aligned.
+struct F8 {
+	float v[8];
+};
+__device__ __forceinline__ F8 ldg256(const void *p) {
+	F8 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+	    : "l"(p));
+	return r;
+}
+
 // softwareRaytracing.glsl:15-37
 __device__ __forceinline__ bool ray_triangle(const float4 *__restrict__ tris, int id, f3 o, f3 d) {
 	const float4 *t = tris + (size_t)id * 3;
@@ -117,8 +130,10 @@ __device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image
 	const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
 	for (;;) {
 		const float4 *n = image + (unsigned)cur * 4u;
-		float4 qx = __ldg(n), qy = __ldg(n + 1), qz = __ldg(n + 2);
-		int2 ch = __ldg(reinterpret_cast<const int2 *>(n + 3));
+		F8 lo = ldg256(n), hi = ldg256(n + 2);
+		float4 qx = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]), qy = make_float4(lo.v[4], lo.v[5], lo.v[6], lo.v[7]);
+		float4 qz = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
+		int2 ch = make_int2(__float_as_int(hi.v[4]), __float_as_int(hi.v[5]));
 		float2 t1x = __fmul2_rn(__fadd2_rn(make_float2(qx.x, qx.y), nox), ivx), t2x = __fmul2_rn(__fadd2_rn(make_float2(qx.z, qx.w), nox), ivx);
 		float2 t1y = __fmul2_rn(__fadd2_rn(make_float2(qy.x, qy.y), noy), ivy), t2y = __fmul2_rn(__fadd2_rn(make_float2(qy.z, qy.w), noy), ivy);
 		float2 t1z = __fmul2_rn(__fadd2_rn(make_float2(qz.x, qz.y), noz), ivz), t2z = __fmul2_rn(__fadd2_rn(make_float2(qz.z, qz.w), noz), ivz);
