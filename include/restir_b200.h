@@ -125,7 +125,13 @@ typedef struct restir_bvh_info {
 	uint32_t nodes, triangles;
 	uint32_t reachable_nodes, depth;
 	uint32_t reference_stack_bound; /* worst-case occupancy of the reference's 32-entry stack on this tree */
-	int32_t traversal;              /* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
+	int32_t traversal;              /* No reference equivalent (the reference traces every ray it asks for).  The unbiased pass answers a neighbour ray
+ * of unbiasedReuse.glsl:139-156 without walking the tree when the answer is already determined, exactly: the pixel's
+ * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every
+ * ray instead (A/B measurements and the tests that require both settings to give identical bits).  Default: 1. */
+int restir_set_ray_elision(restir_context *ctx, int enable);
+
+/* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
 } restir_bvh_info;
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
 /* The same checks restir_upload_bvh runs, on the host and without a context (no GPU needed): RESTIR_E_INVALID

@@ -60,6 +60,7 @@ struct restir_context {
 	bool haveLighting = false;
 	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
 	int traversal = RESTIR_TRAVERSAL_AUTO;
+	int rayElision = 1; // restir_set_ray_elision
 
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
 	uint64_t launches = 0;
@@ -600,6 +601,12 @@ int restir_set_traversal(restir_context *ctx, int mode) {
 	return RESTIR_OK;
 }
 
+int restir_set_ray_elision(restir_context *ctx, int enable) {
+	ENTER(ctx);
+	ctx->rayElision = enable ? 1 : 0;
+	return RESTIR_OK;
+}
+
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out) {
 	if (ctx == nullptr || out == nullptr) {
 		return RESTIR_E_INVALID;
@@ -738,6 +745,7 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 		CU(ctx, launch_trace(tp, kTracePixel, ctx->smCount, ctx->stream));
 		if ((rc = afterLaunch(ctx, "trace_kernel<own>")) != RESTIR_OK) return rc;
 		tp.slots = k;
+		tp.elide = ctx->rayElision;
 		tp.nItems = g.pixelIds * k;
 		tp.neighborPix = ctx->neighborPix;
 		beforeLaunch(ctx, "trace_kernel<neighbours>");

@@ -31,6 +31,7 @@ struct TraceParams {
 	unsigned char *shadowed;           // 1 = shadowed.  kTracePixel: [pixel id * outStride + outOffset]; kTraceUnbiased:
 	                                   // [pixel id * (slots + 1) + slot], the pixel's own ray (traced before, kTracePixel) at slot `slots`
 	unsigned outStride, outOffset;
+	int elide;                         // kTraceUnbiased: answer neighbour rays without a walk where that is exact (restir_trace.cu item_resolve)
 	unsigned long long *counters;
 };
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);

@@ -116,6 +116,9 @@ template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParam
 	opix = (size_t)n;
 	const size_t row = (size_t)p * (tp.slots + 1);
 	out = row + slot;
+	if (!tp.elide) {
+		return kItemRay;
+	}
 	if (tp.shadowed[row + tp.slots] != 0) {
 		return kItemAnswered; // the byte is never read (unbiased_finalize_kernel drops the pixel)
 	}

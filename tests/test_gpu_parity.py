@@ -197,6 +197,32 @@ def test_many_lights_gather_matches_oracle():
     ph.assert_frames_match(ph.run_cuda(case), ph.run_oracle(case), "many-lights")
 
 
+@pytest.mark.parametrize("name", ["procedural:point", "procedural:tri", "sponza"])
+def test_ray_elision_is_exact(name):
+    """The unbiased pass answers some neighbour rays without walking the tree (the pixel's own ray is shadowed; the
+    segment is bit-identical to the neighbour's own ray).  With the shortcut off every ray is walked: both settings
+    must give the oracle's bits and the oracle's testVisibility count, and only the number of walks may differ."""
+    _torch()
+    scene = _scene(name)
+    w, h = 224, 126
+    case = ph.Case(scene, w, h, _cams(name, 3, w, h), unbiased=True, unbiased_neighbors=5)
+    want = ph.run_oracle(case)
+    walked = {}
+    for enable in (1, 0):
+        ctx = ph.make_context(scene)
+        ctx.set_ray_elision(enable)
+        got = ph.run_cuda(case, ctx)
+        ctx.close()
+        ph.assert_frames_match(got, want, f"{name} elision={enable}")
+        walked[enable] = sum(f["counters"]["shadow_rays_traced"] for f in got)
+        asked = sum(f["counters"]["shadow_rays"] for f in got)
+        assert walked[enable] <= asked
+        if not enable:
+            assert walked[enable] == asked
+    print(f"{name}: {walked[0]} rays asked for, {walked[1]} walked with the exact shortcuts on")
+    assert walked[1] < walked[0]
+
+
 # ---- boundary behaviour ---------------------------------------------------------------------------------
 
 def test_reservoir_upload_download_round_trip():
