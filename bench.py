@@ -319,28 +319,46 @@ def main():
         ctx.set_traversal(capi.RESTIR_TRAVERSAL_REFERENCE_ORDER)
     ctx.upload_bvh(scene.nodes, scene.triangles)
     ctx.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
-    if world > 1:
-        ctx.resize_band(w, h, row_begin, row_end, HALO)
-    else:
-        ctx.resize(w, h)
     ctx.set_unbiased_neighbors(cfg["neighbors"] if cfg["unbiased"] else 3)
-    _, _, a0, a1 = ctx.band()
-    rows_alloc = a1 - a0
     own_pixels = (row_end - row_begin) * w
-    renderer = bands.BandRenderer(ctx, h, world, rank, HALO, torch, dist if world > 1 else None)
-
-    # synthetic inputs: two G-buffers (one per camera), rendered on the device by the fixture tool
     dev = f"cuda:{local_rank}"
     tm = torch.from_numpy(np.ascontiguousarray(scene.tri_material)).to(dev)
     mt = torch.from_numpy(scene.material_table().view(np.int32)).to(dev)
-    gb = []
-    for c in cams:
-        planes = [torch.zeros((rows_alloc, w, 4), dtype=torch.uint8, device=dev), torch.zeros((rows_alloc, w, 4), dtype=torch.int16, device=dev),
-                  torch.zeros((rows_alloc, w, 2), dtype=torch.int16, device=dev), torch.zeros((rows_alloc, w, 4), dtype=torch.float32, device=dev),
-                  torch.zeros((rows_alloc, w), dtype=torch.float32, device=dev)]
-        ctx.raycast_gbuffer(c, tm, mt, *planes)
-        gb.append(planes)
-    ctx.synchronize()
+
+    def setup_band(halo_rows):
+        """Allocates the band with `halo_rows` of halo and renders the two synthetic G-buffers (one per camera) on the
+        device with the fixture tool."""
+        if world > 1:
+            ctx.resize_band(w, h, row_begin, row_end, halo_rows)
+        else:
+            ctx.resize(w, h)
+        _, _, a0_, a1_ = ctx.band()
+        rows_ = a1_ - a0_
+        gb_ = []
+        for c in cams:
+            planes = [torch.zeros((rows_, w, 4), dtype=torch.uint8, device=dev), torch.zeros((rows_, w, 4), dtype=torch.int16, device=dev),
+                      torch.zeros((rows_, w, 2), dtype=torch.int16, device=dev), torch.zeros((rows_, w, 4), dtype=torch.float32, device=dev),
+                      torch.zeros((rows_, w), dtype=torch.float32, device=dev)]
+            ctx.raycast_gbuffer(c, tm, mt, *planes)
+            gb_.append(planes)
+        ctx.synchronize()
+        return a0_, a1_, rows_, gb_
+
+    halo = HALO
+    a0, a1, rows_alloc, gb = setup_band(halo)
+    if world > 1:
+        # the halo must also cover the rows temporal reprojection reaches (SURVEY.md §8e: a host-computed bound): the
+        # two cameras alternate, so both directions count; every rank uses the largest reach
+        reach = 0
+        for cur, prv in ((0, 1), (1, 0)):
+            reach = max(reach, bands.temporal_row_reach(gb[cur][3], gb[cur][1], capi.camera_matrix(cams[prv]), w, h, a0, row_begin, row_end, torch))
+        t_reach = torch.tensor([reach], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_reach, op=dist.ReduceOp.MAX)
+        if int(t_reach.item()) > halo:
+            halo = int(t_reach.item())
+            del gb
+            a0, a1, rows_alloc, gb = setup_band(halo)
+    renderer = bands.BandRenderer(ctx, h, world, rank, halo, torch, dist if world > 1 else None)
     out_rgba8 = torch.zeros((rows_alloc, w, 4), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -602,7 +620,7 @@ def main():
                                    f"{'unbiased reuse, ' + str(cfg['neighbors']) + ' neighbours' if cfg['unbiased'] else 'biased reuse 2 passes x ' + str(cfg['neighbors']) + ' neighbours'}, "
                                    f"temporal reuse on, software shadow rays, lights: {scene.light_counts()}",
                        "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
-                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world}, halo {HALO} rows"},
+                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world}, halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
             "rays_per_frame": rays_total / args.steps, "rays_walked_per_frame": traced_prof,
             "rays_note": "value counts the reference's testVisibility calls answered per second (the same unit of work as the --impl reference "
                          "arm); rays_walked_per_frame of them needed a walk of the tree, the rest are answered exactly without one",

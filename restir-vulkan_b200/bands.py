@@ -26,6 +26,30 @@ def halo_rows_for(spatial_radius):
     return int(math.ceil(spatial_radius)) + 1
 
 
+def temporal_row_reach(world_pos, normal, prev_pv, width, height, alloc_begin, row_begin, row_end, torch):
+    """How many rows the temporal reprojection of restirOmni.glsl:163-171 moves this band's pixels, at most.
+
+    world_pos: (rows, W, 4) float32 and normal: (rows, W, 4) int16 device planes covering rows [alloc_begin, ...);
+    prev_pv: the 16 floats of prevFrameProjectionViewMatrix (column-major).  Only the band's own rows and only
+    surface pixels count (a background pixel never passes the normal gate, restir_kernels.cu omni_temporal_kernel);
+    pixels that reproject outside the screen are not looked up by the shader.  The host sizes the halo from the
+    largest reach over all ranks (+1 row of slack for the float evaluation order, which is not the kernel's).
+    """
+    wp = world_pos[row_begin - alloc_begin: row_end - alloc_begin, :, :3].to(torch.float32)
+    surf = (normal[row_begin - alloc_begin: row_end - alloc_begin, :, :3] != 0).any(dim=-1)
+    m = [float(v) for v in prev_pv]
+    x, y, z = wp[..., 0], wp[..., 1], wp[..., 2]
+    px = m[0] * x + m[4] * y + m[8] * z + m[12]
+    py = m[1] * x + m[5] * y + m[9] * z + m[13]
+    pw = m[3] * x + m[7] * y + m[11] * z + m[15]
+    sx = (px / pw + 1.0) * 0.5 * width
+    sy = (py / pw + 1.0) * 0.5 * height
+    inside = (sx > 0) & (sy > 0) & (sx < width) & (sy < height) & surf
+    rows = torch.arange(row_begin, row_end, device=wp.device, dtype=torch.float32)[:, None]
+    reach = torch.where(inside, (torch.trunc(sy) - rows).abs(), torch.zeros_like(sy))
+    return int(reach.max().item()) + 1 if reach.numel() else 0
+
+
 def halo_plan(height, world, rank, halo):
     """Messages of one exchange for `rank`: list of (peer, send_rows, recv_rows) with rows as global [lo, hi).
 

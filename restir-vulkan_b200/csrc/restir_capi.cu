@@ -3,7 +3,9 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -26,7 +28,9 @@ struct restir_context {
 
 	// scene
 	float4 *nodes = nullptr, *tris = nullptr;
-	float4 *image = nullptr; // 64-byte re-stride of `nodes` (traversal_image.h); null => literal 80-byte walk
+	float4 *image = nullptr; // 64-byte image of `nodes` (traversal_image.h); null => literal 80-byte walk
+	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `tris`: what the trace kernel walks, pinned in L2
+	size_t treeBlockBytes = 0;
 	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
 	int smCount = 0;
@@ -338,8 +342,7 @@ void restir_destroy(restir_context *ctx) {
 	dropGBuffers(ctx);
 	dropProfile(ctx);
 	freeDev(ctx->nodes);
-	freeDev(ctx->tris);
-	freeDev(ctx->image);
+	freeDev(ctx->treeBlock); // image + tris
 	freeDev(ctx->shadowed);
 	freeDev(ctx->neighborPix);
 	freeDev(ctx->pointBlob);
@@ -385,18 +388,43 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	freeDev(ctx->nodes);
-	freeDev(ctx->tris);
-	freeDev(ctx->image);
+	freeDev(ctx->treeBlock);
+	ctx->tris = ctx->image = nullptr;
 	ctx->nNodes = ctx->nTris = 0;
+	const bool useImage = info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	const size_t imageBytes = useImage ? ((image.size() * sizeof(Node64) + 255) & ~(size_t)255) : 0;
+	const size_t triBytes = (size_t)n_triangles * sizeof(restir_triangle);
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
-	CU(ctx, cudaMalloc(&ctx->tris, (size_t)n_triangles * sizeof(restir_triangle)));
+	CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + triBytes));
+	ctx->treeBlockBytes = imageBytes + triBytes;
+	ctx->tris = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
 	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
-	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, (size_t)n_triangles * sizeof(restir_triangle), cudaMemcpyHostToDevice, ctx->stream));
-	if (info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER) {
-		CU(ctx, cudaMalloc(&ctx->image, image.size() * sizeof(Node64)));
+	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, triBytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (useImage) {
+		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
 		CU(ctx, cudaMemcpyAsync(ctx->image, image.data(), image.size() * sizeof(Node64), cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	{
+		// keep what the trace kernel walks resident in L2 (126 MB on B200): the per-frame streams (G-buffer, reservoirs:
+		// ~0.5 GB at 1080p) would otherwise push tree lines out between two launches of the trace kernel.  Best effort:
+		// a device without the feature just runs without it.
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 &&
+		    std::getenv("RESTIR_NO_L2_PERSIST") == nullptr) {
+			size_t want = std::min(ctx->treeBlockBytes, (size_t)prop.persistingL2CacheMaxSize);
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+				cudaStreamAttrValue attr{};
+				attr.accessPolicyWindow.base_ptr = ctx->treeBlock;
+				attr.accessPolicyWindow.num_bytes = std::min(ctx->treeBlockBytes, (size_t)prop.accessPolicyMaxWindowSize);
+				attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+				attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+			}
+			cudaGetLastError(); // best effort: never sticky
+		}
+	}
 	ctx->nNodes = n_nodes;
 	ctx->nTris = n_triangles;
 	ctx->imageInfo = info;

@@ -305,8 +305,11 @@ __global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, P
 			res.sumWeights = 0.0f;
 			dirty = true;
 		}
-		// temporal reuse, :163-209
-		if ((p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0) {
+		// temporal reuse, :163-209.  A background pixel (normal == 0, gBufferPass.cpp:117-123) can never pass the
+		// normal gate (:183, dot(0, n') = 0 > 0.5 is false), so its reprojection — which lands wherever the world
+		// origin projects to, usually far outside a row band — is not even looked up.
+		f3 normal = fetch_normal(p.cur, pix);
+		if ((p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0 && dot3(normal, normal) != 0.0f) {
 			f3 worldPos = fetch_world_pos(p.cur, pix);
 			const float *M = p.u.prevFrameProjectionViewMatrix;
 			float px = ((M[0] * worldPos.x + M[4] * worldPos.y) + M[8] * worldPos.z) + M[12] * 1.0f;
@@ -328,7 +331,6 @@ __global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, P
 						f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
 						f3 da = albedo - fetch_albedo(p.prev, sc.srgbLut, ppix, nullptr);
 						if (dot3(da, da) < 0.01f) {
-							f3 normal = fetch_normal(p.cur, pix);
 							float nd = dot3(normal, fetch_normal(p.prev, ppix));
 							if (nd > 0.5f) {
 								float roughness, metallic;
@@ -338,9 +340,7 @@ __global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, P
 								Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
 								// the pixel's RNG stream, advanced past the candidate loop's draws (:106-142)
 								Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);
-								if (dot3(normal, normal) != 0.0f) {
-									rng.state = jump.A * rng.state + jump.G * rng.inc;
-								}
+								rng.state = jump.A * rng.state + jump.G * rng.inc;
 								PackedReservoir prevRes = load_reservoir(prevReservoirs, ppix);
 								prevRes.M = min(prevRes.M, p.u.temporalSampleCountMultiplier * res.M); // :189-191
 								combine_reservoirs(res, prevRes, sc, sf, albedoLum, rng);

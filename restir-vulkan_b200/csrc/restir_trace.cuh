@@ -3,7 +3,7 @@
 //   segment_setup / test_visibility   <- src/shaders/include/visibilityTest.glsl:1-4, 27-28 (software branch)
 //   ray_box_reference, ray_triangle   <- src/shaders/include/softwareRaytracing.glsl:9-14, 15-37
 //   trace_any_reference               <- softwareRaytracing.glsl:39-85, in the reference's node order
-//   trace_any_image                   the same walk over the 64-byte re-stride of the same tree (traversal_image.h)
+//   trace_any_image                   the same walk over the 64-byte image of the same tree (traversal_image.h)
 #pragma once
 
 #include "restir_device.cuh"
@@ -115,7 +115,7 @@ __device__ __forceinline__ bool test_visibility_reference(const SceneView &sc, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same walk over the 64-byte image of the same tree (traversal_image.h): four 16-byte loads per node
+// The same walk over the 64-byte image of the same tree (traversal_image.h): two 32-byte loads per node
 // from one 128-byte line.  Only used when the tree's worst-case stack occupancy is <= 32 (checked at upload),
 // so no push can be dropped and the stack needs no bound checks; the node about to be visited stays in a
 // register instead of going through the stack.  Order of visits and triangle tests is the reference's: left

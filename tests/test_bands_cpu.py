@@ -80,3 +80,32 @@ def test_exchange_halo_over_gloo(world, tmp_path):
         for y in range(a0, a1):
             owner = [r for r in range(world) if bands.band_rows(h, world, r)[0] <= y < bands.band_rows(h, world, r)[1]][0]
             assert (got[y - a0] == y * 1000.0 + owner).all(), (rank, y)
+
+
+def test_temporal_row_reach_bounds_the_reprojection():
+    """bands.temporal_row_reach: the halo a moving camera needs (restirOmni.glsl:163-171 on the host, per band)."""
+    import torch
+
+    bands = __import__("restir_vulkan_b200.bands", fromlist=["bands"])
+    w, h = 8, 40
+    alloc_begin, row_begin, row_end = 5, 10, 30
+    rows = 30
+    # clip = (x, y, 0, 1): column-major prev_pv with px = x, py = y, pw = 1
+    pv = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]
+    world = torch.zeros((rows, w, 4), dtype=torch.float32)
+    normal = torch.zeros((rows, w, 4), dtype=torch.int16)
+    for r in range(rows):
+        g = r + alloc_begin                       # global row; send it to row g + 3.25
+        world[r, :, 1] = (g + 3.25) / h * 2.0 - 1.0
+        world[r, :, 0] = 0.0
+    normal[..., 2] = 32767
+    assert bands.temporal_row_reach(world, normal, pv, w, h, alloc_begin, row_begin, row_end, torch) == 3 + 1
+    # a far jump on a background pixel (normal == 0) does not count; on a surface pixel it does
+    world[12, 3, 1] = (2 + 0.5) / h * 2.0 - 1.0   # global row 17 -> row 2
+    normal[12, 3, :] = 0
+    assert bands.temporal_row_reach(world, normal, pv, w, h, alloc_begin, row_begin, row_end, torch) == 4
+    normal[12, 3, 2] = 32767
+    assert bands.temporal_row_reach(world, normal, pv, w, h, alloc_begin, row_begin, row_end, torch) == 15 + 1
+    # pixels reprojected off-screen are not looked up
+    world[12, 3, 1] = 5.0
+    assert bands.temporal_row_reach(world, normal, pv, w, h, alloc_begin, row_begin, row_end, torch) == 4
