@@ -259,7 +259,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="sponza_1080p_unbiased5", choices=sorted(CONFIGS))
@@ -498,9 +498,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top], "kernel_ms": top_ms,
                 "launches_per_frame": kernel_launches[top],
-                "note": "the trace kernel is bound by instruction issue (~80 % issue-active) and L1 wavefronts (~80 % l1tex), not by HBM: the tree "
-                        "is L2/L1-resident and DRAM sits below 1 %; its yardsticks are Mrays/s and lanes per instruction (profiles/); the "
-                        "streaming kernels' HBM fractions are in kernel_hbm_frac"}
+                "note": "the trace kernel is bound by L1 tag lookups (83 % l1tex) and instruction issue (71 % issue-active) together, not by HBM: "
+                        "the tree is L2/L1-resident and DRAM sits below 2 % (profiles/r1_m_summary.md); its yardsticks are Mrays/s and lanes per "
+                        "instruction; the streaming kernels' HBM fractions are in kernel_hbm_frac"}
     kernel_hbm_frac = {n: (alg[n] * kernel_launches[n] / (kernel_ms[n] * 1e-3) / 1e9 / peak) for n in kernel_ms if alg.get(n)}
     frame_bytes = sum(alg[n] * kernel_launches[n] for n in kernel_ms if alg.get(n))
     hbm_frame_frac = frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak
