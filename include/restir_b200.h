@@ -236,6 +236,10 @@ typedef struct restir_camera { /* src/camera.h:7-13 */
 } restir_camera;
 /* src/camera.h:25-50: column-major projectionViewMatrix. */
 int restir_camera_matrix(const restir_camera *camera, float out_pv[16]);
+/* Device self-test (no reference equivalent): runs n pseudo-random operand pairs through the packed two-at-a-time
+ * arithmetic of the candidate kernel (csrc/restir_math2.cuh: division, reciprocal, square root, evaluatePHat) and
+ * through the scalar arithmetic policy, and counts results whose bits differ: mismatches[0..3]; [4] = values compared. */
+int restir_tools_selftest_packed_math(restir_context *ctx, uint64_t n, uint32_t seed, uint64_t mismatches[5]);
 /* Primary-visibility ray cast of the uploaded BVH into the five G-buffer planes (DEVICE pointers, rows
  * [alloc_begin, alloc_end) of the context's screen), semantics in SURVEY.md §8d / Appendix E.
  * tri_material: DEVICE int32[n_triangles]; material_table: DEVICE uint32[n_materials][4] =

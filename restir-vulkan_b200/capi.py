@@ -66,7 +66,7 @@ EXPORTS = [
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_collect_triangle_lights",
     "restir_generate_random_point_lights", "restir_create_alias_table", "restir_camera_matrix",
-    "restir_tools_raycast_gbuffer",
+    "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math",
 ]
 
 
@@ -316,6 +316,12 @@ class RestirContext:
 
     def set_unbiased_neighbors(self, n):
         self._check(self.lib.restir_set_unbiased_neighbors(self._ctx, C.c_uint32(n)))
+
+    def selftest_packed_math(self, n, seed=1):
+        """(div2, rcp2, sqrt2, evaluate_phat2 mismatches against the scalar policy, values compared)."""
+        out = (C.c_uint64 * 5)()
+        self._check(self.lib.restir_tools_selftest_packed_math(self._ctx, C.c_uint64(n), C.c_uint32(seed), out))
+        return tuple(int(v) for v in out)
 
     def set_ray_elision(self, enable):
         self._check(self.lib.restir_set_ray_elision(self._ctx, C.c_int(1 if enable else 0)))

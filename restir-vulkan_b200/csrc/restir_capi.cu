@@ -65,6 +65,10 @@ struct restir_context {
 	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
 	int traversal = RESTIR_TRAVERSAL_AUTO;
 	int rayElision = 1; // restir_set_ray_elision
+	// RESTIR_CANDIDATES_PAIRED=1 selects the two-candidates-per-iteration kernel (restir_math2.cuh): bit-identical, 22 %
+	// fewer instructions, but 93 registers and per-operation range checks — 4 % faster on Sponza / 200 lights, 10 % slower
+	// with triangle lights or 1 M lights (profiles/r1_m_summary.md), so the scalar kernel stays the default
+	bool scalarCandidates = true;
 
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
 	uint64_t launches = 0;
@@ -292,6 +296,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		return RESTIR_E_NOMEM;
 	}
 	ctx->device = device;
+	if (const char *e = std::getenv("RESTIR_CANDIDATES_PAIRED")) ctx->scalarCandidates = std::atoi(e) == 0;
 	int rc = RESTIR_OK;
 	do {
 		if ((rc = cudaCheck(ctx, cudaSetDevice(device), "cudaSetDevice")) != RESTIR_OK) break;
@@ -629,6 +634,28 @@ int restir_set_traversal(restir_context *ctx, int mode) {
 	return RESTIR_OK;
 }
 
+int restir_tools_selftest_packed_math(restir_context *ctx, uint64_t n, uint32_t seed, uint64_t mismatches[5]) {
+	ENTER(ctx);
+	if (mismatches == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "null result array");
+	}
+	unsigned long long *dev = nullptr;
+	CU(ctx, cudaMalloc(&dev, 5 * sizeof(unsigned long long)));
+	CU(ctx, cudaMemsetAsync(dev, 0, 5 * sizeof(unsigned long long), ctx->stream));
+	launch_selftest_packed(n, seed, dev, ctx->stream);
+	int rc = afterLaunch(ctx, "selftest_packed_kernel");
+	unsigned long long h[5] = {0, 0, 0, 0, 0};
+	if (rc == RESTIR_OK) {
+		rc = cudaCheck(ctx, cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "memcpy");
+	}
+	if (rc == RESTIR_OK) {
+		rc = cudaCheck(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+	}
+	cudaFree(dev);
+	for (int k = 0; k < 5; ++k) mismatches[k] = h[k];
+	return rc;
+}
+
 int restir_set_ray_elision(restir_context *ctx, int enable) {
 	ENTER(ctx);
 	ctx->rayElision = enable ? 1 : 0;
@@ -693,7 +720,7 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	if (temporal && (rc = waitUpload(ctx, gbuffer ^ 1)) != RESTIR_OK) return rc;
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "omni_candidates_kernel");
-	launch_omni_candidates(p, out, ctx->stream);
+	launch_omni_candidates(p, out, ctx->scalarCandidates, ctx->stream);
 	if ((rc = afterLaunch(ctx, "omni_candidates_kernel")) != RESTIR_OK) return rc;
 	if (vis) {
 		TraceParams tp = traceParams(ctx);

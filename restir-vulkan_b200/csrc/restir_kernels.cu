@@ -1,6 +1,6 @@
 // restir_kernels.cu — hand-written sm_100a per-pixel kernels of the ReSTIR resampling path.
 //
-//   omni_candidates_kernel    <- src/shaders/restirOmni.glsl:86-145   (RIS over the alias table)
+//   omni_candidates_kernel    <- src/shaders/restirOmni.glsl:86-145   (RIS over the alias table; _paired_: opt-in variant)
 //   omni_temporal_kernel      <- src/shaders/restirOmni.glsl:148-212  (apply the visibility bit, temporal reuse)
 //   spatial_reuse_kernel      <- src/shaders/spatialReuse.comp:30-86
 //   unbiased_merge_kernel     <- src/shaders/unbiasedReuse.glsl:50-124
@@ -20,6 +20,7 @@
 
 #include "restir_device.cuh"
 #include "restir_kernels.h"
+#include "restir_math2.cuh"
 
 namespace restir {
 
@@ -279,6 +280,119 @@ __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p,
 				selSum = res.sumWeights;
 				selM = res.M;
 			}
+		}
+		if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
+			res.w = selSum / ((float)selM * res.pHat);
+		}
+	}
+	store_reservoir(out, pix, res);                                           // handed to the trace kernel and omni_temporal_kernel
+}
+
+// The same loop, two candidates per iteration (restir_math2.cuh): candidate i and i + 1 are sampled one after the
+// other — the RNG draws keep the reference's order: r1, r2[, r3, r4], update draw, per candidate — evaluated side by
+// side with packed arithmetic, and folded into the reservoir in order.  No candidate takes a shortcut here: a light
+// behind the surface goes through the same instructions with p̂ = +0 selected at the end (weight +0: sumWeights and
+// the selection are unchanged, as in the scalar kernel's early `continue`).  An odd candidate count ends with one
+// candidate whose partner is a copy that is not folded in.
+#ifndef RESTIR_CANDIDATES_MIN_BLOCKS
+#define RESTIR_CANDIDATES_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kThreads, RESTIR_CANDIDATES_MIN_BLOCKS) omni_candidates_paired_kernel(PassParams p, PackedReservoir *__restrict__ out) {
+	int x, y;
+	if (!pixel_of_thread(p.band, x, y)) {
+		return;
+	}
+	const SceneView &sc = p.scene;
+	size_t pix = local_index(p.band, x, y);
+	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
+	f3 normal = fetch_normal(p.cur, pix);
+	float roughness, metallic;
+	fetch_material(p.cur, pix, roughness, metallic);
+	f3 worldPos = fetch_world_pos(p.cur, pix);
+	float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
+	f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+
+	PackedReservoir res;                                                      // :105
+	res.px = res.py = res.pz = 0.0f;
+	res.lightIndex = 0;
+	res.pHat = res.sumWeights = res.w = 0.0f;
+	res.M = 0u;
+	if (dot3(normal, normal) != 0.0f) {                                       // :107
+		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
+		const uint32_t count = p.u.initialLightSampleCount;
+		const bool pointMode = sc.pointCount != 0;
+		float selSum = 0.0f;
+		uint32_t selM = 0u;
+		for (uint32_t i = 0; i < count; i += 2) {                             // :108-142, candidates i and i + 1
+			const bool pair = i + 1 < count;
+			int idx[2], lightIndex[2];
+			float prob[2], u[2], r3[2], r4[2];
+#pragma unroll
+			for (int c = 0; c < 2; ++c) {
+				if (c == 1 && !pair) {
+					idx[1] = idx[0]; prob[1] = prob[0]; u[1] = 2.0f; r3[1] = r3[0]; r4[1] = r4[0];
+					break;
+				}
+				float r1 = pcg_float(rng);
+				float r2 = pcg_float(rng);
+				alias_sample(sc, r1, r2, idx[c], prob[c]);
+				r3[c] = r4[c] = 0.0f;
+				if (!pointMode) {
+					r3[c] = pcg_float(rng);
+					r4[c] = pcg_float(rng);
+				}
+				u[c] = pcg_float(rng);                                        // updateReservoirAt's draw, reservoir.glsl:15
+			}
+			f32 lpos, ln;
+			f2 lum, prob2 = mk2(prob[0], prob[1]);
+			if (pointMode) {                                                  // :116-122
+				float4 pa = __ldg(sc.pointPosLum + idx[0]), pb = __ldg(sc.pointPosLum + idx[1]);
+				lpos = f32{mk2(pa.x, pb.x), mk2(pa.y, pb.y), mk2(pa.z, pb.z)};
+				lum = mk2(pa.w, pb.w);
+				lightIndex[0] = idx[0];
+				lightIndex[1] = idx[1];
+				ln = f32{bc2(0.0f), bc2(0.0f), bc2(0.0f)};
+			} else {                                                          // :123-133
+				const float4 *ta = reinterpret_cast<const float4 *>(sc.triLights + idx[0]);
+				const float4 *tb = reinterpret_cast<const float4 *>(sc.triLights + idx[1]);
+				float4 a0 = __ldg(ta), b0 = __ldg(ta + 1), c0 = __ldg(ta + 2), e0 = __ldg(ta + 3), n0 = __ldg(ta + 4);
+				float4 a1 = __ldg(tb), b1 = __ldg(tb + 1), c1 = __ldg(tb + 2), e1 = __ldg(tb + 3), n1 = __ldg(tb + 4);
+				f2 sq = sqrt2(mk2(r3[0], r3[1]));                              // pickPointOnTriangle :68-71
+				f2 rr4 = mk2(r4[0], r4[1]);
+				f2 w1 = sub2(bc2(1.0f), sq), w2 = mul2(sq, sub2(bc2(1.0f), rr4)), w3 = mul2(rr4, sq);
+				lpos.x = addp2(addp2(mul2(mk2(a0.x, a1.x), w1), mul2(mk2(b0.x, b1.x), w2)), mul2(mk2(c0.x, c1.x), w3));
+				lpos.y = addp2(addp2(mul2(mk2(a0.y, a1.y), w1), mul2(mk2(b0.y, b1.y), w2)), mul2(mk2(c0.y, c1.y), w3));
+				lpos.z = addp2(addp2(mul2(mk2(a0.z, a1.z), w1), mul2(mk2(b0.z, b1.z), w2)), mul2(mk2(c0.z, c1.z), w3));
+				lum = mk2(e0.w, e1.w);
+				lightIndex[0] = -1 - idx[0];
+				lightIndex[1] = -1 - idx[1];
+				f32 wi = normalize32(sub32(bc32(worldPos), lpos));
+				ln = f32{mk2(n0.x, n1.x), mk2(n0.y, n1.y), mk2(n0.z, n1.z)};
+				prob2 = div2(prob2, mul2(abs2(dot32(wi, ln)), mk2(n0.w, n1.w)));
+			}
+			f2 pHat = evaluate_phat2(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
+			// addSampleToReservoir + updateReservoirAt for i, then for i + 1: reservoir.glsl:28-42, 6-26
+			f2 weight = div2(pHat, prob2);
+			float s1 = res.sumWeights + weight.x;
+			float s2 = pair ? s1 + weight.y : s1;
+			f2 replacePossibility = div2(weight, mk2(s1, s2));
+			if (u[0] < replacePossibility.x) {
+				res.px = lpos.x.x; res.py = lpos.y.x; res.pz = lpos.z.x;
+				res.lightIndex = lightIndex[0];
+				res.pHat = pHat.x;
+				selSum = s1;
+				selM = res.M + 1u;
+			}
+			if (pair && u[1] < replacePossibility.y) {
+				res.px = lpos.x.y; res.py = lpos.y.y; res.pz = lpos.z.y;
+				res.lightIndex = lightIndex[1];
+				res.pHat = pHat.y;
+				selSum = s2;
+				selM = res.M + 2u;
+			}
+			res.sumWeights = s2;
+			res.M += pair ? 2u : 1u;
 		}
 		if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
 			res.w = selSum / ((float)selM * res.pHat);
@@ -744,8 +858,12 @@ PassGrid pass_grid(const Band &b) {
 	return PassGrid{g.x, g.y, g.x * 4u, 256ull * g.x * g.y};
 }
 
-void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s) {
-	omni_candidates_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, bool scalar, cudaStream_t s) {
+	if (scalar) {
+		omni_candidates_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
+	} else {
+		omni_candidates_paired_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
+	}
 }
 void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s) {
 	LcgJump jump = lcg_jump((uint64_t)p.u.initialLightSampleCount * draws_per_candidate(p.scene.pointCount != 0));

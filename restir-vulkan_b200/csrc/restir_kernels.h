@@ -47,7 +47,7 @@ PassGrid pass_grid(const Band &b);
 
 // restirOmni.glsl:108-142 (candidates) and :148-209 (apply visibility, temporal reuse); between the two the
 // trace kernel runs in kTracePixel mode on `out`.
-void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s);
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, bool scalar, cudaStream_t s); // scalar: one candidate per iteration (A/B)
 void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s);
 void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s);
 // unbiasedReuse.glsl:84-124 (merge) and :126-182 (normalisation from the visibility bits); the trace kernel
@@ -62,5 +62,8 @@ void launch_unpack_reservoirs(const SceneView &sc, const PackedReservoir *in, re
 void launch_pack_reservoirs(const restir_reservoir *in, PackedReservoir *out, size_t n, cudaStream_t s);
 void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
                                 cudaStream_t s);
+
+// restir_selftest.cu: mismatch[0..3] = div2, rcp2, sqrt2, evaluate_phat2 results differing from the scalar policy; [4] = values compared
+void launch_selftest_packed(uint64_t n, uint32_t seed, unsigned long long *mismatch, cudaStream_t s);
 
 } // namespace restir
