@@ -269,6 +269,7 @@ def main():
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep bands of equal height instead of equal measured cost")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -320,16 +321,15 @@ def main():
     ctx.upload_bvh(scene.nodes, scene.triangles)
     ctx.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
     ctx.set_unbiased_neighbors(cfg["neighbors"] if cfg["unbiased"] else 3)
-    own_pixels = (row_end - row_begin) * w
     dev = f"cuda:{local_rank}"
     tm = torch.from_numpy(np.ascontiguousarray(scene.tri_material)).to(dev)
     mt = torch.from_numpy(scene.material_table().view(np.int32)).to(dev)
 
-    def setup_band(halo_rows):
-        """Allocates the band with `halo_rows` of halo and renders the two synthetic G-buffers (one per camera) on the
-        device with the fixture tool."""
+    def setup_band(rows, halo_rows):
+        """Allocates the band `rows` with `halo_rows` of halo and renders the two synthetic G-buffers (one per camera)
+        on the device with the fixture tool."""
         if world > 1:
-            ctx.resize_band(w, h, row_begin, row_end, halo_rows)
+            ctx.resize_band(w, h, rows[0], rows[1], halo_rows)
         else:
             ctx.resize(w, h)
         _, _, a0_, a1_ = ctx.band()
@@ -344,28 +344,62 @@ def main():
         ctx.synchronize()
         return a0_, a1_, rows_, gb_
 
-    halo = HALO
-    a0, a1, rows_alloc, gb = setup_band(halo)
-    if world > 1:
-        # the halo must also cover the rows temporal reprojection reaches (a host-computed bound): the
-        # two cameras alternate, so both directions count; every rank uses the largest reach
-        reach = 0
-        for cur, prv in ((0, 1), (1, 0)):
-            reach = max(reach, bands.temporal_row_reach(gb[cur][3], gb[cur][1], capi.camera_matrix(cams[prv]), w, h, a0, row_begin, row_end, torch))
-        t_reach = torch.tensor([reach], dtype=torch.int64, device=dev)
-        dist.all_reduce(t_reach, op=dist.ReduceOp.MAX)
-        if int(t_reach.item()) > halo:
-            halo = int(t_reach.item())
-            del gb
-            a0, a1, rows_alloc, gb = setup_band(halo)
-    renderer = bands.BandRenderer(ctx, h, world, rank, halo, torch, dist if world > 1 else None)
-    out_rgba8 = torch.zeros((rows_alloc, w, 4), dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    def build_bands(bounds, halo_rows):
+        """Band of this rank under `bounds` with a halo that also covers the rows temporal reprojection reaches
+        (a host-computed bound; the two cameras alternate, so both directions count; every rank uses the
+        largest reach)."""
+        rows = bands.band_rows(h, world, rank, bounds)
+        a0_, a1_, rows_alloc_, gb_ = setup_band(rows, halo_rows)
+        if world > 1:
+            reach = 0
+            for cur, prv in ((0, 1), (1, 0)):
+                reach = max(reach, bands.temporal_row_reach(gb_[cur][3], gb_[cur][1], capi.camera_matrix(cams[prv]), w, h, a0_, rows[0], rows[1], torch))
+            t_reach = torch.tensor([reach], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_reach, op=dist.ReduceOp.MAX)
+            if int(t_reach.item()) > halo_rows:
+                halo_rows = int(t_reach.item())
+                del gb_
+                a0_, a1_, rows_alloc_, gb_ = setup_band(rows, halo_rows)
+        r_ = bands.BandRenderer(ctx, h, world, rank, halo_rows, torch, dist if world > 1 else None, bounds=bounds)
+        for s_ in (0, 1):
+            ctx.bind_gbuffer(s_, *gb_[s_])
+        return rows, a0_, a1_, rows_alloc_, gb_, halo_rows, r_
 
     def set_frame(f):
         u, lu = make_uniform_blocks(capi, capi.camera_matrix, cfg, w, h, cams, f)
         ctx.set_uniforms(u)
         ctx.set_lighting_uniforms(lu)
+
+    bounds = [bands.band_rows(h, world, r)[0] for r in range(world)] + [h]
+    (row_begin, row_end), a0, a1, rows_alloc, gb, halo, renderer = build_bands(bounds, HALO)
+    balance_note = "equal heights"
+    if world > 1 and not args.no_balance:
+        # bands of equal cost instead of equal height: every rank times its own kernels over two frames (events inside the
+        # library, no peer waits in them), the times are gathered and the boundaries re-cut; twice, since the cost inside a
+        # band is only known as its average
+        for _ in range(2):
+            for f in range(2):
+                set_frame(f)
+                renderer.frame(f & 1, cfg["unbiased"], 1)
+            torch.cuda.synchronize()
+            ctx.profile_begin()
+            for f in range(2, 4):
+                set_frame(f)
+                renderer.frame(f & 1, cfg["unbiased"], 1)
+            mine = sum(ms for _, ms in ctx.profile_end().values())
+            gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(gathered, torch.tensor([mine], dtype=torch.float64, device=dev))
+            secs = [float(g.item()) for g in gathered]
+            new_bounds = bands.balanced_bounds(h, world, bounds, secs, halo)
+            if new_bounds == bounds:
+                break
+            bounds = new_bounds
+            del gb, renderer
+            (row_begin, row_end), a0, a1, rows_alloc, gb, halo, renderer = build_bands(bounds, halo)
+        balance_note = f"equal cost, rows per band {[bounds[r + 1] - bounds[r] for r in range(world)]}"
+    own_pixels = (row_end - row_begin) * w
+    out_rgba8 = torch.zeros((rows_alloc, w, 4), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def device_step(f):
         i = f & 1
@@ -620,7 +654,7 @@ def main():
                                    f"{'unbiased reuse, ' + str(cfg['neighbors']) + ' neighbours' if cfg['unbiased'] else 'biased reuse 2 passes x ' + str(cfg['neighbors']) + ' neighbours'}, "
                                    f"temporal reuse on, software shadow rays, lights: {scene.light_counts()}",
                        "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
-                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world}, halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
+                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world} ({balance_note}), halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
             "rays_per_frame": rays_total / args.steps, "rays_walked_per_frame": traced_prof,
             "rays_note": "value counts the reference's testVisibility calls answered per second (the same unit of work as the --impl reference "
                          "arm); rays_walked_per_frame of them needed a walk of the tree, the rest are answered exactly without one",

@@ -14,11 +14,43 @@ is no collective on the data path.
 import math
 
 
-def band_rows(height, world, rank):
-    """Contiguous, near-equal row bands: rank r owns [begin, end)."""
+def band_rows(height, world, rank, bounds=None):
+    """Contiguous row bands: rank r owns [begin, end).  Near-equal heights, or `bounds` (world + 1 ascending row
+    indices from 0 to height, e.g. from balanced_bounds)."""
+    if bounds is not None:
+        assert len(bounds) == world + 1 and bounds[0] == 0 and bounds[-1] == height
+        return int(bounds[rank]), int(bounds[rank + 1])
     base, extra = divmod(height, world)
     begin = rank * base + min(rank, extra)
     return begin, begin + base + (1 if rank < extra else 0)
+
+
+def balanced_bounds(height, world, bounds, seconds, min_rows):
+    """Band boundaries of equal COST instead of equal height.
+
+    `seconds[r]` is what rank r needed for its band [bounds[r], bounds[r+1]) (the frame time is the slowest band's:
+    sky rows make no candidates and no rays, floor rows trace the longest ones).  Cost is taken as uniform inside each
+    measured band (a piecewise-constant density over the rows) and the new boundaries cut its integral into `world`
+    equal parts, every band at least `min_rows` high (the halo must fit into a neighbour's band, halo_plan).
+    Deterministic: every rank computes the same boundaries from the same gathered times.
+    """
+    assert len(bounds) == world + 1 and len(seconds) == world
+    density = []
+    for r in range(world):
+        rows = bounds[r + 1] - bounds[r]
+        density.extend([max(float(seconds[r]), 1e-9) / rows] * rows)
+    total = sum(density)
+    new, acc, y = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while y < height and acc + density[y] <= target:
+            acc += density[y]
+            y += 1
+        lo = new[-1] + min_rows
+        hi = height - (world - r) * min_rows
+        new.append(min(max(y, lo), hi))
+    new.append(height)
+    return new
 
 
 def halo_rows_for(spatial_radius):
@@ -50,18 +82,18 @@ def temporal_row_reach(world_pos, normal, prev_pv, width, height, alloc_begin, r
     return int(reach.max().item()) + 1 if reach.numel() else 0
 
 
-def halo_plan(height, world, rank, halo):
+def halo_plan(height, world, rank, halo, bounds=None):
     """Messages of one exchange for `rank`: list of (peer, send_rows, recv_rows) with rows as global [lo, hi).
 
     A rank sends the first/last `halo` rows it OWNS and receives the `halo` rows just outside its band, each
     clipped to the peer's band (bands thinner than the halo would need a second hop: rejected).
     """
-    begin, end = band_rows(height, world, rank)
+    begin, end = band_rows(height, world, rank, bounds)
     plan = []
     for peer in (rank - 1, rank + 1):
         if peer < 0 or peer >= world:
             continue
-        pb, pe = band_rows(height, world, peer)
+        pb, pe = band_rows(height, world, peer, bounds)
         if pe - pb < halo or end - begin < halo:
             raise ValueError(f"band of {min(pe - pb, end - begin)} rows is thinner than the {halo}-row halo")
         if peer < rank:
@@ -113,10 +145,10 @@ class BandRenderer:
     """Drives one band context through App's pass order (src/app.h:212-262) with the halo exchanges between
     the passes.  With world == 1 it degenerates to restir_frame + lighting."""
 
-    def __init__(self, ctx, height, world, rank, halo, torch, dist=None, group=None):
+    def __init__(self, ctx, height, world, rank, halo, torch, dist=None, group=None, bounds=None):
         self.ctx, self.world, self.rank, self.torch, self.dist, self.group = ctx, world, rank, torch, dist, group
         self.height, self.halo = height, halo
-        self.plan = halo_plan(height, world, rank, halo) if world > 1 else []
+        self.plan = halo_plan(height, world, rank, halo, bounds) if world > 1 else []
         self.alloc_begin = ctx.band()[2]
         self._views = {}
 

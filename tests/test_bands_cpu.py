@@ -109,3 +109,30 @@ def test_temporal_row_reach_bounds_the_reprojection():
     # pixels reprojected off-screen are not looked up
     world[12, 3, 1] = 5.0
     assert bands.temporal_row_reach(world, normal, pv, w, h, alloc_begin, row_begin, row_end, torch) == 4
+
+
+def test_balanced_bounds_equalise_cost():
+    """bands.balanced_bounds: boundaries of equal cost from per-band times, minimum band height respected."""
+    bands = __import__("restir_vulkan_b200.bands", fromlist=["bands"])
+    h, world = 4320, 8
+    equal = [bands.band_rows(h, world, r)[0] for r in range(world)] + [h]
+    # uniform cost: nothing moves (up to a row)
+    same = bands.balanced_bounds(h, world, equal, [1.0] * world, 137)
+    assert all(abs(a - b) <= 1 for a, b in zip(same, equal))
+    # the top band is three times cheaper per row, the bottom one twice as expensive: the cuts move accordingly
+    secs = [1.0 / 3.0, 1, 1, 1, 1, 1, 1, 2.0]
+    new = bands.balanced_bounds(h, world, equal, secs, 137)
+    assert new[0] == 0 and new[-1] == h and all(b - a >= 137 for a, b in zip(new, new[1:]))
+    dens = []
+    for r in range(world):
+        dens += [secs[r] / (equal[r + 1] - equal[r])] * (equal[r + 1] - equal[r])
+    cost = [sum(dens[new[r]:new[r + 1]]) for r in range(world)]
+    assert max(cost) / (sum(cost) / world) < 1.01
+    assert new[1] > equal[1] and new[-2] > equal[-2]
+    # band_rows / halo_plan follow explicit bounds
+    assert bands.band_rows(h, world, 3, new) == (new[3], new[4])
+    plan = bands.halo_plan(h, world, 3, 137, new)
+    assert plan[0][1] == (new[3], new[3] + 137) and plan[1][2] == (new[4], new[4] + 137)
+    # extreme skew: the minimum height wins
+    skew = bands.balanced_bounds(h, world, equal, [100.0] + [0.001] * 7, 137)
+    assert all(b - a >= 137 for a, b in zip(skew, skew[1:]))
