@@ -159,6 +159,7 @@ def run_cuda(case, ctx=None):
     ctx.set_unbiased_neighbors(case.unbiased_neighbors)
     gb = case.gbuffers()
     out_img = torch.zeros((case.h, case.w, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()                  # torch fills on its own stream; the context's stream is not ordered against it
     out = []
     ctx.counters(reset=True)
     for f in range(len(case.cameras)):

@@ -73,6 +73,7 @@ def test_shadow_rays_bit_exact(name, n_rays):
     ctx = ph.make_context(scene)
     d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
     out = torch.zeros(n_rays, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()   # torch fills on its own stream; the context's stream is not ordered against it
     ctx.counters(reset=True)
     ctx.trace_segments(d1, d2, n_rays, out)
     ctx.synchronize()
@@ -110,6 +111,7 @@ def test_traversal_modes_agree_and_report():
         else:
             assert info["traversal"] == capi.RESTIR_TRAVERSAL_REFERENCE_ORDER
         out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         ctx.trace_segments(d1, d2, n, out)
         ctx.synchronize()
         outs.append(out.cpu().numpy())
@@ -142,6 +144,7 @@ def test_gbuffer_fixture_tool_matches_oracle(name):
     planes = [torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda"), torch.zeros((h, w, 4), dtype=torch.int16, device="cuda"),
               torch.zeros((h, w, 2), dtype=torch.int16, device="cuda"), torch.zeros((h, w, 4), dtype=torch.float32, device="cuda"),
               torch.zeros((h, w), dtype=torch.float32, device="cuda")]
+    torch.cuda.synchronize()
     ctx.raycast_gbuffer(ph.to_capi_camera(cam), tm, mt, *planes)
     ctx.synchronize()
     for got, ref, what in zip(planes, want.planes(), ["albedo", "normal", "material", "worldPos", "depth"]):

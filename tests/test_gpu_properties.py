@@ -49,11 +49,14 @@ class DeviceFrames:
             planes = [torch.zeros((rows, w, 4), dtype=torch.uint8, device="cuda"), torch.zeros((rows, w, 4), dtype=torch.int16, device="cuda"),
                       torch.zeros((rows, w, 2), dtype=torch.int16, device="cuda"), torch.zeros((rows, w, 4), dtype=torch.float32, device="cuda"),
                       torch.zeros((rows, w), dtype=torch.float32, device="cuda")]
+            torch.cuda.synchronize()          # torch fills on its own stream; the context's stream is not ordered against it
             self.ctx.raycast_gbuffer(c, tm, mt, *planes)
             self.gb.append(planes)
+        self.ctx.synchronize()
         for s in (0, 1):
             self.ctx.bind_gbuffer(s, *self.gb[s])
         self.image = torch.zeros((rows, w, 4), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
 
     def uniforms(self, f, **over):
         cam, prev = self.cams[f & 1], self.cams[(f & 1) ^ 1] if f > 0 else self.cams[0]
@@ -130,10 +133,12 @@ def test_degenerate_parameters_are_identities():
     d.ctx.close()
 
 
-@pytest.mark.parametrize("unbiased", [True, False])
-def test_band_split_is_bit_identical_to_whole_frame(unbiased):
-    """The multi-GPU claim on one GPU: two band contexts with halo copies between the passes reproduce the
-    single-context frame exactly (RNG is keyed on global pixel coordinates)."""
+@pytest.mark.parametrize("unbiased,bounds", [(True, None), (False, None), (True, [0, 100, 290, 432]), (False, [0, 150, 250, 432])])
+def test_band_split_is_bit_identical_to_whole_frame(unbiased, bounds):
+    """The multi-GPU claim on one GPU: band contexts (two of equal height, or three of unequal height as
+    bands.balanced_bounds cuts them) with halo copies between the passes reproduce the single-context frame exactly
+    (RNG is keyed on global pixel coordinates).  The halo is sized like bench.py does: spatial reach, or the rows
+    temporal reprojection reaches if that is more (bands.temporal_row_reach)."""
     torch = _torch()
     scene, (pos, look) = _scene_full()
     w, h, halo, frames = 1920, 432, 31, 3
@@ -144,9 +149,19 @@ def test_band_split_is_bit_identical_to_whole_frame(unbiased):
     want = whole.ctx.download_reservoirs((frames - 1) & 1)
     whole.ctx.close()
 
-    world = 2
-    parts = [DeviceFrames(scene, pos, look, w, h, band=bands.band_rows(h, world, r), halo=halo) for r in range(world)]
-    plans = [bands.halo_plan(h, world, r, halo) for r in range(world)]
+    world = 2 if bounds is None else len(bounds) - 1
+    parts = [DeviceFrames(scene, pos, look, w, h, band=bands.band_rows(h, world, r, bounds), halo=halo) for r in range(world)]
+    reach = 0
+    for part in parts:
+        for cur, prv in ((0, 1), (1, 0)):
+            reach = max(reach, bands.temporal_row_reach(part.gb[cur][3], part.gb[cur][1], capi.camera_matrix(part.cams[prv]), w, h,
+                                                        part.a0, part.rb, part.re, torch))
+    if reach > halo:
+        halo = reach
+        for part in parts:
+            part.ctx.close()
+        parts = [DeviceFrames(scene, pos, look, w, h, band=bands.band_rows(h, world, r, bounds), halo=halo) for r in range(world)]
+    plans = [bands.halo_plan(h, world, r, halo, bounds) for r in range(world)]
 
     def exchange(buffer):
         views = [bands.reservoir_rows_tensor(p.ctx, buffer, torch) for p in parts]
@@ -233,6 +248,7 @@ def test_cpp_host_driver_matches_python_driven_run(tmp_path):
 
     df = DeviceFrames(scene, pos, look, w, h)
     img = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     df.ctx.counters(reset=True)
     for f in range(frames):
         df.set(f)
