@@ -110,8 +110,8 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
 
 /* Shadow-ray traversal.  The uploaded tree is always the reference's (aabbTreeBuilder node / triangle
  * layout) and is always walked in softwareRaytracing.glsl:39-85's own order.  AUTO (default):
- * restir_upload_bvh keeps a device copy of the same nodes re-strided to 64 bytes (four 16-byte loads from one
- * line instead of five that straddle lines) and, having checked that the reference's 32-entry stack cannot
+ * restir_upload_bvh keeps a device image of the same nodes at 64 bytes each (two 32-byte loads from one
+ * line instead of five 16-byte loads that straddle lines) and, having checked that the reference's 32-entry stack cannot
  * overflow on this tree, drops the per-push bound check.  REFERENCE_ORDER: walk the 80-byte nodes literally,
  * dropped pushes counted — also what AUTO falls back to when the stack could overflow
  * (restir_get_bvh_info tells).  Takes effect at the next restir_upload_bvh.  Uploads whose child indices are
@@ -125,15 +125,14 @@ typedef struct restir_bvh_info {
 	uint32_t nodes, triangles;
 	uint32_t reachable_nodes, depth;
 	uint32_t reference_stack_bound; /* worst-case occupancy of the reference's 32-entry stack on this tree */
-	int32_t traversal;              /* No reference equivalent (the reference traces every ray it asks for).  The unbiased pass answers a neighbour ray
+	int32_t traversal;              /* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
+} restir_bvh_info;
+int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
+/* No reference equivalent (the reference traces every ray it asks for).  The unbiased pass answers a neighbour ray
  * of unbiasedReuse.glsl:139-156 without walking the tree when the answer is already determined, exactly: the pixel's
  * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every
  * ray instead (A/B measurements and the tests that require both settings to give identical bits).  Default: 1. */
 int restir_set_ray_elision(restir_context *ctx, int enable);
-
-/* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
-} restir_bvh_info;
-int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
 /* The same checks restir_upload_bvh runs, on the host and without a context (no GPU needed): RESTIR_E_INVALID
  * and a message for an upload that would be rejected; otherwise RESTIR_OK, `out` filled (traversal says which
  * walk such an upload would get) and, for the reference-order fallback, the reason in `message`.  The
