@@ -57,13 +57,14 @@ class Case:
     """A frame sequence: per frame a camera; G-buffers rendered by the oracle's fixture generator."""
 
     def __init__(self, scene, width, height, cameras, candidates=32, unbiased=False, spatial_iterations=1, neighbors=4,
-                 unbiased_neighbors=3, flags=3, multiplier=20, radius=30.0, pos_thr=0.1, nor_thr=25.0, gamma=1.0):
+                 unbiased_neighbors=3, flags=3, multiplier=20, radius=30.0, pos_thr=0.1, nor_thr=25.0, gamma=1.0, frame_offset=0):
         self.scene, self.w, self.h = scene, width, height
         self.cameras = cameras
         self.candidates, self.unbiased, self.iterations = candidates, unbiased, spatial_iterations
         self.neighbors, self.unbiased_neighbors = neighbors, unbiased_neighbors
         self.flags, self.multiplier, self.radius = flags, multiplier, radius
         self.pos_thr, self.nor_thr, self.gamma = pos_thr, nor_thr, gamma
+        self.frame_offset = frame_offset          # first frame number = 1 + frame_offset (mod 2^32: the seeds wrap, rand.glsl:20-28)
         self._gbuffers = None
 
     def gbuffers(self):
@@ -82,7 +83,7 @@ class Case:
         u = capi.make_uniforms(
             prevFrameProjectionViewMatrix=po.camera_matrix(prev_cam),
             cameraPos=(cam.position[0], cam.position[1], cam.position[2], 1.0),
-            screenSize=(self.w, self.h), frame=frame_index + 1, initialLightSampleCount=self.candidates,
+            screenSize=(self.w, self.h), frame=(frame_index + 1 + self.frame_offset) & 0xFFFFFFFF, initialLightSampleCount=self.candidates,
             temporalSampleCountMultiplier=self.multiplier, spatialPosThreshold=self.pos_thr,
             spatialNormalThreshold=self.nor_thr, spatialNeighbors=self.neighbors, spatialRadius=self.radius, flags=self.flags)
         lu = capi.make_lighting_uniforms(
@@ -104,6 +105,28 @@ def moving_cameras(n, position, look_at, aspect, step=(0.05, 0.0, 0.0), fov_y=No
 def to_capi_camera(cam):
     return capi.make_camera(position=tuple(cam.position), look_at=tuple(cam.lookAt), up=tuple(cam.worldUp), z_near=cam.zNear,
                             z_far=cam.zFar, fov_y=cam.fovYRadians, aspect=cam.aspectRatio)
+
+
+# Boundary cases of the parameter block and of the screen, run through every link of the parity chain
+# (reference source == oracle in tests/test_oracle_vs_glsl.py, oracle == kernels in tests/test_gpu_parity.py).
+EDGE_CASES = [
+    # id, scene, (w, h), frames, kwargs
+    ("one-candidate-biased", "procedural:point", (64, 36), 2, dict(unbiased=False, candidates=1)),
+    ("one-candidate-unbiased", "procedural:tri", (64, 36), 2, dict(unbiased=True, candidates=1)),
+    ("screen-1x1", "procedural:point", (1, 1), 3, dict(unbiased=True)),
+    ("screen-8x4-one-warp-tile", "procedural:point", (8, 4), 3, dict(unbiased=False)),
+    ("screen-33x9-ragged", "procedural:tri", (33, 9), 3, dict(unbiased=True, unbiased_neighbors=5)),
+    ("radius-0-self-neighbour", "procedural:point", (64, 36), 2, dict(unbiased=False, radius=0.0)),
+    ("radius-0-unbiased", "procedural:point", (64, 36), 2, dict(unbiased=True, radius=0.0)),
+    ("radius-1000-clamped-to-screen", "procedural:point", (64, 36), 2, dict(unbiased=True, radius=1000.0)),
+    ("m-cap-0", "procedural:point", (64, 36), 3, dict(unbiased=False, multiplier=0)),
+    ("m-cap-1", "procedural:tri", (64, 36), 3, dict(unbiased=True, multiplier=1)),
+    ("thresholds-0-reject-all", "procedural:point", (64, 36), 2, dict(unbiased=False, pos_thr=0.0, nor_thr=0.0)),
+    ("frame-number-wraps", "procedural:point", (64, 36), 3, dict(unbiased=False, frame_offset=2 ** 32 - 3)),
+    ("frame-number-wraps-unbiased", "procedural:tri", (64, 36), 3, dict(unbiased=True, frame_offset=2 ** 32 - 3)),
+    ("visibility-off-temporal-on", "procedural:tri", (64, 36), 3, dict(unbiased=True, flags=2)),
+    ("visibility-on-temporal-off", "procedural:point", (64, 36), 2, dict(unbiased=True, flags=1)),
+]
 
 
 # ---- running both sides -----------------------------------------------------------------------------

@@ -190,6 +190,30 @@ def test_frames_match_oracle(name, size, frames, kw):
     assert lit > 0.05, "degenerate case: almost nothing is lit"
 
 
+@pytest.mark.parametrize("label,name,size,frames,kw", ph.EDGE_CASES, ids=[c[0] for c in ph.EDGE_CASES])
+def test_edge_cases_match_oracle(label, name, size, frames, kw):
+    """Boundary values of the parameter block and of the screen (parity_harness.EDGE_CASES): 1x1 and one-tile screens,
+    ragged tile edges, one candidate, radius 0 and radius >> screen, M cap 0 and 1, thresholds that reject every
+    neighbour, frame numbers that wrap the 32-bit seed arithmetic, each visibility / temporal flag alone."""
+    _torch()
+    scene = _scene(name)
+    w, h = size
+    case = ph.Case(scene, w, h, _cams(name, frames, max(w, 2), max(h, 2)), **kw)
+    ph.assert_frames_match(ph.run_cuda(case), ph.run_oracle(case), label)
+
+
+def test_zero_candidates_leave_empty_reservoirs():
+    """initialLightSampleCount = 0: the candidate loop does not run (restirOmni.glsl:108), reservoirs stay as newReservoir
+    left them (oracle definition: zero), yet the passes run to the end and match the oracle."""
+    _torch()
+    scene = _scene("procedural:point")
+    w, h = 48, 27
+    case = ph.Case(scene, w, h, _cams("procedural:point", 2, w, h), unbiased=True, candidates=0)
+    got, want = ph.run_cuda(case), ph.run_oracle(case)
+    ph.assert_frames_match(got, want, "zero candidates")
+    assert (got[-1]["reservoirs"]["M"] == 0).all() and (got[-1]["reservoirs"]["w"] == 0).all()
+
+
 def test_many_lights_gather_matches_oracle():
     """C5-like: 100k random point lights, 64 candidates (light tables no longer fit L1)."""
     _torch()

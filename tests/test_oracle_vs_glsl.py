@@ -133,3 +133,19 @@ def test_frames_oracle_equals_reference_source(name, size, frames, kw):
             assert rel <= ph.RGB_REL_TOL and psnr >= ph.PSNR_MIN_DB
     lit = (want[-1]["reservoirs"]["w"] > 0).mean()
     assert lit > 0.05, "degenerate case: almost nothing is lit"
+
+
+@pytest.mark.parametrize("label,name,size,frames,kw", ph.EDGE_CASES, ids=[c[0] for c in ph.EDGE_CASES])
+def test_edge_cases_oracle_equals_reference_source(label, name, size, frames, kw):
+    """Boundary values of the parameter block and of the screen (parity_harness.EDGE_CASES) through the reference's own
+    shader text and through the oracle: bit for bit."""
+    scene = _scene(name)
+    w, h = size
+    aspect_cams = _cams(name, frames, max(w, 2), max(h, 2))
+    case = ph.Case(scene, w, h, aspect_cams, **kw)
+    want = ph.run_oracle(case, passes=gl)
+    got = ph.run_oracle(case)
+    for f, (o, r) in enumerate(zip(got, want)):
+        assert ph.compare_reservoirs(o["initial"], r["initial"], f"{label} frame {f} after restirOmni") == 0
+        assert ph.compare_reservoirs(o["reservoirs"], r["reservoirs"], f"{label} frame {f} final") == 0
+        assert ph.bits_equal(o["rgba"][..., :3], r["rgba"][..., :3]).all()
