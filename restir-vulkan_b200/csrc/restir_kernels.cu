@@ -440,22 +440,27 @@ __global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, P
 					haloMiss = 1; // band too thin for this camera motion: reported, never silent
 				} else {
 					size_t ppix = local_index(p.band, fx, fy);
-					f3 dp = worldPos - fetch_world_pos(p.prev, ppix);
+					// everything the gates and the merge read at the reprojected pixel is requested at once (one round trip
+					// to L2/HBM instead of four dependent ones); the gates then run in the reference's order
+					f3 prevPos = fetch_world_pos(p.prev, ppix);
+					f3 prevAlbedo = fetch_albedo(p.prev, sc.srgbLut, ppix, nullptr);
+					f3 prevNormal = fetch_normal(p.prev, ppix);
+					PackedReservoir prevRes = load_reservoir(prevReservoirs, ppix);
+					f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
+					float roughness, metallic;
+					fetch_material(p.cur, pix, roughness, metallic);
+					f3 dp = worldPos - prevPos;
 					if (dot3(dp, dp) < 0.01f) {
-						f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
-						f3 da = albedo - fetch_albedo(p.prev, sc.srgbLut, ppix, nullptr);
+						f3 da = albedo - prevAlbedo;
 						if (dot3(da, da) < 0.01f) {
-							float nd = dot3(normal, fetch_normal(p.prev, ppix));
+							float nd = dot3(normal, prevNormal);
 							if (nd > 0.5f) {
-								float roughness, metallic;
-								fetch_material(p.cur, pix, roughness, metallic);
 								float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);
 								f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
 								Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
 								// the pixel's RNG stream, advanced past the candidate loop's draws (:106-142)
 								Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);
 								rng.state = jump.A * rng.state + jump.G * rng.inc;
-								PackedReservoir prevRes = load_reservoir(prevReservoirs, ppix);
 								prevRes.M = min(prevRes.M, p.u.temporalSampleCountMultiplier * res.M); // :189-191
 								combine_reservoirs(res, prevRes, sc, sf, albedoLum, rng);
 								dirty = true;
