@@ -269,6 +269,9 @@ def main():
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo rows pushed by the library's own kernels into the neighbours' memory (default), or NCCL send/recv "
+                         "between the passes (bands.exchange_halo)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep bands of equal height instead of equal measured cost")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -360,7 +363,10 @@ def main():
                 halo_rows = int(t_reach.item())
                 del gb_
                 a0_, a1_, rows_alloc_, gb_ = setup_band(rows, halo_rows)
-        r_ = bands.BandRenderer(ctx, h, world, rank, halo_rows, torch, dist if world > 1 else None, bounds=bounds)
+        peer = world > 1 and args.halo == "peer"
+        if peer:   # the context exchanges halos itself: own kernels over NVLink peer memory (restir_band_connect)
+            bands.connect_neighbours(ctx, world, rank, dist, torch)
+        r_ = bands.BandRenderer(ctx, h, world, rank, halo_rows, torch, dist if world > 1 else None, bounds=bounds, connected=peer)
         for s_ in (0, 1):
             ctx.bind_gbuffer(s_, *gb_[s_])
         return rows, a0_, a1_, rows_alloc_, gb_, halo_rows, r_
@@ -386,7 +392,7 @@ def main():
             for f in range(2, 4):
                 set_frame(f)
                 renderer.frame(f & 1, cfg["unbiased"], 1)
-            mine = sum(ms for _, ms in ctx.profile_end().values())
+            mine = sum(ms for name, (_, ms) in ctx.profile_end().items() if name != "halo_wait_kernel")   # waiting for a neighbour is not this band's cost
             gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
             dist.all_gather(gathered, torch.tensor([mine], dtype=torch.float64, device=dev))
             secs = [float(g.item()) for g in gathered]
@@ -439,16 +445,16 @@ def main():
     counters = ctx.counters(reset=True)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, float(counters["shadow_rays"]), float(counters["kernel_launches"]), float(counters["halo_misses"]),
-                      float(counters["stack_overflows"])], dtype=torch.float64, device=dev)
+                      float(counters["stack_overflows"]), float(counters["halo_wait_timeouts"])], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, rays_total, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
-        halo_misses, overflows = float(tsum[3]), float(tsum[4])
+        halo_misses, overflows, halo_timeouts = float(tsum[3]), float(tsum[4]), float(tsum[5])
     else:
-        rays_total, launches, halo_misses, overflows = float(t[1]), float(t[2]), float(t[3]), float(t[4])
+        rays_total, launches, halo_misses, overflows, halo_timeouts = float(t[1]), float(t[2]), float(t[3]), float(t[4]), float(t[5])
     ms_per_frame = dev_ms / args.steps
     mrays = rays_total / (dev_ms * 1e-3) / 1e6
 
@@ -654,7 +660,7 @@ def main():
                                    f"{'unbiased reuse, ' + str(cfg['neighbors']) + ' neighbours' if cfg['unbiased'] else 'biased reuse 2 passes x ' + str(cfg['neighbors']) + ' neighbours'}, "
                                    f"temporal reuse on, software shadow rays, lights: {scene.light_counts()}",
                        "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
-                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world} ({balance_note}), halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
+                       "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36, "parallelism": f"row-bands x{world} ({balance_note}), halo exchange: {'own kernels over NVLink peer memory' if args.halo == 'peer' else 'NCCL send/recv'}, halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
             "rays_per_frame": rays_total / args.steps, "rays_walked_per_frame": traced_prof,
             "rays_note": "value counts the reference's testVisibility calls answered per second (the same unit of work as the --impl reference "
                          "arm); rays_walked_per_frame of them needed a walk of the tree, the rest are answered exactly without one",
@@ -662,7 +668,7 @@ def main():
             "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac,
             "trace_kernel_mrays_per_s": trace_mrays, "trace_kernel_mrays_walked_per_s": trace_mrays_walked, "bvh": info,
             "hbm_frame_frac": hbm_frame_frac, "frame_algorithmic_bytes": frame_bytes,
-            "gpu_launches": int(launches), "halo_misses": int(halo_misses), "stack_overflows": int(overflows),
+            "gpu_launches": int(launches), "halo_misses": int(halo_misses), "halo_wait_timeouts": int(halo_timeouts), "stack_overflows": int(overflows),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity_sample": parity,
         }
         json_out.write(json.dumps(line) + "\n")

@@ -5,5 +5,5 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 python - <<PY
 import json
 d=json.load(open("gpurun_out/scale_${cfg}_${sc}_n$N.json"))
-print("$cfg $sc N=$N", "ms/frame", round(d["ms_per_step"],3), "Mrays/s", round(d["value"],1), d["config"]["workload"][:80], "halo_misses", d["halo_misses"])
+print("$cfg $sc N=$N", "ms/frame", round(d["ms_per_step"],3), "Mrays/s", round(d["value"],1), "halo_misses", d["halo_misses"], "timeouts", d.get("halo_wait_timeouts"), d["config"]["parallelism"])
 PY

@@ -183,6 +183,33 @@ int restir_reservoir_device_ptr(restir_context *ctx, int buffer, void **ptr, siz
 int restir_trace_segments(restir_context *ctx, const float *p1_device, const float *p2_device, uint64_t n,
                           uint8_t *shadowed_device);
 
+/* ---- row-band neighbours over peer memory (no reference equivalent: the reference is single-GPU) ------------
+ * Without these calls a band context leaves the halo rows of its reservoir buffers to the caller (copy them between
+ * the passes through restir_reservoir_device_ptr).  With its neighbours connected, the context does it itself with
+ * its own kernels over NVLink peer memory: when a pass has produced a buffer it stores the boundary rows straight into
+ * each neighbour's copy of that buffer and raises a counter there; the pass that is about to read a halo first waits,
+ * on the device, for both neighbours' counters (every rank must issue the same pass sequence).  No host
+ * synchronisation and no collective on the data path.
+ *   side 0 = the neighbour that owns the rows above this band, side 1 = the rows below.
+ *   Same process (contexts on one or several devices with peer access): restir_band_local_peer of the neighbour,
+ *   then restir_band_connect.  One process per GPU: restir_band_export_ipc, ship the struct to the neighbour (any
+ *   transport), restir_band_open_ipc there, then restir_band_connect.  Connections end at restir_resize / restir_resize_band / restir_destroy;
+ *   all ranks must (re)connect before the next pass and synchronise once after connecting. */
+typedef struct restir_band_peer {
+	void *reservoirs[3];            /* the neighbour's three packed reservoir buffers, addressable from this process */
+	void *flags;                    /* the neighbour's counter block */
+	uint32_t alloc_begin, alloc_end; /* rows its buffers cover */
+} restir_band_peer;
+typedef struct restir_band_ipc {
+	unsigned char reservoirs[3][64]; /* cudaIpcMemHandle_t */
+	unsigned char flags[64];
+	uint32_t alloc_begin, alloc_end;
+} restir_band_ipc;
+int restir_band_local_peer(restir_context *ctx, restir_band_peer *out);
+int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out);
+int restir_band_open_ipc(restir_context *ctx, const restir_band_ipc *in, restir_band_peer *out);
+int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *peer); /* peer == NULL: no neighbour on that side */
+
 /* ---- counters --------------------------------------------------------------------------------- */
 
 typedef struct restir_counters {
@@ -190,6 +217,7 @@ typedef struct restir_counters {
 	uint64_t stack_overflows;   /* pushes dropped on a full 32-entry traversal stack (UB in the reference) */
 	uint64_t halo_misses;       /* band mode: neighbour / reprojection reads outside [alloc_begin, alloc_end) */
 	uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
+	uint64_t halo_wait_timeouts; /* connected bands: waits for a neighbour's rows that gave up after 2 s (a lost neighbour must not hang the GPU) */
 	uint64_t shadow_rays_traced; /* of shadow_rays, the ones that needed a walk of the tree: the rest were answered exactly
 	                              * without one (neighbour rays of a pixel whose own ray is shadowed, unbiasedReuse.glsl:157-166;
 	                              * neighbour rays bit-identical to the neighbour's own ray) */

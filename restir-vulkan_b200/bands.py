@@ -126,6 +126,27 @@ def exchange_halo(rows_tensor, alloc_begin, plan, dist, group=None):
             recv.copy_(tmp)
 
 
+def connect_neighbours(ctx, world, rank, dist, torch, group=None):
+    """One process per GPU: hands every rank's reservoir buffers to its two neighbours as CUDA IPC mappings and
+    connects them (restir_band_export_ipc / _open_ipc / _connect).  From then on the context exchanges halos itself
+    with its own kernels over NVLink peer memory and BandRenderer issues no exchange.  torch.distributed only carries
+    the 264-byte handles, once."""
+    from .capi import BandIpc
+    import ctypes
+
+    blob = ctx.band_export_ipc()
+    n = ctypes.sizeof(BandIpc)
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    everyone = [torch.zeros(n, dtype=torch.uint8, device=f"cuda:{ctx.device}") for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
+    for side, peer_rank in ((0, rank - 1), (1, rank + 1)):
+        if 0 <= peer_rank < world:
+            ctx.band_connect(side, ctx.band_open_ipc(bytes(everyone[peer_rank].cpu().tolist())))
+        else:
+            ctx.band_connect(side, None)
+    dist.barrier(group=group)   # nobody starts pushing before everybody has connected
+
+
 class _DeviceBytes:
     """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)."""
 
@@ -145,10 +166,13 @@ class BandRenderer:
     """Drives one band context through App's pass order (src/app.h:212-262) with the halo exchanges between
     the passes.  With world == 1 it degenerates to restir_frame + lighting."""
 
-    def __init__(self, ctx, height, world, rank, halo, torch, dist=None, group=None, bounds=None):
+    def __init__(self, ctx, height, world, rank, halo, torch, dist=None, group=None, bounds=None, connected=False):
+        """connected: the context's neighbours are connected (connect_neighbours): it pushes and waits for halos itself."""
         self.ctx, self.world, self.rank, self.torch, self.dist, self.group = ctx, world, rank, torch, dist, group
         self.height, self.halo = height, halo
-        self.plan = halo_plan(height, world, rank, halo, bounds) if world > 1 else []
+        self.plan = halo_plan(height, world, rank, halo, bounds) if world > 1 and not connected else []
+        if world > 1:
+            halo_plan(height, world, rank, halo, bounds)   # still validates that the halo fits into the neighbours' bands
         self.alloc_begin = ctx.band()[2]
         self._views = {}
 

@@ -66,8 +66,19 @@ EXPORTS = [
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_collect_triangle_lights",
     "restir_generate_random_point_lights", "restir_create_alias_table", "restir_camera_matrix",
-    "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math",
+    "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math", "restir_band_local_peer", "restir_band_export_ipc",
+    "restir_band_open_ipc", "restir_band_connect",
 ]
+
+
+class BandPeer(C.Structure):
+    """restir_band_peer: a neighbour's reservoir buffers and counter block, addressable from this process."""
+    _fields_ = [("reservoirs", C.c_void_p * 3), ("flags", C.c_void_p), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32)]
+
+
+class BandIpc(C.Structure):
+    """restir_band_ipc: the same as CUDA IPC handles, to be shipped to the neighbour's process."""
+    _fields_ = [("reservoirs", (C.c_ubyte * 64) * 3), ("flags", C.c_ubyte * 64), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32)]
 
 
 class GBufferPlanes(C.Structure):
@@ -75,7 +86,8 @@ class GBufferPlanes(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches", "shadow_rays_traced")]
+    _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches", "halo_wait_timeouts",
+                                            "shadow_rays_traced")]
 
 
 class BvhInfo(C.Structure):
@@ -374,6 +386,28 @@ class RestirContext:
         self._check(self.lib.restir_reservoir_device_ptr(self._ctx, C.c_int(buffer), C.byref(ptr), C.byref(pitch)))
         return ptr.value, pitch.value
 
+    # ---- row-band neighbours over peer memory (include/restir_b200.h) ----
+    def band_local_peer(self):
+        peer = BandPeer()
+        self._check(self.lib.restir_band_local_peer(self._ctx, C.byref(peer)))
+        return peer
+
+    def band_export_ipc(self):
+        """The 264 bytes a neighbour process needs (bytes object)."""
+        ipc = BandIpc()
+        self._check(self.lib.restir_band_export_ipc(self._ctx, C.byref(ipc)))
+        return bytes(ipc)
+
+    def band_open_ipc(self, blob):
+        ipc = BandIpc.from_buffer_copy(blob)
+        peer = BandPeer()
+        self._check(self.lib.restir_band_open_ipc(self._ctx, C.byref(ipc), C.byref(peer)))
+        return peer
+
+    def band_connect(self, side, peer):
+        """side 0: the neighbour that owns the rows above, 1: below; peer None: no neighbour there."""
+        self._check(self.lib.restir_band_connect(self._ctx, C.c_int(side), C.byref(peer) if peer is not None else None))
+
     def trace_segments(self, p1, p2, n, shadowed):
         self._check(self.lib.restir_trace_segments(self._ctx, _dp(p1), _dp(p2), C.c_uint64(n), _dp(shadowed)))
 
@@ -381,7 +415,8 @@ class RestirContext:
         c = Counters()
         self._check(self.lib.restir_get_counters(self._ctx, C.byref(c), C.c_int(1 if reset else 0)))
         return {"shadow_rays": c.shadow_rays, "stack_overflows": c.stack_overflows, "halo_misses": c.halo_misses,
-                "kernel_launches": c.kernel_launches, "shadow_rays_traced": c.shadow_rays_traced}
+                "kernel_launches": c.kernel_launches, "shadow_rays_traced": c.shadow_rays_traced,
+                "halo_wait_timeouts": c.halo_wait_timeouts}
 
     def raycast_gbuffer(self, cam, tri_material, material_table, albedo, normal, material, world_pos, depth):
         self._check(self.lib.restir_tools_raycast_gbuffer(self._ctx, C.byref(cam), _dp(tri_material), _dp(material_table), _dp(albedo),

@@ -58,6 +58,18 @@ struct restir_context {
 	int *neighborPix = nullptr;        // [tile-ordered pixel id][unbiased neighbours]
 	size_t neighborPixCount = 0;
 
+	// connected row-band neighbours (restir_band_connect): side 0 owns the rows above, side 1 the rows below
+	struct PeerSide {
+		bool connected = false;
+		PackedReservoir *reservoirs[3] = {nullptr, nullptr, nullptr};
+		unsigned long long *flags = nullptr;
+		int allocBegin = 0, allocEnd = 0;
+	} peers[2];
+	unsigned long long *bandFlags = nullptr; // device, [side the push came from][buffer]: raised by the neighbours
+	unsigned *haloTicket = nullptr;
+	uint64_t produced[3] = {0, 0, 0};        // times each buffer has been produced since the neighbours were connected
+	std::vector<void *> ipcOpened;
+
 	restir_uniforms uniforms{};
 	bool haveUniforms = false;
 	restir_lighting_uniforms lighting{};
@@ -266,6 +278,69 @@ int ensureHandOver(restir_context *ctx, const PassGrid &g, unsigned raysPerPixel
 	return RESTIR_OK;
 }
 
+bool bandConnected(const restir_context *ctx) { return ctx->peers[0].connected || ctx->peers[1].connected; }
+
+void dropPeers(restir_context *ctx) {
+	for (auto &p : ctx->peers) {
+		p = restir_context::PeerSide{};
+	}
+	for (void *m : ctx->ipcOpened) {
+		cudaIpcCloseMemHandle(m);
+	}
+	ctx->ipcOpened.clear();
+	ctx->produced[0] = ctx->produced[1] = ctx->produced[2] = 0;
+	if (ctx->bandFlags) {
+		cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream);
+	}
+	cudaGetLastError();
+}
+
+// The pass about to read the halo rows of `buffer` waits (on the device) until both neighbours have pushed their latest rows.
+int haloWait(restir_context *ctx, int buffer) {
+	if (!bandConnected(ctx)) {
+		return RESTIR_OK;
+	}
+	const unsigned long long *a = ctx->peers[0].connected ? ctx->bandFlags + 0 * 3 + buffer : nullptr;
+	const unsigned long long *b = ctx->peers[1].connected ? ctx->bandFlags + 1 * 3 + buffer : nullptr;
+	beforeLaunch(ctx, "halo_wait_kernel");
+	CU(ctx, launch_halo_wait(a, b, ctx->produced[buffer], ctx->counters, ctx->stream));
+	return afterLaunch(ctx, "halo_wait_kernel");
+}
+
+// `buffer` has just been produced: store the rows each neighbour holds as halo into its copy and raise its counter.
+int haloPush(restir_context *ctx, int buffer) {
+	if (!bandConnected(ctx)) {
+		return RESTIR_OK;
+	}
+	ctx->produced[buffer]++;
+	HaloPush hp{};
+	hp.local = ctx->reservoirs[buffer];
+	hp.W = ctx->band.W;
+	hp.localAllocBegin = ctx->band.allocBegin;
+	hp.sequence = ctx->produced[buffer];
+	hp.ticket = ctx->haloTicket;
+	for (int side = 0; side < 2; ++side) {
+		const auto &p = ctx->peers[side];
+		if (!p.connected) {
+			continue;
+		}
+		hp.peer[side] = p.reservoirs[buffer];
+		hp.peerAllocBegin[side] = p.allocBegin;
+		// this side's neighbour sees me on its other side
+		hp.peerFlag[side] = p.flags + (size_t)(side ^ 1) * 3 + buffer;
+		if (side == 0) { // rows above are the neighbour's: it holds my first rows up to its allocEnd
+			hp.firstRow[side] = ctx->band.rowBegin;
+			hp.rows[side] = std::max(0, std::min(p.allocEnd, ctx->band.rowEnd) - ctx->band.rowBegin);
+		} else {         // it holds my last rows from its allocBegin on
+			hp.firstRow[side] = std::max(p.allocBegin, ctx->band.rowBegin);
+			hp.rows[side] = std::max(0, ctx->band.rowEnd - hp.firstRow[side]);
+		}
+	}
+	beforeLaunch(ctx, "halo_push_kernel");
+	CU(ctx, launch_halo_push(hp, ctx->smCount, ctx->stream));
+	return afterLaunch(ctx, "halo_push_kernel");
+}
+
 TraceParams traceParams(const restir_context *ctx) {
 	TraceParams tp{};
 	tp.nodes = ctx->nodes;
@@ -309,6 +384,10 @@ int restir_create(restir_context **out, int device, void *stream) {
 		}
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->counters, sizeof(unsigned long long) * kCounterCount), "cudaMalloc counters")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * kCounterCount, ctx->stream), "memset")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->haloTicket, sizeof(unsigned)), "cudaMalloc halo ticket")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->haloTicket, 0, sizeof(unsigned), ctx->stream), "memset")) != RESTIR_OK) break;
 		// P12: sRGB8 -> linear table, EOTF in double rounded to float
 		float lut[256];
 		for (int i = 0; i < 256; ++i) {
@@ -344,6 +423,9 @@ void restir_destroy(restir_context *ctx) {
 	if (ctx->copyStream) {
 		cudaStreamDestroy(ctx->copyStream);
 	}
+	dropPeers(ctx);
+	freeDev(ctx->bandFlags);
+	freeDev(ctx->haloTicket);
 	dropGBuffers(ctx);
 	dropProfile(ctx);
 	freeDev(ctx->nodes);
@@ -485,6 +567,7 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 		CU(ctx, cudaStreamSynchronize(ctx->copyStream));
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	dropPeers(ctx);
 	dropGBuffers(ctx);
 	for (int s = 0; s < 2; ++s) {
 		ctx->uploadPending[s] = ctx->readRecorded[s] = false;
@@ -656,6 +739,85 @@ int restir_tools_selftest_packed_math(restir_context *ctx, uint64_t n, uint32_t 
 	return rc;
 }
 
+int restir_band_local_peer(restir_context *ctx, restir_band_peer *out) {
+	ENTER(ctx);
+	if (out == nullptr || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_local_peer: null result or restir_resize_band not called");
+	}
+	for (int b = 0; b < 3; ++b) out->reservoirs[b] = ctx->reservoirs[b];
+	out->flags = ctx->bandFlags;
+	out->alloc_begin = (uint32_t)ctx->band.allocBegin;
+	out->alloc_end = (uint32_t)ctx->band.allocEnd;
+	return RESTIR_OK;
+}
+
+int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out) {
+	ENTER(ctx);
+	if (out == nullptr || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_export_ipc: null result or restir_resize_band not called");
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	std::memset(out, 0, sizeof(*out));
+	for (int b = 0; b < 3; ++b) {
+		cudaIpcMemHandle_t h;
+		CU(ctx, cudaIpcGetMemHandle(&h, ctx->reservoirs[b]));
+		std::memcpy(out->reservoirs[b], &h, 64);
+	}
+	cudaIpcMemHandle_t h;
+	CU(ctx, cudaIpcGetMemHandle(&h, ctx->bandFlags));
+	std::memcpy(out->flags, &h, 64);
+	out->alloc_begin = (uint32_t)ctx->band.allocBegin;
+	out->alloc_end = (uint32_t)ctx->band.allocEnd;
+	return RESTIR_OK;
+}
+
+int restir_band_open_ipc(restir_context *ctx, const restir_band_ipc *in, restir_band_peer *out) {
+	ENTER(ctx);
+	if (in == nullptr || out == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_open_ipc: null argument");
+	}
+	std::memset(out, 0, sizeof(*out));
+	for (int b = 0; b < 4; ++b) {
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, b < 3 ? in->reservoirs[b] : in->flags, 64);
+		void *p = nullptr;
+		CU(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		ctx->ipcOpened.push_back(p);
+		if (b < 3) out->reservoirs[b] = p; else out->flags = p;
+	}
+	out->alloc_begin = in->alloc_begin;
+	out->alloc_end = in->alloc_end;
+	return RESTIR_OK;
+}
+
+int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *peer) {
+	ENTER(ctx);
+	if (side < 0 || side > 1 || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_connect: bad side or restir_resize_band not called");
+	}
+	auto &p = ctx->peers[side];
+	p = restir_context::PeerSide{};
+	if (peer == nullptr) {
+		return RESTIR_OK;
+	}
+	if (!peer->reservoirs[0] || !peer->reservoirs[1] || !peer->reservoirs[2] || !peer->flags) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_connect: incomplete peer");
+	}
+	// the neighbour must hold rows of this band as halo, on the right side
+	const bool touches = side == 0 ? ((int)peer->alloc_end > ctx->band.rowBegin && (int)peer->alloc_begin < ctx->band.rowBegin)
+	                               : ((int)peer->alloc_begin < ctx->band.rowEnd && (int)peer->alloc_end > ctx->band.rowEnd);
+	if (!touches) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_band_connect: peer rows [%u,%u) do not overlap this band's edge on side %d", peer->alloc_begin,
+		            peer->alloc_end, side);
+	}
+	for (int b = 0; b < 3; ++b) p.reservoirs[b] = static_cast<PackedReservoir *>(peer->reservoirs[b]);
+	p.flags = static_cast<unsigned long long *>(peer->flags);
+	p.allocBegin = (int)peer->alloc_begin;
+	p.allocEnd = (int)peer->alloc_end;
+	p.connected = true;
+	return RESTIR_OK;
+}
+
 int restir_set_ray_elision(restir_context *ctx, int enable) {
 	ENTER(ctx);
 	ctx->rayElision = enable ? 1 : 0;
@@ -718,6 +880,9 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	if ((rc = ensureHandOver(ctx, g, 1, 0)) != RESTIR_OK) return rc;
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	if (temporal && (rc = waitUpload(ctx, gbuffer ^ 1)) != RESTIR_OK) return rc;
+	// connected bands: the neighbours' rows of the previous frame's reservoirs (temporal reprojection reads them; waiting
+	// even when temporal reuse is off keeps a fast rank from overwriting a halo its neighbour is still reading)
+	if ((rc = haloWait(ctx, prev_buffer)) != RESTIR_OK) return rc;
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "omni_candidates_kernel");
 	launch_omni_candidates(p, out, ctx->scalarCandidates, ctx->stream);
@@ -740,6 +905,7 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 		launch_omni_temporal(p, out, ctx->reservoirs[prev_buffer], ctx->shadowed, ctx->stream);
 		if ((rc = afterLaunch(ctx, "omni_temporal_kernel")) != RESTIR_OK) return rc;
 	}
+	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	if ((rc = markReadIfOwned(ctx, gbuffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer ^ 1); // the previous frame's G-buffer is not read after this pass
 }
@@ -755,9 +921,11 @@ int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out
 		return fail(ctx, RESTIR_E_INVALID, "spatial pass: in and out buffers must differ");
 	}
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
 	beforeLaunch(ctx, "spatial_reuse_kernel");
 	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, ctx->stream);
 	if ((rc = afterLaunch(ctx, "spatial_reuse_kernel")) != RESTIR_OK) return rc;
+	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer);
 }
 
@@ -780,6 +948,7 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	}
 	if ((rc = ensureHandOver(ctx, g, k + 1, k)) != RESTIR_OK) return rc;
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
 	const PackedReservoir *in = ctx->reservoirs[in_buffer];
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "unbiased_merge_kernel");
@@ -810,6 +979,7 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	beforeLaunch(ctx, "unbiased_finalize_kernel");
 	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
 	if ((rc = afterLaunch(ctx, "unbiased_finalize_kernel")) != RESTIR_OK) return rc;
+	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer);
 }
 
@@ -840,8 +1010,9 @@ int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iteration
 	if (i < 0 || i > 1 || spatial_iterations < 0) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_frame: bad frame index");
 	}
-	if (ctx->band.rowBegin != 0 || ctx->band.rowEnd != ctx->band.H) {
-		return fail(ctx, RESTIR_E_INVALID, "restir_frame is for single-GPU contexts; band contexts interleave halo exchanges");
+	const bool edgeless = (ctx->band.rowBegin == 0 || ctx->peers[0].connected) && (ctx->band.rowEnd == ctx->band.H || ctx->peers[1].connected);
+	if (!edgeless) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_frame on a band context needs its neighbours connected (restir_band_connect); otherwise interleave the halo copies yourself");
 	}
 	int rc;
 	const int cur = i, prev = i ^ 1; // app.h:298-332
@@ -944,6 +1115,7 @@ int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
 	if (out) {
 		out->shadow_rays = h[kCounterRays];
 		out->shadow_rays_traced = h[kCounterTraced];
+		out->halo_wait_timeouts = h[kCounterHaloTimeout];
 		out->stack_overflows = h[kCounterOverflow];
 		out->halo_misses = h[kCounterHaloMiss];
 		out->kernel_launches = ctx->launches;

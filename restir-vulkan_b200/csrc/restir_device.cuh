@@ -51,7 +51,7 @@ struct Band {
 	int allocBegin, allocEnd;
 };
 
-enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterWork = 3, kCounterTraced = 4, kCounterCount = 5 };
+enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterWork = 3, kCounterTraced = 4, kCounterHaloTimeout = 5, kCounterCount = 6 };
 // kCounterRays counts the reference's testVisibility calls that were answered, kCounterTraced the ones that needed a walk of the tree.
 // kCounterWork is the persistent trace kernel's work cursor (zeroed before every trace launch).
 

@@ -63,6 +63,22 @@ void launch_pack_reservoirs(const restir_reservoir *in, PackedReservoir *out, si
 void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
                                 cudaStream_t s);
 
+// ---- halo exchange over peer memory (restir_halo.cu) ----------------------------------------------------------
+// side 0 = the neighbour that owns the rows above this band, side 1 = the rows below.
+struct HaloPush {
+	const PackedReservoir *local;  // the buffer just produced (rows [localAllocBegin, ...))
+	PackedReservoir *peer[2];      // the same buffer of the neighbour on each side, mapped into this process; null = no neighbour
+	unsigned long long *peerFlag[2]; // the neighbour's counter for (this side as seen from there, this buffer)
+	int W, localAllocBegin;
+	int peerAllocBegin[2];
+	int firstRow[2], rows[2];      // the rows of this band the neighbour holds as halo
+	unsigned long long sequence;   // how many times this buffer has been produced, this launch included
+	unsigned *ticket;              // zero-initialised scratch word (last-block detection)
+};
+cudaError_t launch_halo_push(const HaloPush &hp, int smCount, cudaStream_t s);
+cudaError_t launch_halo_wait(const unsigned long long *flagA, const unsigned long long *flagB, unsigned long long sequence, unsigned long long *counters,
+                             cudaStream_t s);
+
 // restir_selftest.cu: mismatch[0..3] = div2, rcp2, sqrt2, evaluate_phat2 results differing from the scalar policy; [4] = values compared
 void launch_selftest_packed(uint64_t n, uint32_t seed, unsigned long long *mismatch, cudaStream_t s);
 

@@ -200,6 +200,51 @@ def test_band_split_is_bit_identical_to_whole_frame(unbiased, bounds):
     assert ph.compare_reservoirs(got, want, "band split") == 0
 
 
+@pytest.mark.parametrize("unbiased,bounds", [(True, [0, 216, 432]), (False, [0, 216, 432]), (True, [0, 100, 290, 432]), (False, [0, 150, 250, 432])])
+def test_connected_bands_exchange_halos_themselves(unbiased, bounds):
+    """restir_band_connect: band contexts wired to their neighbours push their boundary rows into the neighbour's
+    buffers with the library's own kernels and wait for the neighbour's rows on the device — no copies by the caller,
+    restir_frame works on a band — and reproduce the single-context frame bit for bit."""
+    torch = _torch()
+    scene, (pos, look) = _scene_full()
+    w, h, halo, frames = 1920, 432, 31, 3
+    whole = DeviceFrames(scene, pos, look, w, h)
+    for f in range(frames):
+        whole.set(f)
+        whole.ctx.frame(f & 1, unbiased, 1)
+    want = whole.ctx.download_reservoirs((frames - 1) & 1)
+    whole.ctx.close()
+
+    world = len(bounds) - 1
+    parts = [DeviceFrames(scene, pos, look, w, h, band=bands.band_rows(h, world, r, bounds), halo=halo) for r in range(world)]
+    reach = 0
+    for part in parts:
+        for cur, prv in ((0, 1), (1, 0)):
+            reach = max(reach, bands.temporal_row_reach(part.gb[cur][3], part.gb[cur][1], capi.camera_matrix(part.cams[prv]), w, h,
+                                                        part.a0, part.rb, part.re, torch))
+    if reach > halo:
+        halo = reach
+        for part in parts:
+            part.ctx.close()
+        parts = [DeviceFrames(scene, pos, look, w, h, band=bands.band_rows(h, world, r, bounds), halo=halo) for r in range(world)]
+    for r, part in enumerate(parts):       # same process: the neighbours' raw pointers
+        part.ctx.band_connect(0, parts[r - 1].ctx.band_local_peer() if r > 0 else None)
+        part.ctx.band_connect(1, parts[r + 1].ctx.band_local_peer() if r + 1 < world else None)
+    with pytest.raises(capi.RestirError):  # a peer that does not touch this band's edge is refused
+        parts[0].ctx.band_connect(0, parts[-1].ctx.band_local_peer())
+    parts[0].ctx.band_connect(0, None)
+    for f in range(frames):
+        for part in parts:
+            part.set(f)
+            part.ctx.frame(f & 1, unbiased, 1)   # asynchronous: a band waiting for its neighbour does not block the host
+    got = np.concatenate([part.owned(part.ctx.download_reservoirs((frames - 1) & 1)) for part in parts])
+    for part in parts:
+        c = part.ctx.counters()
+        assert c["halo_misses"] == 0 and c["halo_wait_timeouts"] == 0
+        part.ctx.close()
+    assert ph.compare_reservoirs(got, want, "connected bands") == 0
+
+
 def test_oracle_spot_check_at_1080p():
     """A 24-row band of the full-size Sponza frame 2 (temporal history from the GPU's own frame 1) through
     the oracle, compared bit for bit — parity at the BASELINE size without running the oracle on 2 Mpx."""
