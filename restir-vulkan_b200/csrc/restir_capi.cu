@@ -384,6 +384,9 @@ int restir_create(restir_context **out, int device, void *stream) {
 		}
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->counters, sizeof(unsigned long long) * kCounterCount), "cudaMalloc counters")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * kCounterCount, ctx->stream), "memset")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_pixel_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_trace_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->haloTicket, sizeof(unsigned)), "cudaMalloc halo ticket")) != RESTIR_OK) break;

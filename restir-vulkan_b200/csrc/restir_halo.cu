@@ -81,4 +81,11 @@ cudaError_t launch_halo_wait(const unsigned long long *flagA, const unsigned lon
 	return cudaGetLastError();
 }
 
+cudaError_t preload_halo_kernels() {
+	cudaFuncAttributes a;
+	cudaError_t e = cudaFuncGetAttributes(&a, halo_push_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, halo_wait_kernel);
+	return e;
+}
+
 } // namespace restir

@@ -908,4 +908,27 @@ void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *po
 	if (nt) derive_tri_table_kernel<<<(nt + 255) / 256, 256, 0, s>>>(tl, nt, triOut);
 }
 
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, which can synchronise the device:
+// fatal timing for a band whose stream is spinning in halo_wait_kernel for a neighbour driven by the same host thread.
+// restir_create touches every kernel once instead.
+cudaError_t preload_pixel_kernels() {
+	cudaFuncAttributes a;
+	cudaError_t e = cudaSuccess;
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_candidates_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_candidates_paired_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_temporal_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<0>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<3>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<5>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_finalize_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lighting_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, raycast_gbuffer_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unpack_reservoirs_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, pack_reservoirs_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, derive_point_table_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, derive_tri_table_kernel);
+	return e;
+}
+
 } // namespace restir

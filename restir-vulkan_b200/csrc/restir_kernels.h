@@ -79,6 +79,11 @@ cudaError_t launch_halo_push(const HaloPush &hp, int smCount, cudaStream_t s);
 cudaError_t launch_halo_wait(const unsigned long long *flagA, const unsigned long long *flagB, unsigned long long sequence, unsigned long long *counters,
                              cudaStream_t s);
 
+// every kernel of the library loaded up front (restir_create), see restir_kernels.cu preload_pixel_kernels
+cudaError_t preload_pixel_kernels();
+cudaError_t preload_trace_kernels();
+cudaError_t preload_halo_kernels();
+
 // restir_selftest.cu: mismatch[0..3] = div2, rcp2, sqrt2, evaluate_phat2 results differing from the scalar policy; [4] = values compared
 void launch_selftest_packed(uint64_t n, uint32_t seed, unsigned long long *mismatch, cudaStream_t s);
 

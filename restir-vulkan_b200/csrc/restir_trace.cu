@@ -296,4 +296,15 @@ cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStrea
 	}
 }
 
+cudaError_t preload_trace_kernels() {
+	cudaFuncAttributes a;
+	cudaError_t e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, false>);
+	return e;
+}
+
 } // namespace restir

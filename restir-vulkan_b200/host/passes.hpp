@@ -215,4 +215,52 @@ public:
 	}
 };
 
+// Row bands in one process (no reference equivalent: the reference is single-GPU).  Each band is a Device of its own
+// — on one GPU or on several with peer access enabled by the caller — allocated with restir_resize_band and wired to
+// its neighbours with restir_band_connect, after which every band runs the same FrameRecorder and the library moves
+// the halo rows itself (restir_b200.h, "row-band neighbours over peer memory").
+class BandSet {
+public:
+	// bounds: bands + 1 ascending rows from 0 to height
+	BandSet(const std::vector<Device *> &devices, uint32_t width, uint32_t height, const std::vector<uint32_t> &bounds, uint32_t halo)
+	    : _devices(devices), _bounds(bounds) {
+		if (devices.empty() || bounds.size() != devices.size() + 1 || bounds.front() != 0 || bounds.back() != height) {
+			throw Error(RESTIR_E_INVALID, "BandSet: bounds must run from 0 to height, one band per device");
+		}
+		for (size_t r = 0; r < devices.size(); ++r) {
+			devices[r]->check(restir_resize_band(devices[r]->get(), width, height, bounds[r], bounds[r + 1], halo));
+		}
+		for (size_t r = 0; r < devices.size(); ++r) {
+			restir_band_peer up{}, down{};
+			if (r > 0) devices[r - 1]->check(restir_band_local_peer(devices[r - 1]->get(), &up));
+			if (r + 1 < devices.size()) devices[r + 1]->check(restir_band_local_peer(devices[r + 1]->get(), &down));
+			devices[r]->check(restir_band_connect(devices[r]->get(), 0, r > 0 ? &up : nullptr));
+			devices[r]->check(restir_band_connect(devices[r]->get(), 1, r + 1 < devices.size() ? &down : nullptr));
+		}
+	}
+	size_t size() const { return _devices.size(); }
+	Device &device(size_t r) const { return *_devices[r]; }
+	uint32_t rowBegin(size_t r) const { return _bounds[r]; }
+	uint32_t rowEnd(size_t r) const { return _bounds[r + 1]; }
+	// rows the band's per-pixel buffers cover (its G-buffer planes and images start at allocBegin)
+	void allocRows(size_t r, uint32_t &begin, uint32_t &end) const {
+		_devices[r]->check(restir_get_band(_devices[r]->get(), nullptr, nullptr, &begin, &end));
+	}
+	// Same pass sequence on every band, issued asynchronously: a band that waits for a neighbour's rows waits on the device.
+	void record(const FrameRecorder &recorder, int i) const {
+		for (Device *d : _devices) {
+			recorder.record(*d, i);
+		}
+	}
+	void waitIdle() const {
+		for (Device *d : _devices) {
+			d->waitIdle();
+		}
+	}
+
+private:
+	std::vector<Device *> _devices;
+	std::vector<uint32_t> _bounds;
+};
+
 } // namespace restir

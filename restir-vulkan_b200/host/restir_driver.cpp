@@ -3,7 +3,11 @@
 // patch the uniforms (src/app.cpp:775-826), record the ReSTIR passes (src/app.h:212-262) and the
 // lighting pass (src/app.cpp:861-862), flipping the G-buffer index (src/app.cpp:900).
 //
-//   restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors]
+//   restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors] [--bands N] [--halo ROWS]
+//
+// --bands N (no reference equivalent): the frame is split into N row bands, each a context of its own on GPU 0, wired
+// to its neighbours with restir::BandSet (restir_band_connect): the library exchanges the halo rows itself and the
+// checksums must equal the single-context run's.
 //
 // <scene_dir> holds triangles.bin (n x 48), tri_material.i32, materials.f32 (m x 16), dims.f32 and
 // material_table.u32 (m x 4) — what scenes/_baked/<name>/ or restir-vulkan_b200/fixtures.py write.
@@ -16,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -71,14 +76,28 @@ struct DeviceGBuffer {
 
 int main(int argc, char **argv) {
 	if (argc < 6) {
-		std::cerr << "usage: restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors]\n";
+		std::cerr << "usage: restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors] [--bands N] [--halo ROWS]\n";
 		return 64;
 	}
 	const std::string dir = argv[1];
 	const uint32_t width = (uint32_t)std::atoi(argv[2]), height = (uint32_t)std::atoi(argv[3]);
 	const int frames = std::atoi(argv[4]);
 	const bool unbiased = std::atoi(argv[5]) != 0;
-	const uint32_t neighbors = argc > 6 ? (uint32_t)std::atoi(argv[6]) : (unbiased ? 3u : 4u);
+	uint32_t neighbors = unbiased ? 3u : 4u, nBands = 1, halo = 64;
+	for (int a = 6; a < argc; ++a) {
+		const std::string arg = argv[a];
+		if (arg == "--bands" && a + 1 < argc) {
+			nBands = (uint32_t)std::atoi(argv[++a]);
+		} else if (arg == "--halo" && a + 1 < argc) {
+			halo = (uint32_t)std::atoi(argv[++a]);
+		} else {
+			neighbors = (uint32_t)std::atoi(argv[a]);
+		}
+	}
+	if (nBands < 1 || nBands > 64) {
+		std::cerr << "restir_driver: --bands must be in 1..64\n";
+		return 64;
+	}
 
 	try {
 		// ---- scene (App::App: loadScene, SceneBuffers::create, AabbTree::build; src/app.cpp:285-360) ----
@@ -106,16 +125,32 @@ int main(int argc, char **argv) {
 		}
 		tri.resize((size_t)nTri);
 
-		restir::Device device(0);
+		// one context per band (a single one covering the screen without --bands), the scene replicated into each
 		restir::AabbTree tree = restir::AabbTree::build(triangles);
-		tree.upload(device);
 		restir::SceneLights lights = restir::SceneLights::create(point, tri, dims.data(), dims.data() + 3);
-		lights.upload(device);
-		device.check(restir_resize(device.get(), width, height)); // App::_updateRestirBuffers
-		device.check(restir_set_unbiased_neighbors(device.get(), unbiased ? neighbors : 3));
+		std::vector<std::unique_ptr<restir::Device>> owned;
+		std::vector<restir::Device *> devices;
+		for (uint32_t r = 0; r < nBands; ++r) {
+			owned.emplace_back(new restir::Device(0));
+			devices.push_back(owned.back().get());
+			tree.upload(*devices[r]);
+			lights.upload(*devices[r]);
+		}
+		std::vector<uint32_t> bounds(nBands + 1);
+		for (uint32_t r = 0; r <= nBands; ++r) {
+			bounds[r] = (uint32_t)((uint64_t)height * r / nBands);
+		}
+		std::unique_ptr<restir::BandSet> bandSet;
+		if (nBands == 1) {
+			devices[0]->check(restir_resize(devices[0]->get(), width, height)); // App::_updateRestirBuffers
+		} else {
+			bandSet.reset(new restir::BandSet(devices, width, height, bounds, halo));
+		}
+		for (restir::Device *d : devices) {
+			d->check(restir_set_unbiased_neighbors(d->get(), unbiased ? neighbors : 3));
+		}
 
-		// ---- inputs: two G-buffers from two camera positions (fixture tool) ----------------------------
-		const size_t pixels = (size_t)width * height;
+		// ---- inputs: two G-buffers from two camera positions (fixture tool), per band its allocated rows -------
 		int32_t *dTriMaterial = nullptr;
 		uint32_t *dMaterialTable = nullptr;
 		cuda(cudaMalloc(&dTriMaterial, triMaterial.size() * 4), "cudaMalloc");
@@ -142,16 +177,22 @@ int main(int argc, char **argv) {
 			c.aspectRatio = (float)width / (float)height;
 			cams[k] = c;
 		}
-		DeviceGBuffer gbuf[2];
-		for (int k = 0; k < 2; ++k) {
-			gbuf[k].allocate(pixels);
-			device.check(restir_tools_raycast_gbuffer(device.get(), &cams[k], dTriMaterial, dMaterialTable, gbuf[k].plane[0], gbuf[k].plane[1],
-			                                          gbuf[k].plane[2], gbuf[k].plane[3], gbuf[k].plane[4]));
-			restir_gbuffer_planes p = gbuf[k].planes();
-			device.check(restir_bind_gbuffer(device.get(), k, RESTIR_GBUFFER_NVIDIA_DEFAULT, &p));
+		std::vector<uint32_t> allocBegin(nBands), allocEnd(nBands);
+		std::vector<void *> images(nBands, nullptr);
+		std::vector<DeviceGBuffer> gbuf(2 * (size_t)nBands);
+		for (uint32_t r = 0; r < nBands; ++r) {
+			devices[r]->check(restir_get_band(devices[r]->get(), nullptr, nullptr, &allocBegin[r], &allocEnd[r]));
+			const size_t pixels = (size_t)(allocEnd[r] - allocBegin[r]) * width;
+			for (int k = 0; k < 2; ++k) {
+				DeviceGBuffer &g = gbuf[2 * r + k];
+				g.allocate(pixels);
+				devices[r]->check(restir_tools_raycast_gbuffer(devices[r]->get(), &cams[k], dTriMaterial, dMaterialTable, g.plane[0], g.plane[1],
+				                                               g.plane[2], g.plane[3], g.plane[4]));
+				restir_gbuffer_planes p = g.planes();
+				devices[r]->check(restir_bind_gbuffer(devices[r]->get(), k, RESTIR_GBUFFER_NVIDIA_DEFAULT, &p));
+			}
+			cuda(cudaMalloc(&images[r], pixels * 4), "cudaMalloc image");
 		}
-		void *image = nullptr;
-		cuda(cudaMalloc(&image, pixels * 4), "cudaMalloc image");
 
 		// ---- main loop (App::mainLoop, src/app.cpp:690-902) ---------------------------------------------
 		restir_uniforms u{};
@@ -171,12 +212,12 @@ int main(int argc, char **argv) {
 
 		restir::FrameRecorder recorder;
 		recorder.unbiasedSpatialReuse = unbiased;
-		restir::LightingPass lighting;
-		lighting.outImage = image;
 		int currentGBufferFrame = 0;
 		restir_counters counters{};
-		device.check(restir_get_counters(device.get(), &counters, 1));
-		device.waitIdle();
+		for (restir::Device *d : devices) {
+			d->check(restir_get_counters(d->get(), &counters, 1));
+			d->waitIdle();
+		}
 		auto t0 = std::chrono::steady_clock::now();
 		for (int f = 0; f < frames; ++f) {
 			const restir_camera &cam = cams[f & 1], &prevCam = cams[f > 0 ? ((f & 1) ^ 1) : 0];
@@ -188,25 +229,52 @@ int main(int argc, char **argv) {
 			u.cameraPos[3] = 1.0f;
 			std::memcpy(lu.cameraPos, u.cameraPos, 16);
 			std::memcpy(lu.prevFrameProjectionViewMatrix, u.prevFrameProjectionViewMatrix, 64);
-			device.check(restir_set_uniforms(device.get(), &u));
-			device.check(restir_set_lighting_uniforms(device.get(), &lu));
-			recorder.record(device, currentGBufferFrame); // app.cpp:828-832
-			lighting.gBuffer = currentGBufferFrame;
-			lighting.reservoirBuffer = currentGBufferFrame;
-			lighting.issueCommands(device);               // app.cpp:861-862
+			for (restir::Device *d : devices) {
+				d->check(restir_set_uniforms(d->get(), &u));
+				d->check(restir_set_lighting_uniforms(d->get(), &lu));
+			}
+			if (bandSet) {
+				bandSet->record(recorder, currentGBufferFrame);
+			} else {
+				recorder.record(*devices[0], currentGBufferFrame); // app.cpp:828-832
+			}
+			for (uint32_t r = 0; r < nBands; ++r) {
+				restir::LightingPass lighting;
+				lighting.outImage = images[r];
+				lighting.gBuffer = currentGBufferFrame;
+				lighting.reservoirBuffer = currentGBufferFrame;
+				lighting.issueCommands(*devices[r]);          // app.cpp:861-862
+			}
 			currentGBufferFrame ^= 1;                     // app.cpp:900
 		}
-		device.waitIdle();
+		for (restir::Device *d : devices) {
+			d->waitIdle();
+		}
 		double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-		device.check(restir_get_counters(device.get(), &counters, 0));
 
+		// the whole frame, assembled from the rows each band owns
+		const size_t pixels = (size_t)width * height;
 		std::vector<restir_reservoir> reservoirs(pixels);
-		device.check(restir_download_reservoirs(device.get(), currentGBufferFrame ^ 1, reservoirs.data()));
 		std::vector<unsigned char> rgba(pixels * 4);
-		cuda(cudaMemcpy(rgba.data(), image, rgba.size(), cudaMemcpyDeviceToHost), "memcpy image");
-		std::printf("{\"frames\": %d, \"ms_per_frame_wall\": %.4f, \"shadow_rays\": %llu, \"kernel_launches\": %llu, "
-		            "\"reservoir_fnv1a\": \"%016llx\", \"image_fnv1a\": \"%016llx\"}\n",
-		            frames, ms / frames, (unsigned long long)counters.shadow_rays, (unsigned long long)counters.kernel_launches,
+		unsigned long long rays = 0, launches = 0, haloMisses = 0, haloTimeouts = 0;
+		for (uint32_t r = 0; r < nBands; ++r) {
+			devices[r]->check(restir_get_counters(devices[r]->get(), &counters, 0));
+			rays += counters.shadow_rays;
+			launches += counters.kernel_launches;
+			haloMisses += counters.halo_misses;
+			haloTimeouts += counters.halo_wait_timeouts;
+			const size_t bandPixels = (size_t)(allocEnd[r] - allocBegin[r]) * width;
+			std::vector<restir_reservoir> part(bandPixels);
+			devices[r]->check(restir_download_reservoirs(devices[r]->get(), currentGBufferFrame ^ 1, part.data()));
+			std::vector<unsigned char> img(bandPixels * 4);
+			cuda(cudaMemcpy(img.data(), images[r], img.size(), cudaMemcpyDeviceToHost), "memcpy image");
+			const size_t first = (size_t)(bounds[r] - allocBegin[r]) * width, count = (size_t)(bounds[r + 1] - bounds[r]) * width;
+			std::copy(part.begin() + first, part.begin() + first + count, reservoirs.begin() + (size_t)bounds[r] * width);
+			std::copy(img.begin() + first * 4, img.begin() + (first + count) * 4, rgba.begin() + (size_t)bounds[r] * width * 4);
+		}
+		std::printf("{\"frames\": %d, \"bands\": %u, \"ms_per_frame_wall\": %.4f, \"shadow_rays\": %llu, \"kernel_launches\": %llu, "
+		            "\"halo_misses\": %llu, \"halo_wait_timeouts\": %llu, \"reservoir_fnv1a\": \"%016llx\", \"image_fnv1a\": \"%016llx\"}\n",
+		            frames, nBands, ms / frames, rays, launches, haloMisses, haloTimeouts,
 		            (unsigned long long)fnv1a(reservoirs.data(), reservoirs.size() * sizeof(restir_reservoir)),
 		            (unsigned long long)fnv1a(rgba.data(), rgba.size()));
 	} catch (const restir::Error &e) {

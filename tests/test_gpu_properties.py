@@ -312,3 +312,14 @@ def test_cpp_host_driver_matches_python_driven_run(tmp_path):
     assert res["image_fnv1a"] == fnv(img.cpu().numpy().tobytes())
     assert res["shadow_rays"] == df.ctx.counters()["shadow_rays"]
     df.ctx.close()
+
+    # the same frames as row bands, entirely from C++ (restir::BandSet over restir_band_connect): three band contexts on
+    # this GPU exchange their halos themselves and must reproduce the single-context checksums, biased and unbiased
+    for unbiased in ("1", "0"):
+        one = json.loads(subprocess.run([exe, d, str(w), str(h), str(frames), unbiased, "3"], check=True, capture_output=True,
+                                        text=True).stdout.strip().splitlines()[-1])
+        banded = json.loads(subprocess.run([exe, d, str(w), str(h), str(frames), unbiased, "3", "--bands", "3", "--halo", "36"], check=True,
+                                           capture_output=True, text=True).stdout.strip().splitlines()[-1])
+        assert banded["bands"] == 3 and banded["halo_misses"] == 0 and banded["halo_wait_timeouts"] == 0
+        assert banded["reservoir_fnv1a"] == one["reservoir_fnv1a"] and banded["image_fnv1a"] == one["image_fnv1a"]
+        assert banded["shadow_rays"] == one["shadow_rays"]
