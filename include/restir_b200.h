@@ -217,7 +217,7 @@ typedef struct restir_counters {
 	uint64_t stack_overflows;   /* pushes dropped on a full 32-entry traversal stack (UB in the reference) */
 	uint64_t halo_misses;       /* band mode: neighbour / reprojection reads outside [alloc_begin, alloc_end) */
 	uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
-	uint64_t halo_wait_timeouts; /* connected bands: waits for a neighbour's rows that gave up after 2 s (a lost neighbour must not hang the GPU) */
+	uint64_t halo_wait_timeouts; /* connected bands: waits for a neighbour's rows that gave up after 5 s (a lost neighbour must not hang the GPU) */
 	uint64_t shadow_rays_traced; /* of shadow_rays, the ones that needed a walk of the tree: the rest were answered exactly
 	                              * without one (neighbour rays of a pixel whose own ray is shadowed, unbiasedReuse.glsl:157-166;
 	                              * neighbour rays bit-identical to the neighbour's own ray) */

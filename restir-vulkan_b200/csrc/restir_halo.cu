@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloPush hp) {
 	}
 }
 
-// Spins until both flags have reached `sequence` (or a generous timeout, counted: a lost neighbour must not hang the GPU).
+// Spins until both flags have reached `sequence` (or a 5 s timeout, counted: a lost neighbour must not hang the GPU).
 __global__ void halo_wait_kernel(const unsigned long long *flagA, const unsigned long long *flagB, unsigned long long sequence,
                                  unsigned long long timeoutNs, unsigned long long *counters) {
 	unsigned long long start;
@@ -77,7 +77,7 @@ cudaError_t launch_halo_push(const HaloPush &hp, int smCount, cudaStream_t s) {
 }
 cudaError_t launch_halo_wait(const unsigned long long *flagA, const unsigned long long *flagB, unsigned long long sequence, unsigned long long *counters,
                              cudaStream_t s) {
-	halo_wait_kernel<<<1, 1, 0, s>>>(flagA, flagB, sequence, 2000000000ull, counters);
+	halo_wait_kernel<<<1, 1, 0, s>>>(flagA, flagB, sequence, 5000000000ull, counters);
 	return cudaGetLastError();
 }
 
