@@ -207,6 +207,10 @@ __host__ __device__ inline uint32_t draws_per_candidate(bool pointMode) { return
 //     selected, so the division is done once after the loop from the (sumWeights, M) recorded at selection;
 //   * a point light behind the surface has pHat = +0 (restirUtils.glsl:8-10) and, for prob > 0, weight +0:
 //     sumWeights and the selection are unchanged and only M and the RNG advance (reservoir.glsl:6-26).
+#ifndef RESTIR_TEMPORAL_MIN_BLOCKS
+#define RESTIR_TEMPORAL_MIN_BLOCKS 5 // latency-bound gathers: 0.111 -> 0.099 ms; the candidate loop is issue-bound and loses with fewer registers (0.707 -> 0.744 at 5)
+#endif
+// no minimum CTA count here: the loop is issue-bound, 64 registers (4 CTAs/SM) is what ptxas picks on its own and both 72 and 51 lose
 __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
 	int x, y;
 	if (!pixel_of_thread(p.band, x, y)) {
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, RESTIR_CANDIDATES_MIN_BLOCKS) omni_c
 }
 
 // restirOmni.glsl:148-212 on the reservoir omni_candidates_kernel wrote.
-__global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, PackedReservoir *__restrict__ out,
+__global__ void __launch_bounds__(kThreads, RESTIR_TEMPORAL_MIN_BLOCKS) omni_temporal_kernel(PassParams p, PackedReservoir *__restrict__ out,
                                                                 const PackedReservoir *__restrict__ prevReservoirs,
                                                                 const unsigned char *__restrict__ shadowed, LcgJump jump) {
 	int x, y;
@@ -479,7 +483,10 @@ __global__ void __launch_bounds__(kThreads) omni_temporal_kernel(PassParams p, P
 
 // ------------------------------------------------------------------------------------------------
 // spatialReuse.comp:30-86
-__global__ void __launch_bounds__(kThreads) spatial_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+#ifndef RESTIR_SPATIAL_MIN_BLOCKS
+#define RESTIR_SPATIAL_MIN_BLOCKS 4 // same reasoning: 0.253 -> 0.222 ms per pass
+#endif
+__global__ void __launch_bounds__(kThreads, RESTIR_SPATIAL_MIN_BLOCKS) spatial_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
                                                                 PackedReservoir *__restrict__ out, int iter) {
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
@@ -537,8 +544,11 @@ constexpr int kMaxUnbiasedNeighbors = 16;
 
 // K > 0: the neighbour count is the compile-time K (the reference's NUM_NEIGHBORS 3 and the north-star's 5): the
 // neighbour loops unroll and the neighbour indices stay in registers; K == 0: any count up to kMaxUnbiasedNeighbors.
+#ifndef RESTIR_REUSE_MIN_BLOCKS
+#define RESTIR_REUSE_MIN_BLOCKS 4 // 64 registers instead of 78: the kernel waits on gathers (long scoreboard), a fourth CTA per SM hides more of them (0.304 -> 0.272 ms)
+#endif
 template <int K>
-__global__ void __launch_bounds__(kThreads) unbiased_merge_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+__global__ void __launch_bounds__(kThreads, RESTIR_REUSE_MIN_BLOCKS) unbiased_merge_kernel(PassParams p, const PackedReservoir *__restrict__ in,
                                                                  PackedReservoir *__restrict__ out, int numNeighborsArg,
                                                                  int *__restrict__ neighborPix) {
 	const int numNeighbors = K ? K : numNeighborsArg;
