@@ -83,7 +83,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
+
+    def mark(self):
+        """The timed region starts here: nvidia-smi needs a moment to produce its first line, so it is started during
+        the warm-up and only the samples from this point on are used."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -108,7 +113,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in (self.lines[self.first:] or self.lines):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
@@ -424,14 +429,15 @@ def main():
     # ---- device-resident timing: K steps, each bracketed by events on the launching stream, L2 flushed
     # between steps (outside the timed brackets) ---------------------------------------------------------
     frame_no = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         device_step(frame_no)
         frame_no += 1
     barrier()
     ctx.counters(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):

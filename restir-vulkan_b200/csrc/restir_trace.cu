@@ -27,7 +27,10 @@
 
 namespace restir {
 
-constexpr int kTraceThreads = 256;
+#ifndef RESTIR_TRACE_THREADS
+#define RESTIR_TRACE_THREADS 256
+#endif
+constexpr int kTraceThreads = RESTIR_TRACE_THREADS;
 constexpr int kTraceWarps = kTraceThreads / 32;
 #ifndef RESTIR_TRACE_CHUNK
 #define RESTIR_TRACE_CHUNK 128
