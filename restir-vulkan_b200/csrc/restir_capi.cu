@@ -29,7 +29,7 @@ struct restir_context {
 	// scene
 	float4 *nodes = nullptr, *tris = nullptr;
 	float4 *image = nullptr; // 64-byte image of `nodes` (traversal_image.h); null => literal 80-byte walk
-	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `tris`: what the trace kernel walks, pinned in L2
+	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `tris`: what the trace kernel walks
 	size_t treeBlockBytes = 0;
 	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
@@ -495,26 +495,6 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 		CU(ctx, cudaMemcpyAsync(ctx->image, image.data(), image.size() * sizeof(Node64), cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
-	{
-		// keep what the trace kernel walks resident in L2 (126 MB on B200): the per-frame streams (G-buffer, reservoirs:
-		// ~0.5 GB at 1080p) would otherwise push tree lines out between two launches of the trace kernel.  Best effort:
-		// a device without the feature just runs without it.
-		cudaDeviceProp prop;
-		if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 &&
-		    std::getenv("RESTIR_NO_L2_PERSIST") == nullptr) {
-			size_t want = std::min(ctx->treeBlockBytes, (size_t)prop.persistingL2CacheMaxSize);
-			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-				cudaStreamAttrValue attr{};
-				attr.accessPolicyWindow.base_ptr = ctx->treeBlock;
-				attr.accessPolicyWindow.num_bytes = std::min(ctx->treeBlockBytes, (size_t)prop.accessPolicyMaxWindowSize);
-				attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
-				attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-				attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-				cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-			}
-			cudaGetLastError(); // best effort: never sticky
-		}
-	}
 	ctx->nNodes = n_nodes;
 	ctx->nTris = n_triangles;
 	ctx->imageInfo = info;
