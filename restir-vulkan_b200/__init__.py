@@ -6,7 +6,8 @@ Layout:
              reference's pass classes (passes.hpp)
   capi.py    ctypes binding of the C ABI (what tests and bench.py call)
   fixtures.py  scene inputs (baked reference scenes, procedural scenes, material tables)
-  bands.py   row-band multi-GPU driver (halo exchange over torch.distributed)
+  bands.py   row-band multi-GPU driver (band cutting, halo sizing, neighbour wiring; torch.distributed is plumbing)
+  capture.py frame captures (include/restir_capture.h): numpy writer / reader
 
 The directory name carries a hyphen, so it is loaded through __graft_entry__.load_package() as the
 module `restir_vulkan_b200`.

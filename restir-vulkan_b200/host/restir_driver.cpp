@@ -11,6 +11,12 @@
 //
 // <scene_dir> holds triangles.bin (n x 48), tri_material.i32, materials.f32 (m x 16), dims.f32 and
 // material_table.u32 (m x 4) — what scenes/_baked/<name>/ or restir-vulkan_b200/fixtures.py write.
+//   restir_driver --replay <capture.rsc>
+//
+// --replay (no reference equivalent): runs a frame capture (include/restir_capture.h — scene buffers, uniforms and
+// G-buffers of every frame, e.g. dumped from a run of the Vulkan application) through the passes and counts what
+// differs from the outputs the capture carries.
+//
 // Prints one JSON line: FNV-1a checksums of the final reservoirs (64-byte layout) and of the RGBA8 image,
 // ms per frame and ray count — tests compare the checksums with the same sequence driven from Python.
 
@@ -26,6 +32,7 @@
 
 #include <cuda_runtime.h>
 
+#include "capture.hpp"
 #include "passes.hpp"
 
 namespace {
@@ -72,9 +79,92 @@ struct DeviceGBuffer {
 	restir_gbuffer_planes planes() const { return restir_gbuffer_planes{plane[0], plane[1], plane[2], plane[3], plane[4]}; }
 };
 
+// --replay: the capture's frames through the passes, compared with the outputs it carries.
+int replay(const std::string &path) {
+	restir::Capture cap = restir::Capture::read(path);
+	const restir_capture_header &h = cap.header;
+	const size_t pixels = (size_t)h.width * h.height;
+	restir::Device device(0);
+	device.check(restir_upload_bvh(device.get(), cap.nodes.data(), h.n_nodes, cap.triangles.data(), h.n_triangles));
+	device.check(restir_upload_lights(device.get(), cap.pointBlob.data(), cap.pointBlob.size(), cap.triBlob.data(), cap.triBlob.size(),
+	                                  cap.aliasBlob.data(), cap.aliasBlob.size()));
+	device.check(restir_resize(device.get(), h.width, h.height));
+	device.check(restir_set_unbiased_neighbors(device.get(), h.unbiased_neighbors ? h.unbiased_neighbors : 3));
+	float *image = nullptr;
+	cuda(cudaMalloc(&image, pixels * 16), "cudaMalloc image");
+	std::vector<restir_reservoir> got(pixels);
+	std::vector<float> rgba(pixels * 4);
+	size_t badInitial = 0, badFinal = 0, badPixels = 0;
+	double maxRel = 0.0;
+	for (uint32_t f = 0; f < h.frames; ++f) {
+		const restir::CaptureFrame &fr = cap.frames[f];
+		const int i = (int)(f & 1u), p = i ^ 1;
+		restir_gbuffer_planes planes{fr.plane[0].data(), fr.plane[1].data(), fr.plane[2].data(), fr.plane[3].data(), fr.plane[4].data()};
+		device.check(restir_upload_gbuffer(device.get(), i, RESTIR_GBUFFER_NVIDIA_DEFAULT, &planes));
+		device.check(restir_set_uniforms(device.get(), &fr.uniforms));
+		device.check(restir_set_lighting_uniforms(device.get(), &fr.lightingUniforms));
+		const int first = h.unbiased ? RESTIR_BUF_TEMP : i; // src/app.h:298-332
+		device.check(restir_pass_restir(device.get(), i, first, p));
+		if (!fr.initial.empty()) {
+			device.check(restir_download_reservoirs(device.get(), first, got.data()));
+			badInitial += restir::countReservoirMismatches(got, fr.initial);
+		}
+		if (h.unbiased) {
+			device.check(restir_pass_unbiased(device.get(), i, RESTIR_BUF_TEMP, i));
+		} else {
+			for (uint32_t j = 0; j < h.spatial_iterations; ++j) {
+				device.check(restir_pass_spatial(device.get(), i, i, p, (int)(2 * j)));
+				device.check(restir_pass_spatial(device.get(), i, p, i, (int)(2 * j + 1)));
+			}
+		}
+		if (!fr.final.empty()) {
+			device.check(restir_download_reservoirs(device.get(), i, got.data()));
+			badFinal += restir::countReservoirMismatches(got, fr.final);
+		}
+		device.check(restir_pass_lighting(device.get(), i, i, image, RESTIR_OUT_RGBA32F));
+		device.waitIdle();
+		if (!fr.rgba.empty()) {
+			cuda(cudaMemcpy(rgba.data(), image, pixels * 16, cudaMemcpyDeviceToHost), "memcpy image");
+			for (size_t k = 0; k < pixels; ++k) {
+				bool bad = false;
+				for (int c = 0; c < 3; ++c) { // tolerance of tests/parity_harness.py: rel 1e-3 with an absolute floor of 1e-6
+					const double a = rgba[k * 4 + c], b = fr.rgba[k * 4 + c];
+					if (a != a && b != b) continue;
+					const double diff = a > b ? a - b : b - a, den = (b < 0 ? -b : b) > 1e-6 ? (b < 0 ? -b : b) : 1e-6;
+					if (!(diff <= 1e-6)) {
+						maxRel = diff / den > maxRel ? diff / den : maxRel;
+						bad = bad || !(diff / den <= 1e-3);
+					}
+				}
+				badPixels += bad ? 1 : 0;
+			}
+		}
+	}
+	restir_counters counters{};
+	device.check(restir_get_counters(device.get(), &counters, 0));
+	std::printf("{\"replay\": \"%s\", \"frames\": %u, \"width\": %u, \"height\": %u, \"unbiased\": %u, \"expected\": %u, "
+	            "\"mismatching_initial_reservoirs\": %zu, \"mismatching_final_reservoirs\": %zu, \"mismatching_pixels\": %zu, "
+	            "\"max_rel_rgb_error\": %.3g, \"shadow_rays\": %llu}\n",
+	            path.c_str(), h.frames, h.width, h.height, h.unbiased, h.expected, badInitial, badFinal, badPixels, maxRel,
+	            (unsigned long long)counters.shadow_rays);
+	cudaFree(image);
+	return (badInitial || badFinal || badPixels) ? 5 : 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv) {
+	if (argc == 3 && std::string(argv[1]) == "--replay") {
+		try {
+			return replay(argv[2]);
+		} catch (const restir::Error &e) {
+			std::cerr << "restir_driver: error " << e.code << ": " << e.what() << "\n";
+			return 1;
+		} catch (const std::exception &e) {
+			std::cerr << "restir_driver: " << e.what() << "\n";
+			return 2;
+		}
+	}
 	if (argc < 6) {
 		std::cerr << "usage: restir_driver <scene_dir> <width> <height> <frames> <unbiased 0|1> [neighbors] [--bands N] [--halo ROWS]\n";
 		return 64;

@@ -212,6 +212,24 @@ def run_cuda(case, ctx=None):
     return out
 
 
+# ---- frame captures (include/restir_capture.h) -----------------------------------------------------------
+
+def make_capture(case, frames_out=None):
+    """The capture of a Case: its scene buffers, per-frame uniforms and G-buffers, and — when `frames_out` (the result of
+    run_oracle / run_cuda) is given — the outputs to compare a replay with."""
+    capture = __import__("restir_vulkan_b200.capture", fromlist=["capture"])
+    frames = []
+    for f, g in enumerate(case.gbuffers()):
+        u, lu = case.uniforms(f)
+        fr = dict(uniforms=u, lighting_uniforms=lu, planes=list(g.planes()))
+        if frames_out is not None:
+            fr.update(initial=frames_out[f]["initial"], final=frames_out[f]["reservoirs"], rgba=frames_out[f]["rgba"])
+        frames.append(fr)
+    sc = case.scene
+    return capture.Capture(case.w, case.h, case.unbiased, case.unbiased_neighbors, case.iterations, sc.nodes, sc.triangles, sc.point_blob,
+                           sc.tri_blob, sc.alias_blob, frames)
+
+
 # ---- comparison -------------------------------------------------------------------------------------
 
 FLOAT_FIELDS = ("position_emissionLum", "normal", "pHat", "sumWeights", "w")
