@@ -53,32 +53,34 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, h, w, halo, out_dir):
+def _worker(rank, world, port, h, w, halo, out_dir, bounds=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    b, e = bands.band_rows(h, world, rank)
+    b, e = bands.band_rows(h, world, rank, bounds)
     a0, a1 = max(0, b - halo), min(h, e + halo)
     # every row carries its global row index and the owner's rank; halos start out as garbage
     buf = torch.full((a1 - a0, w), -1.0)
     for y in range(b, e):
         buf[y - a0] = y * 1000.0 + rank
-    plan = bands.halo_plan(h, world, rank, halo)
+    plan = bands.halo_plan(h, world, rank, halo, bounds)
     bands.exchange_halo(buf, a0, plan, dist)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), buf.numpy())
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_exchange_halo_over_gloo(world, tmp_path):
+@pytest.mark.parametrize("world,bounds", [(2, None), (3, None), (3, [0, 17, 83, 120]), (2, [0, 61, 80])])
+def test_exchange_halo_over_gloo(world, bounds, tmp_path):
+    """Equal bands and bands of unequal height (bands.balanced_bounds cuts them like that): after one exchange every
+    allocated row holds what its owner wrote."""
     h, w, halo = 40 * world, 8, 5
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, h, w, halo, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, h, w, halo, str(tmp_path), bounds), nprocs=world, join=True)
     for rank in range(world):
-        b, e = bands.band_rows(h, world, rank)
+        b, e = bands.band_rows(h, world, rank, bounds)
         a0, a1 = max(0, b - halo), min(h, e + halo)
         got = np.load(tmp_path / f"rank{rank}.npy")
         for y in range(a0, a1):
-            owner = [r for r in range(world) if bands.band_rows(h, world, r)[0] <= y < bands.band_rows(h, world, r)[1]][0]
+            owner = [r for r in range(world) if bands.band_rows(h, world, r, bounds)[0] <= y < bands.band_rows(h, world, r, bounds)[1]][0]
             assert (got[y - a0] == y * 1000.0 + owner).all(), (rank, y)
 
 
