@@ -1,26 +1,29 @@
 // restir_trace.cu — the persistent shadow-ray kernel (sm_100a).
 //
-// One kernel traces every shadow ray of the path: the visibility-reuse ray of restirOmni.glsl:148-160, the
-// neighbour and self rays of unbiasedReuse.glsl:126-166, and the stand-alone segments of
-// restir_trace_segments.  The reference traces them inline, one thread per pixel, in whatever order the
-// pixels come.  Here rays are work items of a persistent grid:
+// One kernel traces every shadow ray of the path: the visibility-reuse ray of restirOmni.glsl:148-160 and the pixels'
+// own rays of unbiasedReuse.glsl:157-166 (kTracePixel), the neighbour rays of unbiasedReuse.glsl:139-156
+// (kTraceUnbiased, launched after the own rays) and the stand-alone segments of restir_trace_segments.  The
+// reference traces them inline, one thread per pixel, in whatever order the pixels come.  Here rays are work items
+// of a persistent grid:
 //
-//   * every WARP pulls chunks of kChunk consecutive items (items are numbered by 8x4 screen tile, so a chunk
-//     is a compact screen patch) from a global cursor;
-//   * it sorts the chunk by the light the ray is aimed at (bitonic sort of 32-bit keys in shared memory), so
+//   * every WARP pulls chunks of consecutive items (128, or 256 neighbour-ray slots; items are numbered by 8x4
+//     screen tile, so a chunk is a compact screen patch) from a global cursor;
+//   * items that need no walk are answered on the spot (item_resolve: neighbour rays of a pixel whose own ray is
+//     shadowed, neighbour rays bit-identical to the neighbour's own ray — exact, see there);
+//   * it sorts the rest by the light the ray is aimed at (bitonic sort of 32-bit keys in shared memory), so
 //     the 32 rays a warp then walks in lockstep start next to each other AND end at the same light: they
-//     visit the same nodes at the same time (one L1 wavefront serves many lanes — the measured limiter of
-//     this kernel is L1 wavefronts, not DRAM, profiles/) and finish at about the same time;
+//     visit the same nodes at the same time (one L1 tag lookup serves many lanes — the measured limiters of
+//     this kernel are L1 lookups and instruction issue, not DRAM, profiles/) and finish at about the same time;
 //   * each lane builds its segment from the G-buffer / reservoir (visibilityTest.glsl:1-4) and walks the tree
-//     (restir_trace.cuh).
+//     (restir_trace.cuh: two 32-byte loads per node, both boxes with packed FADD2 / FMUL2).
 //
-// Measured alternatives that lost (B200, Sponza 1080p, profiles/r1_b*, r1_d*): per-lane refill from a
-// shared-memory ray queue (lanes decorrelate, every 16-byte node load becomes its own L1 wavefront: 1.8
-// Grays/s), and a 4-wide re-layout of the tree in lockstep or with refill (same instruction count per ray as
-// the 2-wide walk once the exact slab arithmetic is kept: 2.9-3.3 Grays/s) against 4.2 Grays/s for the plain
-// 2-wide walk of this file's first version.
+// Measured alternatives that lost (B200, Sponza 1080p, profiles/r1_f_summary.md, r1_m_summary.md): per-lane refill
+// from a shared-memory ray queue (lanes decorrelate, every node load becomes its own L1 lookup: 1.8 Grays/s), a
+// 4-wide re-layout of the tree (same instruction count per ray once the exact slab arithmetic is kept), a stepwise
+// walk with warp votes, the stack in shared memory, a branch-free push/pop, a two-round walk with parked rays,
+// 64- and 128-thread CTAs (flat), 40 registers for 6 CTAs per SM (flat; 36 and 32 lose).
 //
-// Per item one byte is written: 1 = shadowed.
+// Per ray one byte is written: 1 = shadowed.
 
 #include "restir_kernels.h"
 #include "restir_trace.cuh"
