@@ -89,6 +89,21 @@ def with_random_point_lights(scene, count):
                      scene.ref)
 
 
+def with_point_lights(scene, positions, colours):
+    """The scene lit by exactly these point lights (pointLight: vec4 pos, w = 1; vec4 colour, w = luminance —
+    src/misc.cpp:343-356).  Degenerate lights are allowed: tests use zero and huge luminances and lights on surfaces."""
+    positions, colours = np.asarray(positions, np.float32).reshape(-1, 3), np.asarray(colours, np.float32).reshape(-1, 3)
+    rec = np.zeros((positions.shape[0], 8), np.float32)
+    rec[:, 0:3], rec[:, 3] = positions, 1.0
+    rec[:, 4:7] = colours
+    rec[:, 7] = (np.float32(0.2126) * colours[:, 0] + np.float32(0.7152) * colours[:, 1]) + np.float32(0.0722) * colours[:, 2]  # common.glsl:7-9
+    point = rec.view(np.uint8).reshape(-1, 32)
+    alias = capi.create_alias_table(point, np.zeros((0, 80), np.uint8))
+    return SceneData(f"{scene.name}+{positions.shape[0]}pl", scene.triangles, scene.tri_material, scene.materials, scene.nodes,
+                     capi.make_blob(point, 32), capi.make_blob(np.zeros((0, 80), np.uint8), 80), capi.make_blob(alias, 16), scene.dims,
+                     scene.ref)
+
+
 # ---- material -> G-buffer codes (src/shaders/gBuffer.frag:27-79 with all textures = 1) -------------
 
 def _srgb_encode8(c):

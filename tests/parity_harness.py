@@ -129,6 +129,38 @@ EDGE_CASES = [
 ]
 
 
+def degenerate_light_case(kind, w=48, h=27, unbiased=True):
+    """Lights that drive the arithmetic to its edges: `on-surface` puts a light exactly at a visible surface point (zero
+    distance: 0 * inf = NaN in normalize), `zero-luminance` adds lights whose alias probability is 0 (p-hat / 0),
+    `huge` lets p-hat overflow to infinity.  NaN and infinity must flow through the reservoirs exactly as in the reference."""
+    base = fixtures.make_procedural(seed=21, grid=10, boxes=20, lights="point", n_point_lights=6)
+    cams = moving_cameras(2, (3.0, 3.5, 4.2), (0.0, -1.0, 0.0), w / h)
+    probe = Case(base, w, h, cams[:1])
+    world = probe.gbuffers()[0].world_pos.reshape(-1, 4)
+    normal = probe.gbuffers()[0].normal.reshape(-1, 4)
+    surface = np.flatnonzero((normal[:, :3] != 0).any(axis=1))
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(-3, 3, (5, 3)).astype(np.float32)
+    pos[:, 1] = np.abs(pos[:, 1]) + 1.0
+    col = rng.uniform(0.2, 1.0, (5, 3)).astype(np.float32)
+    if kind == "on-surface":
+        pick = surface[[len(surface) // 3, len(surface) // 2, (2 * len(surface)) // 3]]
+        pos[:3] = world[pick, :3]
+    elif kind == "zero-luminance":
+        col[1] = 0.0
+        col[3] = 0.0
+    elif kind == "huge":
+        col[0] = np.float32(3e38)
+        col[2] = np.float32(1e30)
+    else:
+        raise ValueError(kind)
+    scene = fixtures.with_point_lights(base, pos, col)
+    return Case(scene, w, h, cams, candidates=16, unbiased=unbiased, unbiased_neighbors=3)
+
+
+DEGENERATE_LIGHTS = ["on-surface", "zero-luminance", "huge"]
+
+
 # ---- running both sides -----------------------------------------------------------------------------
 
 def run_oracle(case, rows=None, passes=None):

@@ -202,6 +202,23 @@ def test_edge_cases_match_oracle(label, name, size, frames, kw):
     ph.assert_frames_match(ph.run_cuda(case), ph.run_oracle(case), label)
 
 
+@pytest.mark.parametrize("unbiased", [True, False])
+@pytest.mark.parametrize("kind", ph.DEGENERATE_LIGHTS)
+def test_degenerate_lights_match_oracle(kind, unbiased):
+    """NaN and infinity through the reservoirs (parity_harness.degenerate_light_case: a light exactly on a visible surface
+    point, zero-probability lights, luminances that overflow p-hat): the kernels follow the oracle bit for bit, any NaN
+    equal to any NaN — the same cases hold between the oracle and the reference's shader text on the CPU."""
+    _torch()
+    case = ph.degenerate_light_case(kind, unbiased=unbiased)
+    got, want = ph.run_cuda(case), ph.run_oracle(case)
+    for f, (c, o) in enumerate(zip(got, want)):
+        assert ph.compare_reservoirs(c["initial"], o["initial"], f"{kind} frame {f} after restirOmni") == 0
+        assert ph.compare_reservoirs(c["reservoirs"], o["reservoirs"], f"{kind} frame {f} final") == 0
+        assert c["rays"] == o["rays"]
+        same = ph.bits_equal(c["rgba"][..., :3], o["rgba"][..., :3])
+        assert same.all(), f"{kind} frame {f}: {(~same).sum()} colour values differ"
+
+
 def test_zero_candidates_leave_empty_reservoirs():
     """initialLightSampleCount = 0: the candidate loop does not run (restirOmni.glsl:108), reservoirs stay as newReservoir
     left them (oracle definition: zero), yet the passes run to the end and match the oracle."""

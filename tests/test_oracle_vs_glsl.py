@@ -149,3 +149,17 @@ def test_edge_cases_oracle_equals_reference_source(label, name, size, frames, kw
         assert ph.compare_reservoirs(o["initial"], r["initial"], f"{label} frame {f} after restirOmni") == 0
         assert ph.compare_reservoirs(o["reservoirs"], r["reservoirs"], f"{label} frame {f} final") == 0
         assert ph.bits_equal(o["rgba"][..., :3], r["rgba"][..., :3]).all()
+
+
+@pytest.mark.parametrize("unbiased", [True, False])
+@pytest.mark.parametrize("kind", ph.DEGENERATE_LIGHTS)
+def test_degenerate_lights_oracle_equals_reference_source(kind, unbiased):
+    """NaN and infinity through the reservoirs (parity_harness.degenerate_light_case): the reference's shader text and the
+    oracle agree bit for bit, any NaN equal to any NaN."""
+    case = ph.degenerate_light_case(kind, unbiased=unbiased)
+    want = ph.run_oracle(case, passes=gl)
+    got = ph.run_oracle(case)
+    for f, (o, r) in enumerate(zip(got, want)):
+        assert ph.compare_reservoirs(o["initial"], r["initial"], f"{kind} frame {f} after restirOmni") == 0
+        assert ph.compare_reservoirs(o["reservoirs"], r["reservoirs"], f"{kind} frame {f} final") == 0
+        assert ph.bits_equal(o["rgba"][..., :3], r["rgba"][..., :3]).all()
