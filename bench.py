@@ -537,16 +537,27 @@ def main():
     top = max(kernel_ms, key=kernel_ms.get)
     top_ms = kernel_ms[top] / max(kernel_launches[top], 1)
     achieved = alg[top] / (top_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, warp_inst = None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.config, {}).get(top)
+        tdoc = json.load(open(tpath))
+        traffic = tdoc.get(args.config, {}).get(top)
+        warp_inst = tdoc.get(args.config + ":warp_instructions", {})
+    # issue-slot utilisation per kernel: warp instructions of one launch (smsp__inst_executed.sum from the committed ncu
+    # capture of this configuration) / this run's event-timed duration / (SMs x 4 schedulers x SM clock)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    issue_frac = {n: warp_inst[n] / (kernel_ms[n] / max(kernel_launches[n], 1) * 1e-3) / (sm_count * 4 * sm_hz)
+                  for n in kernel_ms if n in warp_inst and world == 1}
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top], "kernel_ms": top_ms,
                 "launches_per_frame": kernel_launches[top],
+                "issue_frac": issue_frac.get(top),
                 "note": "the trace kernel is bound by L1 tag lookups (83 % l1tex) and instruction issue (71 % issue-active) together, not by HBM: "
                         "the tree is L2/L1-resident and DRAM sits below 2 % (profiles/r1_m_summary.md); its yardsticks are Mrays/s and lanes per "
-                        "instruction; the streaming kernels' HBM fractions are in kernel_hbm_frac"}
+                        "instruction; the streaming kernels' HBM fractions are in kernel_hbm_frac; issue_frac / kernel_issue_frac = warp "
+                        "instructions per launch (profiles/traffic.json, from the ncu capture) over this run's kernel time and the SMs' "
+                        "issue rate (N = 1 only)"}
     kernel_hbm_frac = {n: (alg[n] * kernel_launches[n] / (kernel_ms[n] * 1e-3) / 1e9 / peak) for n in kernel_ms if alg.get(n)}
     frame_bytes = sum(alg[n] * kernel_launches[n] for n in kernel_ms if alg.get(n))
     hbm_frame_frac = frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak
@@ -671,7 +682,7 @@ def main():
             "rays_note": "value counts the reference's testVisibility calls answered per second (the same unit of work as the --impl reference "
                          "arm); rays_walked_per_frame of them needed a walk of the tree, the rest are answered exactly without one",
             "pass_ms": dict(zip(names, [float(x) for x in pass_ms])),
-            "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac,
+            "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac, "kernel_issue_frac": issue_frac,
             "trace_kernel_mrays_per_s": trace_mrays, "trace_kernel_mrays_walked_per_s": trace_mrays_walked, "bvh": info,
             "hbm_frame_frac": hbm_frame_frac, "frame_algorithmic_bytes": frame_bytes,
             "gpu_launches": int(launches), "halo_misses": int(halo_misses), "halo_wait_timeouts": int(halo_timeouts), "stack_overflows": int(overflows),

@@ -28,7 +28,7 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units = rows[0], rows[1]
-    traffic, lines, n_trace = {}, [], 0
+    traffic, insts, lines, n_trace = {}, {}, [], 0
     for row in rows[2:]:
         d = dict(zip(head, row))
         name = d["Kernel Name"]
@@ -55,6 +55,10 @@ def main():
             traffic[label] = int(float(d["dram__bytes_read.sum"].replace(",", "")) * scale[u_r] + float(d["dram__bytes_write.sum"].replace(",", "")) * scale[u_w])
         except (KeyError, ValueError):
             pass
+        try:
+            insts[label] = int(float(d["smsp__inst_executed.sum"].replace(",", "")))
+        except (KeyError, ValueError):
+            pass
     open(out, "w").write("\n".join(lines) + "\n")
     if len(sys.argv) >= 5:
         path, config = sys.argv[3], sys.argv[4]
@@ -64,6 +68,7 @@ def main():
             doc = {}
         doc["_comment"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/*_ncu_metrics.txt)"
         doc[config] = traffic
+        doc[config + ":warp_instructions"] = insts   # smsp__inst_executed.sum per launch (bench.py: issue-slot utilisation)
         json.dump(doc, open(path, "w"), indent=1)
     print(f"{len(rows) - 2} launches -> {out}")
 
