@@ -19,7 +19,7 @@ def test_header_symbols_are_exported():
 
 def test_headers_compile_as_c11():
     import subprocess
-    src = '#include "restir_b200.h"\nint main(void){return sizeof(restir_reservoir)==64?0:1;}\n'
+    src = '#include "restir_b200.h"\n#include "restir_capture.h"\nint main(void){return sizeof(restir_reservoir)==64&&sizeof(restir_capture_header)==72?0:1;}\n'
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
                    input=src.encode(), check=True)
 
