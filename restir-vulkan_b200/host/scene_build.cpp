@@ -15,7 +15,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <random>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -76,17 +79,10 @@ inline void setBox(float dst[4], const Vec3 &s) { // vec4(vec3) sets w = 1 (nvma
 
 } // namespace
 
-extern "C" int restir_build_aabb_tree(const void *triangles, uint32_t n_triangles, void *nodes_out) {
-	if (triangles == nullptr || nodes_out == nullptr || n_triangles < 2) {
-		return RESTIR_E_INVALID; // the reference asserts on a 1-triangle scene (aabbTreeBuilder.cpp:212)
-	}
-	constexpr size_t kBins = 12;
-	const restir_triangle *tris = static_cast<const restir_triangle *>(triangles);
-	restir_aabb_node *nodes = static_cast<restir_aabb_node *>(nodes_out);
-	std::memset(nodes, 0, sizeof(restir_aabb_node) * (size_t)(n_triangles - 1));
-
-	std::vector<LeafRecord> leaves(n_triangles);
-	for (uint32_t i = 0; i < n_triangles; ++i) { // aabbForTriangle + centroid, :8-14, :70-75
+// Leaf records of the triangles, aabbForTriangle + centroid (aabbTreeBuilder.cpp:8-14, 70-75)
+static void makeLeaves(const restir_triangle *tris, uint32_t n_triangles, std::vector<LeafRecord> &leaves) {
+	leaves.resize(n_triangles);
+	for (uint32_t i = 0; i < n_triangles; ++i) {
 		LeafRecord &l = leaves[i];
 		const float *a = tris[i].p1, *b = tris[i].p2, *c = tris[i].p3;
 		for (int k = 0; k < 3; ++k) {
@@ -102,18 +98,137 @@ extern "C" int restir_build_aabb_tree(const void *triangles, uint32_t n_triangle
 		l.geom = (int32_t)i;
 		l.bin = 0;
 	}
+}
 
-	auto writeSlot = [&](int64_t slot, int32_t value) {
-		if (slot < 0) {
-			return; // dummyRoot (:81): always receives 0
+static inline void writeSlot(restir_aabb_node *nodes, int64_t slot, int32_t value) {
+	if (slot < 0) {
+		return; // dummyRoot (:81): always receives 0
+	}
+	restir_aabb_node &n = nodes[slot >> 1];
+	if (slot & 1) {
+		n.rightChild = value;
+	} else {
+		n.leftChild = value;
+	}
+}
+
+// One BuildStep of the reference's loop (aabbTreeBuilder.cpp:86-209) on a range of more than two leaves: picks the
+// split, partitions leaves[beg, end) in place with the reference's own swap sequence, fills node `id` and returns the
+// pivot.  Touches nothing but its own range and its own node, so the steps of one breadth-first level are independent.
+static size_t splitRange(std::vector<LeafRecord> &leaves, restir_aabb_node *nodes, int32_t id, size_t beg, size_t end) {
+	constexpr size_t kBins = 12;
+	// :107-122 bounds of centroids and of geometry
+	Vec3 cLo = leaves[beg].centroid, cHi = cLo;
+	Vec3 gLo = leaves[beg].lo, gHi = leaves[beg].hi;
+	for (size_t i = beg + 1; i < end; ++i) {
+		growMin(cLo, leaves[i].centroid);
+		growMax(cHi, leaves[i].centroid);
+		growMin(gLo, leaves[i].lo);
+		growMax(gHi, leaves[i].hi);
+	}
+	const float outerArea = halfArea(gLo, gHi);
+	// :124-129 split axis = widest centroid extent
+	const float ext[3] = {cHi[0] - cLo[0], cHi[1] - cLo[1], cHi[2] - cLo[2]};
+	int axis = ext[0] > ext[1] ? 0 : 1;
+	if (ext[2] > ext[axis]) {
+		axis = 2;
+	}
+	// :130-142 binning.  When every centroid coincides on the axis the quotient is 0/0 = NaN and the
+	// reference's size_t cast is undefined; defined here as bin 0 (the median fallback then applies).
+	Bin bins[kBins];
+	const float binWidth = ext[axis] / (float)kBins;
+	for (size_t i = beg; i < end; ++i) {
+		LeafRecord &l = leaves[i];
+		float q = (l.centroid[axis] - cLo[axis]) / binWidth;
+		q = (q < 0.5f) ? 0.5f : q;
+		q = (q > (float)kBins - 0.5f) ? (float)kBins - 0.5f : q;
+		l.bin = (q == q) ? (uint32_t)q : 0u;
+		Bin &b = bins[l.bin];
+		growMin(b.lo, l.lo);
+		growMax(b.hi, l.hi);
+		++b.count;
+	}
+	// :143-151 suffix unions: rightOf[i] = bins[i+1..]
+	Bin rightOf[kBins - 1];
+	{
+		Bin acc = bins[kBins - 1];
+		for (size_t i = kBins - 1; i > 0;) {
+			rightOf[--i] = acc;
+			acc.absorb(bins[i]);
 		}
-		restir_aabb_node &n = nodes[slot >> 1];
-		if (slot & 1) {
-			n.rightChild = value;
-		} else {
-			n.leftChild = value;
+	}
+	// :152-171 cheapest of the 11 splits; an empty side costs 0 * inf = NaN and never wins
+	size_t bestSplit = 0;
+	Vec3 lLo{}, lHi{}, rLo{}, rHi{};
+	{
+		float bestCost = FLT_MAX;
+		Bin leftAcc;
+		for (size_t s = 0; s < kBins - 1; ++s) {
+			leftAcc.absorb(bins[s]);
+			const Bin &rightAcc = rightOf[s];
+			float cost = 0.125f + (leftAcc.cost() + rightAcc.cost()) / outerArea;
+			if (cost < bestCost) {
+				bestCost = cost;
+				bestSplit = s;
+				lLo = leftAcc.lo;
+				lHi = leftAcc.hi;
+				rLo = rightAcc.lo;
+				rHi = rightAcc.hi;
+			}
 		}
-	};
+	}
+	// :172-178 in-place partition, same swap sequence
+	size_t pivot = beg;
+	for (size_t i = beg; i < end; ++i) {
+		if (leaves[i].bin <= bestSplit) {
+			std::swap(leaves[i], leaves[pivot++]);
+		}
+	}
+	// :179-196 everything on one side: split at the median, recompute both boxes
+	if (pivot == beg || pivot == end) {
+		pivot = (beg + end) / 2;
+		lLo = leaves[beg].lo;
+		lHi = leaves[beg].hi;
+		for (size_t i = beg + 1; i < pivot; ++i) {
+			growMin(lLo, leaves[i].lo);
+			growMax(lHi, leaves[i].hi);
+		}
+		rLo = leaves[pivot].lo;
+		rHi = leaves[pivot].hi;
+		for (size_t i = pivot; i < end; ++i) {
+			growMin(rLo, leaves[i].lo);
+			growMax(rHi, leaves[i].hi);
+		}
+	}
+	// :198-207
+	restir_aabb_node &n = nodes[id];
+	setBox(n.leftAabbMin, lLo);
+	setBox(n.leftAabbMax, lHi);
+	setBox(n.rightAabbMin, rLo);
+	setBox(n.rightAabbMax, rHi);
+	return pivot;
+}
+
+// :91-104
+static void pairNode(const std::vector<LeafRecord> &leaves, restir_aabb_node *nodes, int32_t id, size_t beg) {
+	const LeafRecord &l = leaves[beg], &r = leaves[beg + 1];
+	restir_aabb_node &n = nodes[id];
+	n.leftChild = ~l.geom;
+	n.rightChild = ~r.geom;
+	setBox(n.leftAabbMin, l.lo);
+	setBox(n.leftAabbMax, l.hi);
+	setBox(n.rightAabbMin, r.lo);
+	setBox(n.rightAabbMax, r.hi);
+}
+
+extern "C" int restir_build_aabb_tree(const void *triangles, uint32_t n_triangles, void *nodes_out) {
+	if (triangles == nullptr || nodes_out == nullptr || n_triangles < 2) {
+		return RESTIR_E_INVALID; // the reference asserts on a 1-triangle scene (aabbTreeBuilder.cpp:212)
+	}
+	restir_aabb_node *nodes = static_cast<restir_aabb_node *>(nodes_out);
+	std::memset(nodes, 0, sizeof(restir_aabb_node) * (size_t)(n_triangles - 1));
+	std::vector<LeafRecord> leaves;
+	makeLeaves(static_cast<const restir_triangle *>(triangles), n_triangles, leaves);
 
 	int32_t nextNode = 0;
 	std::vector<Job> fifo; // breadth-first, like the reference's std::deque (:80-85)
@@ -123,116 +238,104 @@ extern "C" int restir_build_aabb_tree(const void *triangles, uint32_t n_triangle
 		const Job job = fifo[head];
 		const size_t span = job.end - job.beg;
 		if (span == 1) { // :88-90
-			writeSlot(job.slot, ~leaves[job.beg].geom);
+			writeSlot(nodes, job.slot, ~leaves[job.beg].geom);
 			continue;
 		}
-		if (span == 2) { // :91-104
-			const LeafRecord &l = leaves[job.beg], &r = leaves[job.beg + 1];
-			int32_t id = nextNode++;
-			writeSlot(job.slot, id);
-			restir_aabb_node &n = nodes[id];
-			n.leftChild = ~l.geom;
-			n.rightChild = ~r.geom;
-			setBox(n.leftAabbMin, l.lo);
-			setBox(n.leftAabbMax, l.hi);
-			setBox(n.rightAabbMin, r.lo);
-			setBox(n.rightAabbMax, r.hi);
-			continue;
-		}
-
-		// :107-122 bounds of centroids and of geometry
-		Vec3 cLo = leaves[job.beg].centroid, cHi = cLo;
-		Vec3 gLo = leaves[job.beg].lo, gHi = leaves[job.beg].hi;
-		for (size_t i = job.beg + 1; i < job.end; ++i) {
-			growMin(cLo, leaves[i].centroid);
-			growMax(cHi, leaves[i].centroid);
-			growMin(gLo, leaves[i].lo);
-			growMax(gHi, leaves[i].hi);
-		}
-		const float outerArea = halfArea(gLo, gHi);
-		// :124-129 split axis = widest centroid extent
-		const float ext[3] = {cHi[0] - cLo[0], cHi[1] - cLo[1], cHi[2] - cLo[2]};
-		int axis = ext[0] > ext[1] ? 0 : 1;
-		if (ext[2] > ext[axis]) {
-			axis = 2;
-		}
-		// :130-142 binning.  When every centroid coincides on the axis the quotient is 0/0 = NaN and the
-		// reference's size_t cast is undefined; defined here as bin 0 (the median fallback then applies).
-		Bin bins[kBins];
-		const float binWidth = ext[axis] / (float)kBins;
-		for (size_t i = job.beg; i < job.end; ++i) {
-			LeafRecord &l = leaves[i];
-			float q = (l.centroid[axis] - cLo[axis]) / binWidth;
-			q = (q < 0.5f) ? 0.5f : q;
-			q = (q > (float)kBins - 0.5f) ? (float)kBins - 0.5f : q;
-			l.bin = (q == q) ? (uint32_t)q : 0u;
-			Bin &b = bins[l.bin];
-			growMin(b.lo, l.lo);
-			growMax(b.hi, l.hi);
-			++b.count;
-		}
-		// :143-151 suffix unions: rightOf[i] = bins[i+1..]
-		Bin rightOf[kBins - 1];
-		{
-			Bin acc = bins[kBins - 1];
-			for (size_t i = kBins - 1; i > 0;) {
-				rightOf[--i] = acc;
-				acc.absorb(bins[i]);
-			}
-		}
-		// :152-171 cheapest of the 11 splits; an empty side costs 0 * inf = NaN and never wins
-		size_t bestSplit = 0;
-		Vec3 lLo{}, lHi{}, rLo{}, rHi{};
-		{
-			float bestCost = FLT_MAX;
-			Bin leftAcc;
-			for (size_t s = 0; s < kBins - 1; ++s) {
-				leftAcc.absorb(bins[s]);
-				const Bin &rightAcc = rightOf[s];
-				float cost = 0.125f + (leftAcc.cost() + rightAcc.cost()) / outerArea;
-				if (cost < bestCost) {
-					bestCost = cost;
-					bestSplit = s;
-					lLo = leftAcc.lo;
-					lHi = leftAcc.hi;
-					rLo = rightAcc.lo;
-					rHi = rightAcc.hi;
-				}
-			}
-		}
-		// :172-178 in-place partition, same swap sequence
-		size_t pivot = job.beg;
-		for (size_t i = job.beg; i < job.end; ++i) {
-			if (leaves[i].bin <= bestSplit) {
-				std::swap(leaves[i], leaves[pivot++]);
-			}
-		}
-		// :179-196 everything on one side: split at the median, recompute both boxes
-		if (pivot == job.beg || pivot == job.end) {
-			pivot = (job.beg + job.end) / 2;
-			lLo = leaves[job.beg].lo;
-			lHi = leaves[job.beg].hi;
-			for (size_t i = job.beg + 1; i < pivot; ++i) {
-				growMin(lLo, leaves[i].lo);
-				growMax(lHi, leaves[i].hi);
-			}
-			rLo = leaves[pivot].lo;
-			rHi = leaves[pivot].hi;
-			for (size_t i = pivot; i < job.end; ++i) {
-				growMin(rLo, leaves[i].lo);
-				growMax(rHi, leaves[i].hi);
-			}
-		}
-		// :198-207
 		int32_t id = nextNode++;
-		writeSlot(job.slot, id);
-		restir_aabb_node &n = nodes[id];
-		setBox(n.leftAabbMin, lLo);
-		setBox(n.leftAabbMax, lHi);
-		setBox(n.rightAabbMin, rLo);
-		setBox(n.rightAabbMax, rHi);
+		writeSlot(nodes, job.slot, id);
+		if (span == 2) {
+			pairNode(leaves, nodes, id, job.beg);
+			continue;
+		}
+		size_t pivot = splitRange(leaves, nodes, id, job.beg, job.end);
 		fifo.push_back(Job{(int64_t)id * 2, job.beg, pivot});
 		fifo.push_back(Job{(int64_t)id * 2 + 1, pivot, job.end});
+	}
+	return RESTIR_OK;
+}
+
+// The same tree, byte for byte, built level by level: the reference's queue is breadth-first, node ids are handed out in
+// queue order and a step touches only its own leaf range, its own node and one child slot of its parent, so all steps of
+// a level can run at once — on `n_threads` host threads here, and in the same formulation on a device (SURVEY.md §8f:
+// rebuild for dynamic geometry).  Inside a step everything stays sequential and in the reference's order: its min/max
+// (`a < b ? a : b`) is not commutative for signed zeros, and the partition is the reference's own swap sequence.
+extern "C" int restir_build_aabb_tree_mt(const void *triangles, uint32_t n_triangles, void *nodes_out, uint32_t n_threads) {
+	if (triangles == nullptr || nodes_out == nullptr || n_triangles < 2) {
+		return RESTIR_E_INVALID;
+	}
+	if (n_threads == 0) {
+		n_threads = std::max(1u, std::thread::hardware_concurrency());
+	}
+	restir_aabb_node *nodes = static_cast<restir_aabb_node *>(nodes_out);
+	std::memset(nodes, 0, sizeof(restir_aabb_node) * (size_t)(n_triangles - 1));
+	std::vector<LeafRecord> leaves;
+	makeLeaves(static_cast<const restir_triangle *>(triangles), n_triangles, leaves);
+
+	std::vector<Job> level{Job{-1, 0, n_triangles}}, next;
+	std::vector<int32_t> ids;     // node id of every step of the level that makes a node
+	std::vector<size_t> childAt;  // where a splitting step's two children go in the next level
+	std::vector<size_t> pivots;
+	int32_t nextNode = 0;
+	while (!level.empty()) {
+		// queue order fixes the node ids (alloc++ at :93 / :198) and the order of the next level (:208-209)
+		ids.assign(level.size(), -1);
+		childAt.assign(level.size(), 0);
+		size_t children = 0;
+		for (size_t j = 0; j < level.size(); ++j) {
+			const size_t span = level[j].end - level[j].beg;
+			if (span >= 2) {
+				ids[j] = nextNode++;
+			}
+			if (span > 2) {
+				childAt[j] = children;
+				children += 2;
+			}
+		}
+		next.assign(children, Job{0, 0, 0});
+		std::atomic<size_t> cursor{0};
+		// steps are handed out in queue order, a few at a time: one atomic per step would cost more than the small steps of
+		// the deep levels themselves
+		const size_t batch = std::max<size_t>(1, level.size() / ((size_t)n_threads * 8));
+		auto work = [&]() {
+			for (;;) {
+				const size_t first = cursor.fetch_add(batch, std::memory_order_relaxed);
+				if (first >= level.size()) {
+					return;
+				}
+				const size_t last = std::min(level.size(), first + batch);
+				for (size_t j = first; j < last; ++j) {
+					const Job &job = level[j];
+					const size_t span = job.end - job.beg;
+					if (span == 1) {
+						writeSlot(nodes, job.slot, ~leaves[job.beg].geom);
+						continue;
+					}
+					writeSlot(nodes, job.slot, ids[j]);
+					if (span == 2) {
+						pairNode(leaves, nodes, ids[j], job.beg);
+						continue;
+					}
+					size_t pivot = splitRange(leaves, nodes, ids[j], job.beg, job.end);
+					next[childAt[j]] = Job{(int64_t)ids[j] * 2, job.beg, pivot};
+					next[childAt[j] + 1] = Job{(int64_t)ids[j] * 2 + 1, pivot, job.end};
+				}
+			}
+		};
+		const size_t want = std::min<size_t>(n_threads, level.size());
+		if (want <= 1) {
+			work();
+		} else {
+			std::vector<std::thread> pool;
+			pool.reserve(want - 1);
+			for (size_t t = 1; t < want; ++t) {
+				pool.emplace_back(work);
+			}
+			work();
+			for (std::thread &t : pool) {
+				t.join();
+			}
+		}
+		level.swap(next);
 	}
 	return RESTIR_OK;
 }

@@ -87,3 +87,30 @@ def test_tree_is_well_formed():
 
 def test_builder_rejects_degenerate_input():
     assert capi.load_library().restir_build_aabb_tree(None, 0, None) != 0
+
+
+@pytest.mark.parametrize("name", ["procedural", "cornellBox", "sponza", "office"])
+def test_level_parallel_builder_gives_the_same_bytes(name):
+    """restir_build_aabb_tree_mt (one breadth-first level at a time, steps of a level on several threads) against the
+    sequential builder — which the tests above hold to the reference's own bytes — for 1, 2, 3 and all threads."""
+    import time
+
+    if name == "procedural":
+        scene = fixtures.make_procedural(seed=5, grid=30, boxes=200, lights="point")
+    else:
+        if not fixtures.baked_available(name):
+            pytest.skip(f"scenes/_baked/{name} not present")
+        scene = fixtures.load_baked(name, rebuild=False)
+    tris = scene.triangles
+    t0 = time.perf_counter()
+    want = capi.build_aabb_tree(tris)
+    t1 = time.perf_counter()
+    for threads in (1, 2, 3, 0):
+        t2 = time.perf_counter()
+        got = capi.build_aabb_tree_mt(tris, threads)
+        t3 = time.perf_counter()
+        assert np.array_equal(got, want), f"{name}: {threads} threads: {(got != want).any(axis=1).sum()} nodes differ"
+    print(f"{name}: {tris.shape[0]} triangles, sequential {1e3 * (t1 - t0):.1f} ms, all threads {1e3 * (t3 - t2):.1f} ms")
+    # degenerate input is refused the same way
+    with pytest.raises(capi.RestirError):
+        capi.build_aabb_tree_mt(tris[:1], 0)
