@@ -209,6 +209,11 @@ int restir_band_local_peer(restir_context *ctx, restir_band_peer *out);
 int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out);
 int restir_band_open_ipc(restir_context *ctx, const restir_band_ipc *in, restir_band_peer *out);
 int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *peer); /* peer == NULL: no neighbour on that side */
+/* Host helper: band boundaries of equal measured COST instead of equal height.  bounds_in / bounds_out: n_bands + 1
+ * ascending rows from 0 to height; seconds[r]: what band r took (its own kernels, restir_profile_end); every new band
+ * is at least min_rows high (>= the halo).  The frame time of a band split is the slowest band's. */
+int restir_band_balanced_bounds(uint32_t height, uint32_t n_bands, const uint32_t *bounds_in, const double *seconds, uint32_t min_rows,
+                                uint32_t *bounds_out);
 
 /* ---- counters --------------------------------------------------------------------------------- */
 

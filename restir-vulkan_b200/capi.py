@@ -67,7 +67,7 @@ EXPORTS = [
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
     "restir_generate_random_point_lights", "restir_create_alias_table", "restir_camera_matrix",
     "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math", "restir_band_local_peer", "restir_band_export_ipc",
-    "restir_band_open_ipc", "restir_band_connect",
+    "restir_band_open_ipc", "restir_band_connect", "restir_band_balanced_bounds",
 ]
 
 
@@ -180,6 +180,18 @@ def build_aabb_tree_mt(triangles, threads=0):
     if rc != 0:
         raise RestirError(f"restir_build_aabb_tree_mt failed ({rc})")
     return nodes
+
+
+def band_balanced_bounds(height, bounds, seconds, min_rows):
+    """restir_band_balanced_bounds (host): the C++ twin of bands.balanced_bounds."""
+    n = len(bounds) - 1
+    b_in = (C.c_uint32 * (n + 1))(*[int(b) for b in bounds])
+    secs = (C.c_double * n)(*[float(x) for x in seconds])
+    out = (C.c_uint32 * (n + 1))()
+    rc = load_library().restir_band_balanced_bounds(C.c_uint32(height), C.c_uint32(n), b_in, secs, C.c_uint32(min_rows), out)
+    if rc != 0:
+        raise RestirError(f"restir_band_balanced_bounds failed ({rc})")
+    return [int(v) for v in out]
 
 
 def check_aabb_tree(nodes, n_triangles):

@@ -463,3 +463,45 @@ extern "C" int restir_create_alias_table(const restir_point_light *point, uint64
 	}
 	return RESTIR_OK;
 }
+
+// Row-band boundaries of equal measured cost (no reference equivalent: the reference is single-GPU).  `seconds[r]` is
+// what band r = [bounds_in[r], bounds_in[r+1]) cost; the cost is taken as uniform inside a measured band and the new
+// boundaries cut its integral into n_bands equal parts, every band at least min_rows high (the halo must fit into a
+// neighbour's band).  Same arithmetic as restir-vulkan_b200/bands.py::balanced_bounds (the tests hold the two together).
+extern "C" int restir_band_balanced_bounds(uint32_t height, uint32_t n_bands, const uint32_t *bounds_in, const double *seconds,
+                                            uint32_t min_rows, uint32_t *bounds_out) {
+	if (n_bands == 0 || bounds_in == nullptr || seconds == nullptr || bounds_out == nullptr || bounds_in[0] != 0 || bounds_in[n_bands] != height ||
+	    (uint64_t)min_rows * n_bands > height) {
+		return RESTIR_E_INVALID;
+	}
+	std::vector<double> density(height);
+	for (uint32_t r = 0; r < n_bands; ++r) {
+		if (bounds_in[r + 1] <= bounds_in[r]) {
+			return RESTIR_E_INVALID;
+		}
+		const uint32_t rows = bounds_in[r + 1] - bounds_in[r];
+		const double d = std::max(seconds[r], 1e-9) / (double)rows;
+		for (uint32_t y = bounds_in[r]; y < bounds_in[r + 1]; ++y) {
+			density[y] = d;
+		}
+	}
+	double total = 0.0;
+	for (uint32_t y = 0; y < height; ++y) {
+		total += density[y];
+	}
+	bounds_out[0] = 0;
+	double acc = 0.0;
+	uint32_t y = 0;
+	for (uint32_t r = 1; r < n_bands; ++r) {
+		const double target = total * (double)r / (double)n_bands;
+		while (y < height && acc + density[y] <= target) {
+			acc += density[y];
+			++y;
+		}
+		const uint32_t lo = bounds_out[r - 1] + min_rows, hi = height - (n_bands - r) * min_rows;
+		bounds_out[r] = std::min(std::max(y, lo), hi);
+	}
+	bounds_out[n_bands] = height;
+	return RESTIR_OK;
+}
+

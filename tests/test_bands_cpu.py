@@ -138,3 +138,21 @@ def test_balanced_bounds_equalise_cost():
     # extreme skew: the minimum height wins
     skew = bands.balanced_bounds(h, world, equal, [100.0] + [0.001] * 7, 137)
     assert all(b - a >= 137 for a, b in zip(skew, skew[1:]))
+
+
+def test_cpp_balanced_bounds_equal_the_python_ones():
+    """restir_band_balanced_bounds (host C++, for C++ drivers of restir::BandSet) against bands.balanced_bounds."""
+    import parity_harness as ph
+
+    bands = __import__("restir_vulkan_b200.bands", fromlist=["bands"])
+    rng = np.random.default_rng(4)
+    for h, world, min_rows in [(4320, 8, 137), (1080, 2, 31), (2160, 3, 54), (8640, 8, 139), (64, 4, 16)]:
+        equal = [bands.band_rows(h, world, r)[0] for r in range(world)] + [h]
+        for _ in range(20):
+            secs = list(rng.uniform(0.2, 3.0, world))
+            want = bands.balanced_bounds(h, world, equal, secs, min_rows)
+            assert ph.capi.band_balanced_bounds(h, equal, secs, min_rows) == want
+            again = bands.balanced_bounds(h, world, want, secs[::-1], min_rows)      # from unequal bands too
+            assert ph.capi.band_balanced_bounds(h, want, secs[::-1], min_rows) == again
+    with pytest.raises(ph.capi.RestirError):
+        ph.capi.band_balanced_bounds(100, [0, 50, 100], [1.0, 1.0], 60)              # two bands of 60 rows do not fit
