@@ -32,6 +32,8 @@ extern "C" {
 #define RESTIR_E_CUDA (-2)     /* CUDA runtime error (sticky) */
 #define RESTIR_E_NOMEM (-3)
 #define RESTIR_E_UNSUPPORTED (-4)
+#define RESTIR_E_HALO (-5)     /* connected bands: a wait for a neighbour's halo rows timed out — every frame since is suspect (sticky until
+                                * the counters are reset) */
 
 typedef struct restir_context restir_context;
 
@@ -53,7 +55,8 @@ typedef struct restir_context restir_context;
 int restir_create(restir_context **out, int device, void *stream);
 void restir_destroy(restir_context *ctx);
 const char *restir_last_error(const restir_context *ctx);
-/* Replaces: waiting on _mainFence (src/app.cpp:771-773). */
+/* Replaces: waiting on _mainFence (src/app.cpp:771-773).  Returns RESTIR_E_HALO when a connected band gave up waiting for a
+ * neighbour's halo rows since the counters were last reset (restir_get_counters): the passes after that wait read stale rows. */
 int restir_synchronize(restir_context *ctx);
 
 /* ---- scene resources (set 0 / set 2 descriptors) ------------------------------------------------ */
@@ -162,7 +165,9 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
  *   unbiased != 0: restir(out=TEMP, prev=FRAME[i^1]) ; unbiased(in=TEMP, out=FRAME[i])
  *   unbiased == 0: restir(out=FRAME[i], prev=FRAME[i^1]) ; for j < spatial_iterations:
  *                  spatial(in=FRAME[i], out=FRAME[i^1], iter=2j) ; spatial(in=FRAME[i^1], out=FRAME[i], iter=2j+1)
- * Single-GPU contexts only (band contexts need halo exchanges between the passes; see restir_halo_*). */
+ * On a band context every band edge inside the screen must have its neighbour connected (restir_band_connect): the
+ * context then exchanges the halo rows itself between the passes; otherwise RESTIR_E_INVALID (drive the passes one by
+ * one and copy the halo rows through restir_reservoir_device_ptr instead). */
 int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations);
 
 /* ---- reservoir access (parity / replay / halo exchange) -------------------------------------- */
@@ -199,16 +204,21 @@ typedef struct restir_band_peer {
 	void *reservoirs[3];            /* the neighbour's three packed reservoir buffers, addressable from this process */
 	void *flags;                    /* the neighbour's counter block */
 	uint32_t alloc_begin, alloc_end; /* rows its buffers cover */
+	uint32_t row_begin, row_end;     /* rows it owns (shades and pushes): must cover this band's halo rows on that side */
 } restir_band_peer;
 typedef struct restir_band_ipc {
 	unsigned char reservoirs[3][64]; /* cudaIpcMemHandle_t */
 	unsigned char flags[64];
 	uint32_t alloc_begin, alloc_end;
+	uint32_t row_begin, row_end;
 } restir_band_ipc;
 int restir_band_local_peer(restir_context *ctx, restir_band_peer *out);
 int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out);
 int restir_band_open_ipc(restir_context *ctx, const restir_band_ipc *in, restir_band_peer *out);
-int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *peer); /* peer == NULL: no neighbour on that side */
+/* peer == NULL: no neighbour on that side.  RESTIR_E_INVALID when the neighbour's own rows do not cover this band's halo
+ * rows on that side (a halo taller than the neighbouring band would need a second hop, which is not made: those rows
+ * would silently stay empty) or when it holds none of this band's rows. */
+int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *peer);
 /* Host helper: band boundaries of equal measured COST instead of equal height.  bounds_in / bounds_out: n_bands + 1
  * ascending rows from 0 to height; seconds[r]: what band r took (its own kernels, restir_profile_end); every new band
  * is at least min_rows high (>= the halo).  The frame time of a band split is the slowest band's. */
@@ -227,7 +237,7 @@ typedef struct restir_counters {
 	                              * without one (neighbour rays of a pixel whose own ray is shadowed, unbiasedReuse.glsl:157-166;
 	                              * neighbour rays bit-identical to the neighbour's own ray) */
 } restir_counters;
-/* Synchronises the stream. */
+/* Synchronises the stream.  `out` is always filled; the return value is RESTIR_E_HALO when halo_wait_timeouts != 0. */
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset);
 
 /* Per-kernel device times (no reference equivalent: the reference has no GPU timestamps, only an FPS

@@ -130,18 +130,12 @@ def connect_neighbours(ctx, world, rank, dist, torch, group=None):
     """One process per GPU: hands every rank's reservoir buffers to its two neighbours as CUDA IPC mappings and
     connects them (restir_band_export_ipc / _open_ipc / _connect).  From then on the context exchanges halos itself
     with its own kernels over NVLink peer memory and BandRenderer issues no exchange.  torch.distributed only carries
-    the 264-byte handles, once."""
-    from .capi import BandIpc
-    import ctypes
-
-    blob = ctx.band_export_ipc()
-    n = ctypes.sizeof(BandIpc)
-    mine = torch.tensor(list(blob), dtype=torch.uint8, device=f"cuda:{ctx.device}")
-    everyone = [torch.zeros(n, dtype=torch.uint8, device=f"cuda:{ctx.device}") for _ in range(world)]
-    dist.all_gather(everyone, mine, group=group)
+    the 272-byte handles, once."""
+    everyone = [None] * world
+    dist.all_gather_object(everyone, ctx.band_export_ipc(), group=group)   # any backend: NCCL between GPUs, gloo in the one-GPU test
     for side, peer_rank in ((0, rank - 1), (1, rank + 1)):
         if 0 <= peer_rank < world:
-            ctx.band_connect(side, ctx.band_open_ipc(bytes(everyone[peer_rank].cpu().tolist())))
+            ctx.band_connect(side, ctx.band_open_ipc(everyone[peer_rank]))
         else:
             ctx.band_connect(side, None)
     dist.barrier(group=group)   # nobody starts pushing before everybody has connected
@@ -200,3 +194,14 @@ class BandRenderer:
                 self._exchange(p)
                 ctx.pass_spatial(i, p, i, 2 * j + 1)
         self._exchange(i)   # next frame's temporal reprojection reads FRAME[i] within the halo
+
+
+def mismatching_owned_reservoirs(band_ctx, whole_ctx, buffer, torch):
+    """How many of the reservoirs this band OWNS in `buffer` differ, in any bit of their packed 32 bytes, from the same
+    pixels of a context that rendered the whole screen (same device).  Compared on the device."""
+    row_begin, row_end, alloc_begin, _ = band_ctx.band()
+    mine = reservoir_rows_tensor(band_ctx, buffer, torch)[row_begin - alloc_begin: row_end - alloc_begin]
+    whole = reservoir_rows_tensor(whole_ctx, buffer, torch)[row_begin: row_end]
+    differs = (mine.view(mine.shape[0], -1, 32) != whole.view(whole.shape[0], -1, 32)).any(dim=-1)
+    return int(differs.sum().item())
+

@@ -16,6 +16,7 @@ RESTIR_BUF_FRAME0, RESTIR_BUF_FRAME1, RESTIR_BUF_TEMP = 0, 1, 2
 RESTIR_OUT_RGBA32F, RESTIR_OUT_RGBA8_SRGB = 0, 1
 RESTIR_VISIBILITY_REUSE_FLAG, RESTIR_TEMPORAL_REUSE_FLAG = 1, 2
 RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_IMAGE = 0, 1, 2
+RESTIR_E_INVALID, RESTIR_E_CUDA, RESTIR_E_NOMEM, RESTIR_E_UNSUPPORTED, RESTIR_E_HALO = -1, -2, -3, -4, -5
 
 RESERVOIR_DTYPE = np.dtype(
     [
@@ -73,12 +74,14 @@ EXPORTS = [
 
 class BandPeer(C.Structure):
     """restir_band_peer: a neighbour's reservoir buffers and counter block, addressable from this process."""
-    _fields_ = [("reservoirs", C.c_void_p * 3), ("flags", C.c_void_p), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32)]
+    _fields_ = [("reservoirs", C.c_void_p * 3), ("flags", C.c_void_p), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32),
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
 
 
 class BandIpc(C.Structure):
     """restir_band_ipc: the same as CUDA IPC handles, to be shipped to the neighbour's process."""
-    _fields_ = [("reservoirs", (C.c_ubyte * 64) * 3), ("flags", C.c_ubyte * 64), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32)]
+    _fields_ = [("reservoirs", (C.c_ubyte * 64) * 3), ("flags", C.c_ubyte * 64), ("alloc_begin", C.c_uint32), ("alloc_end", C.c_uint32),
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
 
 
 class GBufferPlanes(C.Structure):
@@ -415,7 +418,7 @@ class RestirContext:
         return peer
 
     def band_export_ipc(self):
-        """The 264 bytes a neighbour process needs (bytes object)."""
+        """The 272 bytes a neighbour process needs (bytes object)."""
         ipc = BandIpc()
         self._check(self.lib.restir_band_export_ipc(self._ctx, C.byref(ipc)))
         return bytes(ipc)
@@ -433,9 +436,12 @@ class RestirContext:
     def trace_segments(self, p1, p2, n, shadowed):
         self._check(self.lib.restir_trace_segments(self._ctx, _dp(p1), _dp(p2), C.c_uint64(n), _dp(shadowed)))
 
-    def counters(self, reset=False):
+    def counters(self, reset=False, check=True):
+        """check=False: return the counters even when halo_wait_timeouts != 0 (the call then reports RESTIR_E_HALO)."""
         c = Counters()
-        self._check(self.lib.restir_get_counters(self._ctx, C.byref(c), C.c_int(1 if reset else 0)))
+        rc = self.lib.restir_get_counters(self._ctx, C.byref(c), C.c_int(1 if reset else 0))
+        if rc != RESTIR_E_HALO or check:
+            self._check(rc)
         return {"shadow_rays": c.shadow_rays, "stack_overflows": c.stack_overflows, "halo_misses": c.halo_misses,
                 "kernel_launches": c.kernel_launches, "shadow_rays_traced": c.shadow_rays_traced,
                 "halo_wait_timeouts": c.halo_wait_timeouts}

@@ -29,7 +29,8 @@ struct restir_context {
 	// scene
 	float4 *nodes = nullptr, *tris = nullptr;
 	float4 *image = nullptr; // 64-byte image of `nodes` (traversal_image.h); null => literal 80-byte walk
-	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `tris`: what the trace kernel walks
+	float4 *triEdges = nullptr; // 64-byte (p1, e1, e2) records of `tris` (restir_trace.cuh)
+	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `triEdges`: what the trace kernel walks
 	size_t treeBlockBytes = 0;
 	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
@@ -63,7 +64,7 @@ struct restir_context {
 		bool connected = false;
 		PackedReservoir *reservoirs[3] = {nullptr, nullptr, nullptr};
 		unsigned long long *flags = nullptr;
-		int allocBegin = 0, allocEnd = 0;
+		int allocBegin = 0, allocEnd = 0, rowBegin = 0, rowEnd = 0;
 	} peers[2];
 	unsigned long long *bandFlags = nullptr; // device, [side the push came from][buffer]: raised by the neighbours
 	unsigned *haloTicket = nullptr;
@@ -346,6 +347,7 @@ TraceParams traceParams(const restir_context *ctx) {
 	tp.nodes = ctx->nodes;
 	tp.tris = ctx->tris;
 	tp.image = ctx->image;
+	tp.triEdges = ctx->triEdges;
 	tp.band = ctx->band;
 	tp.shadowed = ctx->shadowed;
 	tp.counters = ctx->counters;
@@ -432,7 +434,8 @@ void restir_destroy(restir_context *ctx) {
 	dropGBuffers(ctx);
 	dropProfile(ctx);
 	freeDev(ctx->nodes);
-	freeDev(ctx->treeBlock); // image + tris
+	freeDev(ctx->tris);
+	freeDev(ctx->treeBlock); // image + triEdges
 	freeDev(ctx->shadowed);
 	freeDev(ctx->neighborPix);
 	freeDev(ctx->pointBlob);
@@ -460,6 +463,13 @@ int restir_synchronize(restir_context *ctx) {
 		CU(ctx, cudaStreamSynchronize(ctx->copyStream));
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	if (bandConnected(ctx)) {
+		unsigned long long timeouts = 0;
+		CU(ctx, cudaMemcpy(&timeouts, ctx->counters + kCounterHaloTimeout, sizeof(timeouts), cudaMemcpyDeviceToHost));
+		if (timeouts != 0) {
+			return fail(ctx, RESTIR_E_HALO, "%llu wait(s) for a neighbour's halo rows timed out: the passes after them read stale rows", timeouts);
+		}
+	}
 	return RESTIR_OK;
 }
 
@@ -478,21 +488,27 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	freeDev(ctx->nodes);
+	freeDev(ctx->tris);
 	freeDev(ctx->treeBlock);
-	ctx->tris = ctx->image = nullptr;
+	ctx->image = ctx->triEdges = nullptr;
 	ctx->nNodes = ctx->nTris = 0;
 	const bool useImage = info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
-	const size_t imageBytes = useImage ? ((image.size() * sizeof(Node64) + 255) & ~(size_t)255) : 0;
 	const size_t triBytes = (size_t)n_triangles * sizeof(restir_triangle);
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
-	CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + triBytes));
-	ctx->treeBlockBytes = imageBytes + triBytes;
-	ctx->tris = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
+	CU(ctx, cudaMalloc(&ctx->tris, triBytes));
 	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
 	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, triBytes, cudaMemcpyHostToDevice, ctx->stream));
 	if (useImage) {
+		// what the trace kernel walks, in one allocation: the 64-byte nodes, then the 64-byte (p1, e1, e2) triangle records
+		const size_t imageBytes = (image.size() * sizeof(Node64) + 255) & ~(size_t)255;
+		const size_t edgeBytes = (size_t)n_triangles * 64;
+		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes));
+		ctx->treeBlockBytes = imageBytes + edgeBytes;
 		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
+		ctx->triEdges = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
 		CU(ctx, cudaMemcpyAsync(ctx->image, image.data(), image.size() * sizeof(Node64), cudaMemcpyHostToDevice, ctx->stream));
+		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, ctx->stream);
+		CU(ctx, cudaGetLastError());
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->nNodes = n_nodes;
@@ -528,7 +544,15 @@ int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t poi
 	if ((rc = uploadBlob(ctx, alias_blob, alias_bytes, sizeof(restir_alias_column), ctx->aliasBlob, ctx->aliasCount, "alias-table")) != RESTIR_OK) return rc;
 	int lights = ctx->pointCount != 0 ? ctx->pointCount : ctx->triCount; // restirOmni.glsl:116 picks the list the same way
 	if (ctx->aliasCount == 0 || ctx->aliasCount != lights) {
-		return fail(ctx, RESTIR_E_INVALID, "alias table has %d columns for %d lights", ctx->aliasCount, lights);
+		const int columns = ctx->aliasCount;
+		freeDev(ctx->aliasBlob); // no pass may run on mismatched tables (makeParams checks the alias blob)
+		ctx->aliasCount = 0;
+		return fail(ctx, RESTIR_E_INVALID, "alias table has %d columns for %d lights", columns, lights);
+	}
+	// a stored reservoir names its light by index and its normal / emission are re-read from the tables (PackedReservoir):
+	// history sampled from the previous tables means nothing under the new ones (and could index past them)
+	for (auto &r : ctx->reservoirs) {
+		if (r) CU(ctx, cudaMemsetAsync(r, 0, ctx->allocPixels() * sizeof(PackedReservoir), ctx->stream));
 	}
 	freeDev(ctx->pointPosLum);
 	freeDev(ctx->triAux);
@@ -688,6 +712,9 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count) {
 		return fail(ctx, RESTIR_E_INVALID, "unbiased neighbour count must be in 1..16");
 	}
 	ctx->unbiasedNeighbors = count;
+	if (bandConnected(ctx)) { // see restir_band_connect
+		return ensureHandOver(ctx, pass_grid(ctx->band), count + 1, count);
+	}
 	return RESTIR_OK;
 }
 
@@ -731,6 +758,8 @@ int restir_band_local_peer(restir_context *ctx, restir_band_peer *out) {
 	out->flags = ctx->bandFlags;
 	out->alloc_begin = (uint32_t)ctx->band.allocBegin;
 	out->alloc_end = (uint32_t)ctx->band.allocEnd;
+	out->row_begin = (uint32_t)ctx->band.rowBegin;
+	out->row_end = (uint32_t)ctx->band.rowEnd;
 	return RESTIR_OK;
 }
 
@@ -751,6 +780,8 @@ int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out) {
 	std::memcpy(out->flags, &h, 64);
 	out->alloc_begin = (uint32_t)ctx->band.allocBegin;
 	out->alloc_end = (uint32_t)ctx->band.allocEnd;
+	out->row_begin = (uint32_t)ctx->band.rowBegin;
+	out->row_end = (uint32_t)ctx->band.rowEnd;
 	return RESTIR_OK;
 }
 
@@ -770,6 +801,8 @@ int restir_band_open_ipc(restir_context *ctx, const restir_band_ipc *in, restir_
 	}
 	out->alloc_begin = in->alloc_begin;
 	out->alloc_end = in->alloc_end;
+	out->row_begin = in->row_begin;
+	out->row_end = in->row_end;
 	return RESTIR_OK;
 }
 
@@ -793,12 +826,27 @@ int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *p
 		return fail(ctx, RESTIR_E_INVALID, "restir_band_connect: peer rows [%u,%u) do not overlap this band's edge on side %d", peer->alloc_begin,
 		            peer->alloc_end, side);
 	}
+	// ... and own every halo row this band keeps on that side: a neighbour pushes only rows it shades itself, so rows of a
+	// band two hops away would stay at their zero fill and be gathered as empty reservoirs without any halo_miss
+	const bool covers = side == 0 ? ((int)peer->row_end == ctx->band.rowBegin && (int)peer->row_begin <= ctx->band.allocBegin)
+	                              : ((int)peer->row_begin == ctx->band.rowEnd && (int)peer->row_end >= ctx->band.allocEnd);
+	if (!covers) {
+		return fail(ctx, RESTIR_E_INVALID,
+		            "restir_band_connect: the neighbour on side %d owns rows [%u,%u), which do not cover this band's halo rows [%d,%d): the halo must "
+		            "not be taller than the neighbouring band",
+		            side, peer->row_begin, peer->row_end, side == 0 ? ctx->band.allocBegin : ctx->band.rowEnd,
+		            side == 0 ? ctx->band.rowBegin : ctx->band.allocEnd);
+	}
 	for (int b = 0; b < 3; ++b) p.reservoirs[b] = static_cast<PackedReservoir *>(peer->reservoirs[b]);
 	p.flags = static_cast<unsigned long long *>(peer->flags);
 	p.allocBegin = (int)peer->alloc_begin;
 	p.allocEnd = (int)peer->alloc_end;
+	p.rowBegin = (int)peer->row_begin;
+	p.rowEnd = (int)peer->row_end;
 	p.connected = true;
-	return RESTIR_OK;
+	// the hand-over buffers of the cut passes are sized now: growing them later would synchronise this stream in the middle of
+	// a frame, possibly behind a wait for a neighbour that the same host thread has not driven yet
+	return ensureHandOver(ctx, pass_grid(ctx->band), ctx->unbiasedNeighbors + 1, ctx->unbiasedNeighbors);
 }
 
 int restir_set_ray_elision(restir_context *ctx, int enable) {
@@ -1106,6 +1154,9 @@ int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
 	if (reset) {
 		CU(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(h), ctx->stream));
 		ctx->launches = 0;
+	}
+	if (h[kCounterHaloTimeout] != 0) {
+		return fail(ctx, RESTIR_E_HALO, "%llu wait(s) for a neighbour's halo rows timed out: the passes after them read stale rows", h[kCounterHaloTimeout]);
 	}
 	return RESTIR_OK;
 }

@@ -210,6 +210,16 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 #ifndef RESTIR_TRACE_MIN_BLOCKS
 #define RESTIR_TRACE_MIN_BLOCKS 5
 #endif
+// RESTIR_TRACE_REFILL = T > 0 (experiment, off): a warp does not wait for its last rays.  When T or fewer lanes are still
+// walking, the idle lanes take the next rays of the sorted chunk (which start at the root together and are aimed at the
+// same light) while the survivors keep their lanes and their stacks.  T = 0 (default): lockstep batches of 32.
+// Measured (profiles/r2_a_trace_ab.md): T = 4 / 8 / 16 / 24 give 3.78 / 3.74 / 3.73 / 3.73 ms per frame against 3.46 in
+// lockstep — restirOmni's rays (11 of 32 lanes in lockstep) gain 10 % between T = 4 and T = 24, but the neighbour rays
+// lose as much (survivors deep in the tree next to fresh rays at the root: more distinct node loads per instruction) and
+// the loop that can resume a walk costs 20 % over the one that cannot.
+#ifndef RESTIR_TRACE_REFILL
+#define RESTIR_TRACE_REFILL 0
+#endif
 template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
 	constexpr int CHUNK = ChunkOf<MODE>::value;
 	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
@@ -217,6 +227,7 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 	unsigned *keys = allKeys[threadIdx.x >> 5];
 	const unsigned full = 0xffffffffu;
 	unsigned rays = 0, answered = 0, overflow = 0;
+	const float4 *const walkTris = RESTIR_TRACE_TRI_EDGES ? tp.triEdges : tp.tris;
 
 	for (;;) {
 		unsigned base = 0;
@@ -227,30 +238,81 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 		if (base >= tp.nItems) {
 			break;
 		}
+		unsigned valid = 0;
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned local = r * 32u + lane;
-			keys[local] = item_key<MODE>(tp, base + local, local, answered);
+			unsigned key = item_key<MODE>(tp, base + local, local, answered);
+			keys[local] = key;
+			valid += __popc(__ballot_sync(full, key != kInvalidKey));
 		}
 		__syncwarp();
-		if (MODE != kTraceSegments && RESTIR_TRACE_SORT) {
-			warp_sort<CHUNK>(keys, lane);
+		if (valid == 0) {
+			continue;
 		}
-#pragma unroll 1
-		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
-			unsigned key = keys[r * 32u + lane];
-			if (__ballot_sync(full, key != kInvalidKey) == 0u) {
-				if (MODE != kTraceSegments && RESTIR_TRACE_SORT) break; // sorted: only holes follow
-				continue;
+		constexpr bool kSorted = MODE != kTraceSegments && RESTIR_TRACE_SORT;
+		if (kSorted) {
+			warp_sort<CHUNK>(keys, lane); // holes (kInvalidKey) end up behind the `valid` rays
+		}
+		if (IMAGE && RESTIR_TRACE_REFILL > 0) {
+			// rays of the chunk in key order; in an unsorted chunk holes are skipped as they come
+			const unsigned count = kSorted ? valid : (unsigned)CHUNK;
+			unsigned next = 0;
+			bool walking = false;
+			size_t out = 0;
+			WalkRay ray;
+			int stack[32];
+			int top = 0, cur = 0;
+			for (;;) {
+				unsigned act = __ballot_sync(full, walking);
+				if ((unsigned)__popc(act) <= (unsigned)RESTIR_TRACE_REFILL && next < count) {
+					unsigned idle = ~act;
+					unsigned mine = next + (unsigned)__popc(idle & ((1u << lane) - 1u));
+					if (!walking && mine < count) {
+						unsigned key = keys[mine];
+						if (key != kInvalidKey) {
+							f3 p1, p2, o, d;
+							out = item_segment<MODE>(tp, base + (key & 255u), p1, p2);
+							segment_setup(p1, p2, o, d);
+							ray = walk_ray(o, d);
+							top = 0;
+							cur = 0;
+							walking = true;
+							rays++;
+						}
+					}
+					next += (unsigned)__popc(idle);
+					act = __ballot_sync(full, walking);
+				}
+				if (act == 0u) {
+					if (next >= count) break;
+					continue;
+				}
+				if (walking) {
+					int st = walk_step(tp.image, walkTris, ray, cur, top, stack);
+					if (st != kWalkOn) {
+						tp.shadowed[out] = st == kWalkHit ? 1 : 0;
+						walking = false;
+					}
+				}
 			}
-			if (key != kInvalidKey) {
-				unsigned item = base + (key & 255u);
-				f3 p1, p2, o, d;
-				size_t out = item_segment<MODE>(tp, item, p1, p2);
-				segment_setup(p1, p2, o, d);
-				bool clear = IMAGE ? trace_any_image(tp.image, tp.tris, o, d) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
-				tp.shadowed[out] = clear ? 0 : 1;
-				rays++;
+		} else {
+#pragma unroll 1
+			for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
+				unsigned key = keys[r * 32u + lane];
+				if (__ballot_sync(full, key != kInvalidKey) == 0u) {
+					if (kSorted) break; // sorted: only holes follow
+					continue;
+				}
+				if (key != kInvalidKey) {
+					unsigned item = base + (key & 255u);
+					f3 p1, p2, o, d;
+					size_t out = item_segment<MODE>(tp, item, p1, p2);
+					segment_setup(p1, p2, o, d);
+					bool clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
+					tp.shadowed[out] = clear ? 0 : 1;
+					rays++;
+				}
 			}
 		}
 		__syncwarp();

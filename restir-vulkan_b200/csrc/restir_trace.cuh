@@ -115,64 +115,132 @@ __device__ __forceinline__ bool test_visibility_reference(const SceneView &sc, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same walk over the 64-byte image of the same tree (traversal_image.h): two 32-byte loads per node
-// from one 128-byte line.  Only used when the tree's worst-case stack occupancy is <= 32 (checked at upload),
-// so no push can be dropped and the stack needs no bound checks; the node about to be visited stays in a
-// register instead of going through the stack.  Order of visits and triangle tests is the reference's: left
-// box, right box, then the right child before the left one.  Returns true when nothing is hit.
+// The walk over the 64-byte image of the same tree (traversal_image.h): two 32-byte loads per node from one
+// 128-byte line.  Only used when the tree is no deeper than the 32-entry stack (checked at upload), so no push
+// can be dropped and the stack needs no bound checks; the node about to be visited stays in a register instead
+// of going through the stack.
+//
+// What is fixed by the reference (softwareRaytracing.glsl:39-85) is WHICH boxes and triangles a segment is tested
+// against — a triangle is tested iff every box on the path from the root to its leaf is hit, with the reference's
+// slab and Moller-Trumbore arithmetic — not the ORDER: the answer is any-hit.  Two exact choices, both measured
+// (profiles/r2_a_trace_ab.md, B200, Sponza 1080p unbiased 5):
+//   RESTIR_TRACE_NEAR_FIRST 0 (default): of two hit inner children the right one is visited first, the reference's
+//     pop order.  1: the one the segment enters first (smaller slab entry parameter, already computed).  Near-first
+//     LOSES here (3.43 -> 3.49 ms/frame): a batch of 32 rays ends with its slowest ray, and the unshadowed rays of a
+//     batch visit the same nodes in any order, while lanes that pick their own order stop sharing node loads (the
+//     kernel is bound by L1 tag lookups).
+//   RESTIR_TRACE_TRI_EDGES 1 (default): triangles are read as (p1, e1 = p2 - p1, e2 = p3 - p1) from 64-byte records
+//     derived at upload with the very subtractions softwareRaytracing.glsl:16-17 makes per test (same operands, same
+//     IEEE operation => same bits): one 32-byte + one 4-byte load from one line and six subtractions less per test
+//     (restirOmni's rays, where triangle tests are 28 % of the instructions: 0.630 -> 0.615 ms).
+#ifndef RESTIR_TRACE_NEAR_FIRST
+#define RESTIR_TRACE_NEAR_FIRST 0
+#endif
+#ifndef RESTIR_TRACE_TRI_EDGES
+#define RESTIR_TRACE_TRI_EDGES 1
+#endif
+
+// softwareRaytracing.glsl:15-37 on a derived (p1, e1, e2) record
+__device__ __forceinline__ bool ray_triangle_edges(const float4 *__restrict__ triEdges, int id, f3 o, f3 d) {
+	const float4 *t = triEdges + (size_t)id * 4;
+	F8 a = ldg256(t);
+	float e2z = __ldg(reinterpret_cast<const float *>(t + 2));
+	f3 p1 = mk3(a.v[0], a.v[1], a.v[2]);
+	f3 e1 = mk3(a.v[3], a.v[4], a.v[5]);
+	f3 e2 = mk3(a.v[6], a.v[7], e2z);
+	f3 p = cross3(d, e2);
+	float f = 1.0f / dot3(e1, p);
+	f3 s = o - p1;
+	float baryX = f * dot3(s, p);
+	if (baryX < 0.0f || baryX > 1.0f) {
+		return false;
+	}
+	f3 q = cross3(s, e1);
+	float baryY = f * dot3(d, q);
+	if (baryY < 0.0f || baryY + baryX > 1.0f) {
+		return false;
+	}
+	f = f * dot3(e2, q);
+	return f > 0.0f && f < 1.0f;
+}
+
+// Per-ray constants of the packed slab test: (b - o) * inv as FADD2 (b + (-o), the same IEEE operation) and FMUL2,
+// the left box in the low half and the right box in the high half of every pair.
+struct WalkRay {
+	f3 o, d;
+	float2 nox, noy, noz, ivx, ivy, ivz;
+};
+__device__ __forceinline__ WalkRay walk_ray(f3 o, f3 d) {
+	WalkRay r;
+	r.o = o;
+	r.d = d;
+	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	r.nox = make_float2(-o.x, -o.x); r.noy = make_float2(-o.y, -o.y); r.noz = make_float2(-o.z, -o.z);
+	r.ivx = make_float2(inv.x, inv.x); r.ivy = make_float2(inv.y, inv.y); r.ivz = make_float2(inv.z, inv.z);
+	return r;
+}
+
+enum WalkStatus { kWalkOn = 0, kWalkClear = 1, kWalkHit = 2 };
+
+// One node visit: both boxes, hit leaves, then the next node (or the end of the walk).
+__device__ __forceinline__ int walk_step(const float4 *__restrict__ image, const float4 *__restrict__ tris, const WalkRay &r, int &cur, int &top, int *stack) {
+	const float4 *n = image + (unsigned)cur * 4u;
+	F8 lo = ldg256(n), hi = ldg256(n + 2);
+	float4 qx = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]), qy = make_float4(lo.v[4], lo.v[5], lo.v[6], lo.v[7]);
+	float4 qz = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
+	int2 ch = make_int2(__float_as_int(hi.v[4]), __float_as_int(hi.v[5]));
+	float2 t1x = __fmul2_rn(__fadd2_rn(make_float2(qx.x, qx.y), r.nox), r.ivx), t2x = __fmul2_rn(__fadd2_rn(make_float2(qx.z, qx.w), r.nox), r.ivx);
+	float2 t1y = __fmul2_rn(__fadd2_rn(make_float2(qy.x, qy.y), r.noy), r.ivy), t2y = __fmul2_rn(__fadd2_rn(make_float2(qy.z, qy.w), r.noy), r.ivy);
+	float2 t1z = __fmul2_rn(__fadd2_rn(make_float2(qz.x, qz.y), r.noz), r.ivz), t2z = __fmul2_rn(__fadd2_rn(make_float2(qz.z, qz.w), r.noz), r.ivz);
+	// softwareRaytracing.glsl:11-13 per box
+	float lmin = fmaxf(fminf(t1x.x, t2x.x), fmaxf(fminf(t1y.x, t2y.x), fminf(t1z.x, t2z.x)));
+	float lmax = fminf(fmaxf(t1x.x, t2x.x), fminf(fmaxf(t1y.x, t2y.x), fmaxf(t1z.x, t2z.x)));
+	float rmin = fmaxf(fminf(t1x.y, t2x.y), fmaxf(fminf(t1y.y, t2y.y), fminf(t1z.y, t2z.y)));
+	float rmax = fminf(fmaxf(t1x.y, t2x.y), fminf(fmaxf(t1y.y, t2y.y), fmaxf(t1z.y, t2z.y)));
+	bool hl = lmin < 1.0f && lmax >= lmin && lmax > 0.0f;
+	bool hr = rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
+	// hit leaves: left first, then right (most visits have none: one branch skips the whole block)
+	int t0 = (hl && ch.x < 0) ? ~ch.x : -1, t1 = (hr && ch.y < 0) ? ~ch.y : -1;
+	if ((t0 & t1) >= 0) { // at least one of them is a triangle index
+		if (t0 < 0) {
+			t0 = t1;
+			t1 = -1;
+		}
+#pragma unroll 1
+		do {
+			if (RESTIR_TRACE_TRI_EDGES ? ray_triangle_edges(tris, t0, r.o, r.d) : ray_triangle(tris, t0, r.o, r.d)) {
+				return kWalkHit;
+			}
+			t0 = t1;
+			t1 = -1;
+		} while (t0 >= 0);
+	}
+	bool il = hl && ch.x >= 0, ir = hr && ch.y >= 0;
+	if (il && ir) {
+		// both inner children hit: one is visited now, the other pushed
+		bool leftFirst = RESTIR_TRACE_NEAR_FIRST ? lmin < rmin : false;
+		stack[top++] = leftFirst ? ch.y : ch.x;
+		cur = leftFirst ? ch.x : ch.y;
+	} else if (il || ir) {
+		cur = il ? ch.x : ch.y;
+	} else {
+		if (top == 0) {
+			return kWalkClear;
+		}
+		cur = stack[--top];
+	}
+	return kWalkOn;
+}
+
+// Returns true when nothing is hit.
 __device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image, const float4 *__restrict__ tris, f3 o, f3 d) {
 	int stack[32];
 	int top = 0, cur = 0;
-	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-	// both boxes of a node at once: (b - o) * inv as FADD2 (b + (-o), the same IEEE operation) and FMUL2, the
-	// left box in the low half and the right box in the high half of every pair
-	const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
-	const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+	const WalkRay r = walk_ray(o, d);
 	for (;;) {
-		const float4 *n = image + (unsigned)cur * 4u;
-		F8 lo = ldg256(n), hi = ldg256(n + 2);
-		float4 qx = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]), qy = make_float4(lo.v[4], lo.v[5], lo.v[6], lo.v[7]);
-		float4 qz = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
-		int2 ch = make_int2(__float_as_int(hi.v[4]), __float_as_int(hi.v[5]));
-		float2 t1x = __fmul2_rn(__fadd2_rn(make_float2(qx.x, qx.y), nox), ivx), t2x = __fmul2_rn(__fadd2_rn(make_float2(qx.z, qx.w), nox), ivx);
-		float2 t1y = __fmul2_rn(__fadd2_rn(make_float2(qy.x, qy.y), noy), ivy), t2y = __fmul2_rn(__fadd2_rn(make_float2(qy.z, qy.w), noy), ivy);
-		float2 t1z = __fmul2_rn(__fadd2_rn(make_float2(qz.x, qz.y), noz), ivz), t2z = __fmul2_rn(__fadd2_rn(make_float2(qz.z, qz.w), noz), ivz);
-		// softwareRaytracing.glsl:11-13 per box
-		float lmin = fmaxf(fminf(t1x.x, t2x.x), fmaxf(fminf(t1y.x, t2y.x), fminf(t1z.x, t2z.x)));
-		float lmax = fminf(fmaxf(t1x.x, t2x.x), fminf(fmaxf(t1y.x, t2y.x), fmaxf(t1z.x, t2z.x)));
-		float rmin = fmaxf(fminf(t1x.y, t2x.y), fmaxf(fminf(t1y.y, t2y.y), fminf(t1z.y, t2z.y)));
-		float rmax = fminf(fmaxf(t1x.y, t2x.y), fminf(fmaxf(t1y.y, t2y.y), fmaxf(t1z.y, t2z.y)));
-		bool hl = lmin < 1.0f && lmax >= lmin && lmax > 0.0f;
-		bool hr = rmin < 1.0f && rmax >= rmin && rmax > 0.0f;
-		// hit leaves: left first, then right (most visits have none: one branch skips the whole block)
-		int t0 = (hl && ch.x < 0) ? ~ch.x : -1, t1 = (hr && ch.y < 0) ? ~ch.y : -1;
-		if ((t0 & t1) >= 0) { // at least one of them is a triangle index
-			if (t0 < 0) {
-				t0 = t1;
-				t1 = -1;
-			}
-#pragma unroll 1
-			do {
-				if (ray_triangle(tris, t0, o, d)) {
-					return false;
-				}
-				t0 = t1;
-				t1 = -1;
-			} while (t0 >= 0);
-		}
-		bool il = hl && ch.x >= 0, ir = hr && ch.y >= 0;
-		if (ir) {
-			if (il) {
-				stack[top++] = ch.x;
-			}
-			cur = ch.y;
-		} else if (il) {
-			cur = ch.x;
-		} else {
-			if (top == 0) {
-				return true;
-			}
-			cur = stack[--top];
+		int st = walk_step(image, tris, r, cur, top, stack);
+		if (st != kWalkOn) {
+			return st == kWalkClear;
 		}
 	}
 }

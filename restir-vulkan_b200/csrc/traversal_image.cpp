@@ -66,8 +66,21 @@ bool build_traversal_image(const restir_aabb_node *nodes, uint32_t nNodes, uint3
 		need[order[k]] = v;
 	}
 	info.referenceStackBound = std::max(1, need[0]);
-	if (info.referenceStackBound > 32) {
-		std::snprintf(msg, sizeof(msg), "the reference's 32-entry stack can overflow on this tree (worst case %d entries)", info.referenceStackBound);
+	// a walk that picks the order per visit (restir_trace.cuh, near child first) holds at most one pending sibling
+	// per node on the path to the current one
+	std::vector<int32_t> needAny(nNodes, 0);
+	for (size_t k = order.size(); k-- > 0;) {
+		const restir_aabb_node &n = nodes[order[k]];
+		int li = n.leftChild >= 0, ri = n.rightChild >= 0;
+		int v = 0;
+		if (ri) v = std::max(v, li + needAny[n.rightChild]);
+		if (li) v = std::max(v, ri + needAny[n.leftChild]);
+		needAny[order[k]] = v;
+	}
+	info.anyOrderStackBound = std::max(1, needAny[0]);
+	if (info.referenceStackBound > 32 || info.anyOrderStackBound > 32) {
+		std::snprintf(msg, sizeof(msg), "the reference's 32-entry stack can overflow on this tree (worst case %d entries, %d in any visiting order)", info.referenceStackBound,
+		              info.anyOrderStackBound);
 		info.why = msg;
 		return true; // usable stays false
 	}

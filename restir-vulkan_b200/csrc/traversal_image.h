@@ -35,6 +35,7 @@ struct TraversalImageInfo {
 	bool usable = false;         // false: keep the literal reference traversal (reason in `why`)
 	std::string why;
 	int referenceStackBound = 0; // worst-case occupancy of the reference's stack (all boxes hit)
+	int anyOrderStackBound = 0;  // the same for a walk that may visit the two children of a node in either order
 	int depth = 0;               // level of the deepest leaf (root node = level 0)
 	uint32_t reachableNodes = 0;
 };

@@ -228,6 +228,14 @@ public:
 			throw Error(RESTIR_E_INVALID, "BandSet: bounds must run from 0 to height, one band per device");
 		}
 		for (size_t r = 0; r < devices.size(); ++r) {
+			// a neighbour pushes only the rows it shades itself: a halo taller than a band would leave the rows of the band
+			// two hops away empty (restir_band_connect rejects it too)
+			if (devices.size() > 1 && (bounds[r + 1] <= bounds[r] || bounds[r + 1] - bounds[r] < halo)) {
+				throw Error(RESTIR_E_INVALID, "BandSet: band " + std::to_string(r) + " has " + std::to_string(bounds[r + 1] - bounds[r]) +
+				                                  " rows, fewer than the " + std::to_string(halo) + "-row halo");
+			}
+		}
+		for (size_t r = 0; r < devices.size(); ++r) {
 			devices[r]->check(restir_resize_band(devices[r]->get(), width, height, bounds[r], bounds[r + 1], halo));
 		}
 		for (size_t r = 0; r < devices.size(); ++r) {

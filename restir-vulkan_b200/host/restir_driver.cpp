@@ -367,6 +367,10 @@ int main(int argc, char **argv) {
 		            frames, nBands, ms / frames, rays, launches, haloMisses, haloTimeouts,
 		            (unsigned long long)fnv1a(reservoirs.data(), reservoirs.size() * sizeof(restir_reservoir)),
 		            (unsigned long long)fnv1a(rgba.data(), rgba.size()));
+		if (haloMisses != 0 || haloTimeouts != 0) { // the frame is not the single-GPU frame: never a success
+			std::cerr << "restir_driver: " << haloMisses << " halo misses, " << haloTimeouts << " halo wait timeouts\n";
+			return 2;
+		}
 	} catch (const restir::Error &e) {
 		std::cerr << "restir_driver: error " << e.code << ": " << e.what() << "\n";
 		return 1;

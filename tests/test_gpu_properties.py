@@ -245,6 +245,55 @@ def test_connected_bands_exchange_halos_themselves(unbiased, bounds):
     assert ph.compare_reservoirs(got, want, "connected bands") == 0
 
 
+@pytest.mark.parametrize("unbiased,world", [(True, 2), (False, 3)])
+def test_band_processes_over_cuda_ipc(tmp_path, unbiased, world):
+    """The path `torchrun bench.py --gpus N` times: one PROCESS per band, neighbours mapped through CUDA IPC handles
+    (restir_band_export_ipc / _open_ipc / _connect), halos pushed and awaited by the library's kernels.  The processes share
+    this one GPU (tests/band_ipc_worker.py); each compares the reservoirs and the RGBA8 rows it owns with a whole-screen
+    context, bit for bit."""
+    import socket
+    import sys
+
+    _torch()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "band_ipc_worker.py")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, worker, str(tmp_path / f"rank{r}.json"), "1" if unbiased else "0"], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(world)]
+    assert len({r["pid"] for r in res}) == world and sum(r["pixels"] for r in res) == 1920 * 432
+    for r in res:
+        assert r["mismatching_reservoirs"] == 0 and r["mismatching_pixels"] == 0, res
+        assert r["halo_misses"] == 0 and r["halo_wait_timeouts"] == 0, res
+
+
+def test_band_connect_rejects_a_halo_taller_than_the_neighbour():
+    """A neighbour pushes only rows it shades itself: when this band's halo reaches past the neighbouring band (rows of a
+    band two hops away), those rows would stay empty without any halo_miss — restir_band_connect refuses the connection."""
+    scene = fixtures.make_procedural(seed=4, grid=8, boxes=10, lights="point", n_point_lights=9)
+    ctxs = [ph.make_context(scene) for _ in range(3)]
+    w, h, halo = 64, 96, 40
+    for r, (b, e) in enumerate(((0, 32), (32, 64), (64, 96))):     # 32-row bands under a 40-row halo
+        ctxs[r].resize_band(w, h, b, e, halo)
+    with pytest.raises(capi.RestirError, match="halo"):
+        ctxs[0].band_connect(1, ctxs[1].band_local_peer())
+    with pytest.raises(capi.RestirError, match="halo"):
+        ctxs[2].band_connect(0, ctxs[1].band_local_peer())
+    for r, (b, e) in enumerate(((0, 32), (32, 64), (64, 96))):     # a 32-row halo fits
+        ctxs[r].resize_band(w, h, b, e, 32)
+    ctxs[0].band_connect(1, ctxs[1].band_local_peer())
+    ctxs[1].band_connect(0, ctxs[0].band_local_peer())
+    for c in ctxs:
+        c.close()
+
+
 def test_oracle_spot_check_at_1080p():
     """A 24-row band of the full-size Sponza frame 2 (temporal history from the GPU's own frame 1) through
     the oracle, compared bit for bit — parity at the BASELINE size without running the oracle on 2 Mpx."""
