@@ -169,6 +169,13 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
  * context then exchanges the halo rows itself between the passes; otherwise RESTIR_E_INVALID (drive the passes one by
  * one and copy the halo rows through restir_reservoir_device_ptr instead). */
 int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations);
+/* Replaces: the same command buffer INCLUDING its lighting pass (src/app.h:212-262: the ReSTIR passes, then
+ * LightingPass::issueCommands on the same G-buffer and FRAME[i]) = restir_frame followed by
+ * restir_pass_lighting(ctx, i, FRAME[i], out_device, out_format), same results bit for bit.  The lighting of a pixel runs
+ * at the end of the kernel that produces its final reservoir (the unbiased pass's normalisation, or the last spatial
+ * pass), from registers: it does not read the reservoir and the G-buffer texels back.  The reference authors measured the
+ * same fusion (media/milestone3 slides 6-7).  Lighting uniforms must be set. */
+int restir_frame_lit(restir_context *ctx, int i, int unbiased, int spatial_iterations, void *out_device, int out_format);
 
 /* ---- reservoir access (parity / replay / halo exchange) -------------------------------------- */
 
@@ -283,10 +290,6 @@ typedef struct restir_camera { /* src/camera.h:7-13 */
 } restir_camera;
 /* src/camera.h:25-50: column-major projectionViewMatrix. */
 int restir_camera_matrix(const restir_camera *camera, float out_pv[16]);
-/* Device self-test (no reference equivalent): runs n pseudo-random operand pairs through the packed two-at-a-time
- * arithmetic of the candidate kernel (csrc/restir_math2.cuh: division, reciprocal, square root, evaluatePHat) and
- * through the scalar arithmetic policy, and counts results whose bits differ: mismatches[0..3]; [4] = values compared. */
-int restir_tools_selftest_packed_math(restir_context *ctx, uint64_t n, uint32_t seed, uint64_t mismatches[5]);
 /* Primary-visibility ray cast of the uploaded BVH into the five G-buffer planes (DEVICE pointers, rows
  * [alloc_begin, alloc_end) of the context's screen), semantics in SURVEY.md §8d / Appendix E.
  * tri_material: DEVICE int32[n_triangles]; material_table: DEVICE uint32[n_materials][4] =

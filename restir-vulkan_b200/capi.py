@@ -63,11 +63,11 @@ EXPORTS = [
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
     "restir_set_traversal", "restir_set_ray_elision", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
-    "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame",
+    "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
     "restir_generate_random_point_lights", "restir_create_alias_table", "restir_camera_matrix",
-    "restir_tools_raycast_gbuffer", "restir_tools_selftest_packed_math", "restir_band_local_peer", "restir_band_export_ipc",
+    "restir_tools_raycast_gbuffer", "restir_band_local_peer", "restir_band_export_ipc",
     "restir_band_open_ipc", "restir_band_connect", "restir_band_balanced_bounds",
 ]
 
@@ -354,12 +354,6 @@ class RestirContext:
     def set_unbiased_neighbors(self, n):
         self._check(self.lib.restir_set_unbiased_neighbors(self._ctx, C.c_uint32(n)))
 
-    def selftest_packed_math(self, n, seed=1):
-        """(div2, rcp2, sqrt2, evaluate_phat2 mismatches against the scalar policy, values compared)."""
-        out = (C.c_uint64 * 5)()
-        self._check(self.lib.restir_tools_selftest_packed_math(self._ctx, C.c_uint64(n), C.c_uint32(seed), out))
-        return tuple(int(v) for v in out)
-
     def set_ray_elision(self, enable):
         self._check(self.lib.restir_set_ray_elision(self._ctx, C.c_int(1 if enable else 0)))
 
@@ -395,6 +389,11 @@ class RestirContext:
 
     def frame(self, i, unbiased, spatial_iterations=1):
         self._check(self.lib.restir_frame(self._ctx, C.c_int(i), C.c_int(1 if unbiased else 0), C.c_int(spatial_iterations)))
+
+    def frame_lit(self, i, unbiased, spatial_iterations, out, out_format=RESTIR_OUT_RGBA32F):
+        """restir_frame + restir_pass_lighting(i, FRAME[i]) with the lighting fused into the last reuse kernel."""
+        self._check(self.lib.restir_frame_lit(self._ctx, C.c_int(i), C.c_int(1 if unbiased else 0), C.c_int(spatial_iterations), _dp(out),
+                                              C.c_int(out_format)))
 
     def download_reservoirs(self, buffer):
         out = np.zeros(self.alloc_rows() * self.width, RESERVOIR_DTYPE)

@@ -58,6 +58,8 @@ struct restir_context {
 	size_t shadowedBytes = 0;
 	int *neighborPix = nullptr;        // [tile-ordered pixel id][unbiased neighbours]
 	size_t neighborPixCount = 0;
+	uint32_t *neighborM = nullptr;     // [tile-ordered pixel id][unbiased neighbours + 1]: sample counts for the normalisation
+	size_t neighborMCount = 0;
 
 	// connected row-band neighbours (restir_band_connect): side 0 owns the rows above, side 1 the rows below
 	struct PeerSide {
@@ -78,11 +80,6 @@ struct restir_context {
 	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
 	int traversal = RESTIR_TRAVERSAL_AUTO;
 	int rayElision = 1; // restir_set_ray_elision
-	// RESTIR_CANDIDATES_PAIRED=1 selects the two-candidates-per-iteration kernel (restir_math2.cuh): bit-identical, 22 %
-	// fewer instructions, but 93 registers and per-operation range checks — 4 % faster on Sponza / 200 lights, 10 % slower
-	// with triangle lights or 1 M lights (profiles/r1_m_summary.md), so the scalar kernel stays the default
-	bool scalarCandidates = true;
-
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
 	uint64_t launches = 0;
 
@@ -276,6 +273,14 @@ int ensureHandOver(restir_context *ctx, const PassGrid &g, unsigned raysPerPixel
 		CU(ctx, cudaMalloc(&ctx->neighborPix, count * sizeof(int)));
 		ctx->neighborPixCount = count;
 	}
+	size_t countM = neighbors ? (size_t)g.pixelIds * (neighbors + 1) : 0;
+	if (ctx->neighborMCount < countM) {
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		freeDev(ctx->neighborM);
+		ctx->neighborMCount = 0;
+		CU(ctx, cudaMalloc(&ctx->neighborM, countM * sizeof(uint32_t)));
+		ctx->neighborMCount = countM;
+	}
 	return RESTIR_OK;
 }
 
@@ -373,7 +378,6 @@ int restir_create(restir_context **out, int device, void *stream) {
 		return RESTIR_E_NOMEM;
 	}
 	ctx->device = device;
-	if (const char *e = std::getenv("RESTIR_CANDIDATES_PAIRED")) ctx->scalarCandidates = std::atoi(e) == 0;
 	int rc = RESTIR_OK;
 	do {
 		if ((rc = cudaCheck(ctx, cudaSetDevice(device), "cudaSetDevice")) != RESTIR_OK) break;
@@ -438,6 +442,7 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->treeBlock); // image + triEdges
 	freeDev(ctx->shadowed);
 	freeDev(ctx->neighborPix);
+	freeDev(ctx->neighborM);
 	freeDev(ctx->pointBlob);
 	freeDev(ctx->triBlob);
 	freeDev(ctx->aliasBlob);
@@ -727,28 +732,6 @@ int restir_set_traversal(restir_context *ctx, int mode) {
 	return RESTIR_OK;
 }
 
-int restir_tools_selftest_packed_math(restir_context *ctx, uint64_t n, uint32_t seed, uint64_t mismatches[5]) {
-	ENTER(ctx);
-	if (mismatches == nullptr) {
-		return fail(ctx, RESTIR_E_INVALID, "null result array");
-	}
-	unsigned long long *dev = nullptr;
-	CU(ctx, cudaMalloc(&dev, 5 * sizeof(unsigned long long)));
-	CU(ctx, cudaMemsetAsync(dev, 0, 5 * sizeof(unsigned long long), ctx->stream));
-	launch_selftest_packed(n, seed, dev, ctx->stream);
-	int rc = afterLaunch(ctx, "selftest_packed_kernel");
-	unsigned long long h[5] = {0, 0, 0, 0, 0};
-	if (rc == RESTIR_OK) {
-		rc = cudaCheck(ctx, cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "memcpy");
-	}
-	if (rc == RESTIR_OK) {
-		rc = cudaCheck(ctx, cudaStreamSynchronize(ctx->stream), "sync");
-	}
-	cudaFree(dev);
-	for (int k = 0; k < 5; ++k) mismatches[k] = h[k];
-	return rc;
-}
-
 int restir_band_local_peer(restir_context *ctx, restir_band_peer *out) {
 	ENTER(ctx);
 	if (out == nullptr || ctx->band.W == 0) {
@@ -916,7 +899,7 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	if ((rc = haloWait(ctx, prev_buffer)) != RESTIR_OK) return rc;
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "omni_candidates_kernel");
-	launch_omni_candidates(p, out, ctx->scalarCandidates, ctx->stream);
+	launch_omni_candidates(p, out, ctx->stream);
 	if ((rc = afterLaunch(ctx, "omni_candidates_kernel")) != RESTIR_OK) return rc;
 	if (vis) {
 		TraceParams tp = traceParams(ctx);
@@ -941,8 +924,38 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	return markReadIfOwned(ctx, gbuffer ^ 1); // the previous frame's G-buffer is not read after this pass
 }
 
+namespace {
+// lighting output of a pass: checked like restir_pass_lighting's
+int checkLightingTarget(restir_context *ctx, const void *out_device, int out_format) {
+	if (!ctx->haveLighting) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_set_lighting_uniforms has not been called");
+	}
+	if (out_device == nullptr || (out_format != RESTIR_OUT_RGBA32F && out_format != RESTIR_OUT_RGBA8_SRGB)) {
+		return fail(ctx, RESTIR_E_INVALID, "lighting pass: bad output");
+	}
+	if ((int)ctx->lighting.bufferSize[0] != ctx->band.W || (int)ctx->lighting.bufferSize[1] != ctx->band.H) {
+		return fail(ctx, RESTIR_E_INVALID, "lighting uniforms bufferSize does not match restir_resize");
+	}
+	return RESTIR_OK;
+}
+int passSpatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter, void *lit_out, int lit_format);
+int passUnbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, void *lit_out, int lit_format);
+} // namespace
+
 int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter) {
 	ENTER(ctx);
+	return passSpatial(ctx, gbuffer, in_buffer, out_buffer, iter, nullptr, 0);
+}
+
+int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer) {
+	ENTER(ctx);
+	return passUnbiased(ctx, gbuffer, in_buffer, out_buffer, nullptr, 0);
+}
+
+namespace {
+
+// lit_out != null: the lighting pass of the same pixels runs inside the pass's last kernel (restir_frame_lit)
+int passSpatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, int iter, void *lit_out, int lit_format) {
 	PassParams p;
 	int rc;
 	if ((rc = makeParams(ctx, gbuffer, false, true, p)) != RESTIR_OK) return rc;
@@ -953,15 +966,17 @@ int restir_pass_spatial(restir_context *ctx, int gbuffer, int in_buffer, int out
 	}
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
-	beforeLaunch(ctx, "spatial_reuse_kernel");
-	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, ctx->stream);
-	if ((rc = afterLaunch(ctx, "spatial_reuse_kernel")) != RESTIR_OK) return rc;
+	if (lit_out && (rc = checkLightingTarget(ctx, lit_out, lit_format)) != RESTIR_OK) return rc;
+	const char *name = lit_out ? "spatial_reuse_kernel+lighting" : "spatial_reuse_kernel";
+	beforeLaunch(ctx, name);
+	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, lit_out ? &ctx->lighting : nullptr, lit_out, lit_format,
+	                     ctx->stream);
+	if ((rc = afterLaunch(ctx, name)) != RESTIR_OK) return rc;
 	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer);
 }
 
-int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer) {
-	ENTER(ctx);
+int passUnbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer, void *lit_out, int lit_format) {
 	PassParams p;
 	int rc;
 	if ((rc = makeParams(ctx, gbuffer, true, true, p)) != RESTIR_OK) return rc;
@@ -980,10 +995,11 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 	if ((rc = ensureHandOver(ctx, g, k + 1, k)) != RESTIR_OK) return rc;
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
+	if (lit_out && (rc = checkLightingTarget(ctx, lit_out, lit_format)) != RESTIR_OK) return rc;
 	const PackedReservoir *in = ctx->reservoirs[in_buffer];
 	PackedReservoir *out = ctx->reservoirs[out_buffer];
 	beforeLaunch(ctx, "unbiased_merge_kernel");
-	launch_unbiased_merge(p, in, out, (int)k, ctx->neighborPix, ctx->stream);
+	launch_unbiased_merge(p, in, out, (int)k, ctx->neighborPix, ctx->neighborM, ctx->stream);
 	if ((rc = afterLaunch(ctx, "unbiased_merge_kernel")) != RESTIR_OK) return rc;
 	if (vis) {
 		// the pixels' own rays first (:157-166): a shadowed pixel needs none of its neighbour rays, and a neighbour ray
@@ -1007,12 +1023,16 @@ int restir_pass_unbiased(restir_context *ctx, int gbuffer, int in_buffer, int ou
 		CU(ctx, launch_trace(tp, kTraceUnbiased, ctx->smCount, ctx->stream));
 		if ((rc = afterLaunch(ctx, "trace_kernel<neighbours>")) != RESTIR_OK) return rc;
 	}
-	beforeLaunch(ctx, "unbiased_finalize_kernel");
-	launch_unbiased_finalize(p, in, out, (int)k, ctx->neighborPix, ctx->shadowed, ctx->stream);
-	if ((rc = afterLaunch(ctx, "unbiased_finalize_kernel")) != RESTIR_OK) return rc;
+	const char *name = lit_out ? "unbiased_finalize_kernel+lighting" : "unbiased_finalize_kernel";
+	beforeLaunch(ctx, name);
+	launch_unbiased_finalize(p, out, (int)k, ctx->neighborPix, ctx->neighborM, ctx->shadowed, lit_out ? &ctx->lighting : nullptr, lit_out, lit_format,
+	                         ctx->stream);
+	if ((rc = afterLaunch(ctx, name)) != RESTIR_OK) return rc;
 	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer);
 }
+
+} // namespace
 
 int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out_device, int out_format) {
 	ENTER(ctx);
@@ -1020,15 +1040,7 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
 	int rc;
 	if ((rc = makeParams(ctx, gbuffer, false, true, p)) != RESTIR_OK) return rc;
 	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
-	if (!ctx->haveLighting) {
-		return fail(ctx, RESTIR_E_INVALID, "restir_set_lighting_uniforms has not been called");
-	}
-	if (out_device == nullptr || (out_format != RESTIR_OUT_RGBA32F && out_format != RESTIR_OUT_RGBA8_SRGB)) {
-		return fail(ctx, RESTIR_E_INVALID, "lighting pass: bad output");
-	}
-	if ((int)ctx->lighting.bufferSize[0] != ctx->band.W || (int)ctx->lighting.bufferSize[1] != ctx->band.H) {
-		return fail(ctx, RESTIR_E_INVALID, "lighting uniforms bufferSize does not match restir_resize");
-	}
+	if ((rc = checkLightingTarget(ctx, out_device, out_format)) != RESTIR_OK) return rc;
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
 	beforeLaunch(ctx, "lighting_kernel");
 	launch_lighting(p, ctx->lighting, ctx->reservoirs[buffer], out_device, out_format, ctx->stream);
@@ -1036,8 +1048,7 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
 	return markReadIfOwned(ctx, gbuffer);
 }
 
-int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations) {
-	ENTER(ctx);
+static int frameImpl(restir_context *ctx, int i, int unbiased, int spatial_iterations, void *lit_out, int lit_format) {
 	if (i < 0 || i > 1 || spatial_iterations < 0) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_frame: bad frame index");
 	}
@@ -1046,17 +1057,35 @@ int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iteration
 		return fail(ctx, RESTIR_E_INVALID, "restir_frame on a band context needs its neighbours connected (restir_band_connect); otherwise interleave the halo copies yourself");
 	}
 	int rc;
+	if (lit_out && (rc = checkLightingTarget(ctx, lit_out, lit_format)) != RESTIR_OK) return rc;
 	const int cur = i, prev = i ^ 1; // app.h:298-332
 	if (unbiased) {
 		if ((rc = restir_pass_restir(ctx, i, RESTIR_BUF_TEMP, prev)) != RESTIR_OK) return rc;
-		return restir_pass_unbiased(ctx, i, RESTIR_BUF_TEMP, cur);
+		return passUnbiased(ctx, i, RESTIR_BUF_TEMP, cur, lit_out, lit_format);
 	}
 	if ((rc = restir_pass_restir(ctx, i, cur, prev)) != RESTIR_OK) return rc;
 	for (int j = 0; j < spatial_iterations; ++j) {
-		if ((rc = restir_pass_spatial(ctx, i, cur, prev, j * 2)) != RESTIR_OK) return rc;
-		if ((rc = restir_pass_spatial(ctx, i, prev, cur, j * 2 + 1)) != RESTIR_OK) return rc;
+		const bool last = j + 1 == spatial_iterations;
+		if ((rc = passSpatial(ctx, i, cur, prev, j * 2, nullptr, 0)) != RESTIR_OK) return rc;
+		if ((rc = passSpatial(ctx, i, prev, cur, j * 2 + 1, last ? lit_out : nullptr, lit_format)) != RESTIR_OK) return rc;
+	}
+	if (lit_out && spatial_iterations == 0) { // nothing to fuse the lighting into
+		return restir_pass_lighting(ctx, i, cur, lit_out, lit_format);
 	}
 	return RESTIR_OK;
+}
+
+int restir_frame(restir_context *ctx, int i, int unbiased, int spatial_iterations) {
+	ENTER(ctx);
+	return frameImpl(ctx, i, unbiased, spatial_iterations, nullptr, 0);
+}
+
+int restir_frame_lit(restir_context *ctx, int i, int unbiased, int spatial_iterations, void *out_device, int out_format) {
+	ENTER(ctx);
+	if (out_device == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_frame_lit: null output");
+	}
+	return frameImpl(ctx, i, unbiased, spatial_iterations, out_device, out_format);
 }
 
 static int ensureStaging(restir_context *ctx) {

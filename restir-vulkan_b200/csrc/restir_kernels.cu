@@ -1,6 +1,6 @@
 // restir_kernels.cu — hand-written sm_100a per-pixel kernels of the ReSTIR resampling path.
 //
-//   omni_candidates_kernel    <- src/shaders/restirOmni.glsl:86-145   (RIS over the alias table; _paired_: opt-in variant)
+//   omni_candidates_kernel    <- src/shaders/restirOmni.glsl:86-145   (RIS over the alias table)
 //   omni_temporal_kernel      <- src/shaders/restirOmni.glsl:148-212  (apply the visibility bit, temporal reuse)
 //   spatial_reuse_kernel      <- src/shaders/spatialReuse.comp:30-86
 //   unbiased_merge_kernel     <- src/shaders/unbiasedReuse.glsl:50-124
@@ -20,7 +20,6 @@
 
 #include "restir_device.cuh"
 #include "restir_kernels.h"
-#include "restir_math2.cuh"
 
 namespace restir {
 
@@ -111,7 +110,11 @@ __device__ __forceinline__ void sample_light_attrs(const SceneView &sc, const Pa
 	} else if (r.lightIndex >= 0) {
 		n = mk3(0.0f, 0.0f, 0.0f);
 		useN = false;
-		lum = __ldg(sc.pointPosLum + r.lightIndex).w;
+		lum = r.lightIndex < sc.pointCount ? __ldg(sc.pointPosLum + r.lightIndex).w : 0.0f; // uploaded reservoirs may name any index
+	} else if (-1 - r.lightIndex >= sc.triCount) {
+		n = mk3(0.0f, 0.0f, 0.0f);
+		useN = true;
+		lum = 0.0f;
 	} else {
 		float4 a = __ldg(sc.triAux + (-1 - r.lightIndex));
 		n = mk3(a.x, a.y, a.z);
@@ -151,6 +154,9 @@ __device__ __forceinline__ void combine_reservoirs(PackedReservoir &self, const 
 		self.w = self.sumWeights / ((float)self.M * self.pHat);
 	}
 }
+
+__device__ __forceinline__ void shade_pixel(const PassParams &p, const restir_lighting_uniforms &lu, size_t pix, const PackedReservoir &r,
+                                            void *__restrict__ outPixels, int outFormat);
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void add_counter(unsigned long long *counters, int slot, unsigned v) {
@@ -207,23 +213,35 @@ __host__ __device__ inline uint32_t draws_per_candidate(bool pointMode) { return
 //     selected, so the division is done once after the loop from the (sumWeights, M) recorded at selection;
 //   * a point light behind the surface has pHat = +0 (restirUtils.glsl:8-10) and, for prob > 0, weight +0:
 //     sumWeights and the selection are unchanged and only M and the RNG advance (reservoir.glsl:6-26).
+//
+// RESTIR_CANDIDATES_SKIP_AHEAD (point lights): such candidates cost ~25 instructions, the others ~290, and which
+// is which differs from lane to lane.  In a plain loop a lane whose light is behind its surface idles through the
+// other lanes' evaluation (r1 capture M: 23.8 of 32 lanes).  Here every lane first runs ahead, on its own, over the
+// candidates that need no evaluation, until it holds one that does; then the warp evaluates one candidate per lane
+// together.  The expensive part runs max-over-lanes(front-facing candidates) times instead of `count` times — the
+// pixels of an 8x4 tile lie on the same surface and turn their back on about the same lights.  Each lane's draws
+// stay in the reference's order (r1, r2, update draw per candidate).
 #ifndef RESTIR_TEMPORAL_MIN_BLOCKS
 #define RESTIR_TEMPORAL_MIN_BLOCKS 5 // latency-bound gathers: 0.111 -> 0.099 ms; the candidate loop is issue-bound and loses with fewer registers (0.707 -> 0.744 at 5)
+#endif
+#ifndef RESTIR_CANDIDATES_SKIP_AHEAD
+#define RESTIR_CANDIDATES_SKIP_AHEAD 1
 #endif
 // no minimum CTA count here: the loop is issue-bound, 64 registers (4 CTAs/SM) is what ptxas picks on its own and both 72 and 51 lose
 __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
 	int x, y;
-	if (!pixel_of_thread(p.band, x, y)) {
-		return;
-	}
+	const bool inside = pixel_of_thread(p.band, x, y); // no early return: the skip-ahead loop votes with the whole warp
 	const SceneView &sc = p.scene;
-	size_t pix = local_index(p.band, x, y);
-	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
-	f3 normal = fetch_normal(p.cur, pix);
-	float roughness, metallic;
-	fetch_material(p.cur, pix, roughness, metallic);
-	f3 worldPos = fetch_world_pos(p.cur, pix);
-	float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
+	const size_t pix = inside ? local_index(p.band, x, y) : 0;
+	f3 normal = mk3(0.0f, 0.0f, 0.0f), worldPos = normal, albedo = normal;
+	float roughness = 0.0f, metallic = 0.0f;
+	if (inside) {
+		albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
+		normal = fetch_normal(p.cur, pix);
+		fetch_material(p.cur, pix, roughness, metallic);
+		worldPos = fetch_world_pos(p.cur, pix);
+	}
+	float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);                 // :103
 	f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
 	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
 
@@ -232,12 +250,53 @@ __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p,
 	res.lightIndex = 0;
 	res.pHat = res.sumWeights = res.w = 0.0f;
 	res.M = 0u;
-	if (dot3(normal, normal) != 0.0f) {                                       // :107
-		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
-		const uint32_t count = p.u.initialLightSampleCount;
-		const bool pointMode = sc.pointCount != 0;
-		float selSum = 0.0f;
-		uint32_t selM = 0u;
+	const bool lit = inside && dot3(normal, normal) != 0.0f;                  // :107
+	Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);      // :106
+	const uint32_t count = lit ? p.u.initialLightSampleCount : 0u;
+	const bool pointMode = sc.pointCount != 0;
+	float selSum = 0.0f;
+	uint32_t selM = 0u;
+	if (pointMode && RESTIR_CANDIDATES_SKIP_AHEAD) {
+		uint32_t i = 0;
+		for (;;) {
+			// run ahead over the candidates that only move M and the RNG, :116-122
+			bool have = false;
+			int idx = 0;
+			float prob = 0.0f;
+			float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			while (i < count) {
+				float r1 = pcg_float(rng);
+				float r2 = pcg_float(rng);
+				alias_sample(sc, r1, r2, idx, prob);
+				pl = __ldg(sc.pointPosLum + idx);
+				++i;
+				res.M += 1u;
+				if (dot3(mk3(pl.x, pl.y, pl.z) - worldPos, normal) < 0.0f && prob > 0.0f) { // pHat = +0, weight = +0
+					pcg_next(rng);
+					continue;
+				}
+				have = true;
+				break;
+			}
+			if (!__any_sync(0xffffffffu, have)) {
+				break;
+			}
+			if (have) {
+				f3 lpos = mk3(pl.x, pl.y, pl.z);
+				float pHat = evaluate_phat(sf, albedoLum, lpos, mk3(0.0f, 0.0f, 0.0f), false, pl.w); // :135-139
+				float weight = pHat / prob;                                       // reservoir.glsl:28-42, 6-26
+				res.sumWeights = res.sumWeights + weight;
+				float replacePossibility = weight / res.sumWeights;
+				if (pcg_float(rng) < replacePossibility) {
+					res.px = lpos.x; res.py = lpos.y; res.pz = lpos.z;
+					res.lightIndex = idx;
+					res.pHat = pHat;
+					selSum = res.sumWeights;
+					selM = res.M;
+				}
+			}
+		}
+	} else {
 		for (uint32_t i = 0; i < count; ++i) {                                // :108-142
 			float r1 = pcg_float(rng);
 			float r2 = pcg_float(rng);
@@ -285,124 +344,13 @@ __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p,
 				selM = res.M;
 			}
 		}
-		if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
-			res.w = selSum / ((float)selM * res.pHat);
-		}
 	}
-	store_reservoir(out, pix, res);                                           // handed to the trace kernel and omni_temporal_kernel
-}
-
-// The same loop, two candidates per iteration (restir_math2.cuh): candidate i and i + 1 are sampled one after the
-// other — the RNG draws keep the reference's order: r1, r2[, r3, r4], update draw, per candidate — evaluated side by
-// side with packed arithmetic, and folded into the reservoir in order.  No candidate takes a shortcut here: a light
-// behind the surface goes through the same instructions with p̂ = +0 selected at the end (weight +0: sumWeights and
-// the selection are unchanged, as in the scalar kernel's early `continue`).  An odd candidate count ends with one
-// candidate whose partner is a copy that is not folded in.
-#ifndef RESTIR_CANDIDATES_MIN_BLOCKS
-#define RESTIR_CANDIDATES_MIN_BLOCKS 3
-#endif
-__global__ void __launch_bounds__(kThreads, RESTIR_CANDIDATES_MIN_BLOCKS) omni_candidates_paired_kernel(PassParams p, PackedReservoir *__restrict__ out) {
-	int x, y;
-	if (!pixel_of_thread(p.band, x, y)) {
-		return;
+	if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
+		res.w = selSum / ((float)selM * res.pHat);
 	}
-	const SceneView &sc = p.scene;
-	size_t pix = local_index(p.band, x, y);
-	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);                 // :98-101
-	f3 normal = fetch_normal(p.cur, pix);
-	float roughness, metallic;
-	fetch_material(p.cur, pix, roughness, metallic);
-	f3 worldPos = fetch_world_pos(p.cur, pix);
-	float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);             // :103
-	f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
-	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
-
-	PackedReservoir res;                                                      // :105
-	res.px = res.py = res.pz = 0.0f;
-	res.lightIndex = 0;
-	res.pHat = res.sumWeights = res.w = 0.0f;
-	res.M = 0u;
-	if (dot3(normal, normal) != 0.0f) {                                       // :107
-		Pcg32 rng = pcg_seed(p.u.frame, (uint32_t)y * 10007u + (uint32_t)x);    // :106
-		const uint32_t count = p.u.initialLightSampleCount;
-		const bool pointMode = sc.pointCount != 0;
-		float selSum = 0.0f;
-		uint32_t selM = 0u;
-		for (uint32_t i = 0; i < count; i += 2) {                             // :108-142, candidates i and i + 1
-			const bool pair = i + 1 < count;
-			int idx[2], lightIndex[2];
-			float prob[2], u[2], r3[2], r4[2];
-#pragma unroll
-			for (int c = 0; c < 2; ++c) {
-				if (c == 1 && !pair) {
-					idx[1] = idx[0]; prob[1] = prob[0]; u[1] = 2.0f; r3[1] = r3[0]; r4[1] = r4[0];
-					break;
-				}
-				float r1 = pcg_float(rng);
-				float r2 = pcg_float(rng);
-				alias_sample(sc, r1, r2, idx[c], prob[c]);
-				r3[c] = r4[c] = 0.0f;
-				if (!pointMode) {
-					r3[c] = pcg_float(rng);
-					r4[c] = pcg_float(rng);
-				}
-				u[c] = pcg_float(rng);                                        // updateReservoirAt's draw, reservoir.glsl:15
-			}
-			f32 lpos, ln;
-			f2 lum, prob2 = mk2(prob[0], prob[1]);
-			if (pointMode) {                                                  // :116-122
-				float4 pa = __ldg(sc.pointPosLum + idx[0]), pb = __ldg(sc.pointPosLum + idx[1]);
-				lpos = f32{mk2(pa.x, pb.x), mk2(pa.y, pb.y), mk2(pa.z, pb.z)};
-				lum = mk2(pa.w, pb.w);
-				lightIndex[0] = idx[0];
-				lightIndex[1] = idx[1];
-				ln = f32{bc2(0.0f), bc2(0.0f), bc2(0.0f)};
-			} else {                                                          // :123-133
-				const float4 *ta = reinterpret_cast<const float4 *>(sc.triLights + idx[0]);
-				const float4 *tb = reinterpret_cast<const float4 *>(sc.triLights + idx[1]);
-				float4 a0 = __ldg(ta), b0 = __ldg(ta + 1), c0 = __ldg(ta + 2), e0 = __ldg(ta + 3), n0 = __ldg(ta + 4);
-				float4 a1 = __ldg(tb), b1 = __ldg(tb + 1), c1 = __ldg(tb + 2), e1 = __ldg(tb + 3), n1 = __ldg(tb + 4);
-				f2 sq = sqrt2(mk2(r3[0], r3[1]));                              // pickPointOnTriangle :68-71
-				f2 rr4 = mk2(r4[0], r4[1]);
-				f2 w1 = sub2(bc2(1.0f), sq), w2 = mul2(sq, sub2(bc2(1.0f), rr4)), w3 = mul2(rr4, sq);
-				lpos.x = addp2(addp2(mul2(mk2(a0.x, a1.x), w1), mul2(mk2(b0.x, b1.x), w2)), mul2(mk2(c0.x, c1.x), w3));
-				lpos.y = addp2(addp2(mul2(mk2(a0.y, a1.y), w1), mul2(mk2(b0.y, b1.y), w2)), mul2(mk2(c0.y, c1.y), w3));
-				lpos.z = addp2(addp2(mul2(mk2(a0.z, a1.z), w1), mul2(mk2(b0.z, b1.z), w2)), mul2(mk2(c0.z, c1.z), w3));
-				lum = mk2(e0.w, e1.w);
-				lightIndex[0] = -1 - idx[0];
-				lightIndex[1] = -1 - idx[1];
-				f32 wi = normalize32(sub32(bc32(worldPos), lpos));
-				ln = f32{mk2(n0.x, n1.x), mk2(n0.y, n1.y), mk2(n0.z, n1.z)};
-				prob2 = div2(prob2, mul2(abs2(dot32(wi, ln)), mk2(n0.w, n1.w)));
-			}
-			f2 pHat = evaluate_phat2(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
-			// addSampleToReservoir + updateReservoirAt for i, then for i + 1: reservoir.glsl:28-42, 6-26
-			f2 weight = div2(pHat, prob2);
-			float s1 = res.sumWeights + weight.x;
-			float s2 = pair ? s1 + weight.y : s1;
-			f2 replacePossibility = div2(weight, mk2(s1, s2));
-			if (u[0] < replacePossibility.x) {
-				res.px = lpos.x.x; res.py = lpos.y.x; res.pz = lpos.z.x;
-				res.lightIndex = lightIndex[0];
-				res.pHat = pHat.x;
-				selSum = s1;
-				selM = res.M + 1u;
-			}
-			if (pair && u[1] < replacePossibility.y) {
-				res.px = lpos.x.y; res.py = lpos.y.y; res.pz = lpos.z.y;
-				res.lightIndex = lightIndex[1];
-				res.pHat = pHat.y;
-				selSum = s2;
-				selM = res.M + 2u;
-			}
-			res.sumWeights = s2;
-			res.M += pair ? 2u : 1u;
-		}
-		if (selM != 0u) { // w = (sumWeights + weight) / (M * pHat) as of the selection, reservoir.glsl:33
-			res.w = selSum / ((float)selM * res.pHat);
-		}
+	if (inside) {
+		store_reservoir(out, pix, res);                                       // handed to the trace kernel and omni_temporal_kernel
 	}
-	store_reservoir(out, pix, res);                                           // handed to the trace kernel and omni_temporal_kernel
 }
 
 // restirOmni.glsl:148-212 on the reservoir omni_candidates_kernel wrote.
@@ -486,8 +434,12 @@ __global__ void __launch_bounds__(kThreads, RESTIR_TEMPORAL_MIN_BLOCKS) omni_tem
 #ifndef RESTIR_SPATIAL_MIN_BLOCKS
 #define RESTIR_SPATIAL_MIN_BLOCKS 4 // same reasoning: 0.253 -> 0.222 ms per pass
 #endif
+// LIGHT: the lighting pass (lighting.frag, debugMode 0) of the same pixel follows from registers — the tail of
+// restir_frame_lit: lighting_kernel would re-read the reservoir just written and the G-buffer texels just used.
+template <bool LIGHT>
 __global__ void __launch_bounds__(kThreads, RESTIR_SPATIAL_MIN_BLOCKS) spatial_reuse_kernel(PassParams p, const PackedReservoir *__restrict__ in,
-                                                                PackedReservoir *__restrict__ out, int iter) {
+                                                                PackedReservoir *__restrict__ out, int iter, restir_lighting_uniforms lu,
+                                                                void *__restrict__ outPixels, int outFormat) {
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
 	unsigned haloMiss = 0;
@@ -531,6 +483,9 @@ __global__ void __launch_bounds__(kThreads, RESTIR_SPATIAL_MIN_BLOCKS) spatial_r
 			combine_reservoirs(res, other, sc, sf, albedoLum, rng);               // :72-83
 		}
 		store_reservoir(out, pix, res);
+		if (LIGHT) {
+			shade_pixel(p, lu, pix, res, outPixels, outFormat);
+		}
 	}
 	add_counter(p.counters, kCounterHaloMiss, haloMiss);
 }
@@ -550,7 +505,7 @@ constexpr int kMaxUnbiasedNeighbors = 16;
 template <int K>
 __global__ void __launch_bounds__(kThreads, RESTIR_REUSE_MIN_BLOCKS) unbiased_merge_kernel(PassParams p, const PackedReservoir *__restrict__ in,
                                                                  PackedReservoir *__restrict__ out, int numNeighborsArg,
-                                                                 int *__restrict__ neighborPix) {
+                                                                 int *__restrict__ neighborPix, uint32_t *__restrict__ neighborM) {
 	const int numNeighbors = K ? K : numNeighborsArg;
 	int x, y;
 	bool active = pixel_of_thread(p.band, x, y);
@@ -570,6 +525,10 @@ __global__ void __launch_bounds__(kThreads, RESTIR_REUSE_MIN_BLOCKS) unbiased_me
 		PackedReservoir res = load_reservoir(in, pix);
 		Pcg32 rng = pcg_seed(p.u.frame * 17u, (uint32_t)y * 10007u + (uint32_t)x); // :72
 		int npx[K ? K : kMaxUnbiasedNeighbors];
+		// the sample counts the normalisation adds up (:126, :139-156), handed to unbiased_finalize_kernel: slot j = neighbour j,
+		// slot numNeighbors = this pixel before the merge
+		uint32_t *ms = neighborM + tile_pixel_id() * (unsigned long long)(numNeighbors + 1);
+		ms[numNeighbors] = res.M;
 #pragma unroll(K ? K : 1)
 		for (int i = 0; i < numNeighbors; ++i) {                                  // :84-124
 			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;
@@ -587,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, RESTIR_REUSE_MIN_BLOCKS) unbiased_me
 			size_t npix = local_index(p.band, nx, ny);
 			PackedReservoir other = load_reservoir(in, npix);
 			npx[i] = (int)npix;
+			ms[i] = other.M;
 			res.M += other.M;                                                     // :104
 			if (other.w != 0.0f && other.M != 0u) {                               // see combine_reservoirs
 				f3 n; bool useN; float lum;
@@ -619,11 +579,13 @@ __global__ void __launch_bounds__(kThreads, RESTIR_REUSE_MIN_BLOCKS) unbiased_me
 }
 
 // unbiasedReuse.glsl:126-182 given the visibility bytes: Z = own M + the M of every participating, unshadowed
-// neighbour; everything is dropped when the pixel itself is shadowed.
-__global__ void __launch_bounds__(kThreads) unbiased_finalize_kernel(PassParams p, const PackedReservoir *__restrict__ in,
-                                                                    PackedReservoir *__restrict__ out, int numNeighbors,
-                                                                    const int *__restrict__ neighborPix,
-                                                                    const unsigned char *__restrict__ shadowed) {
+// neighbour (the counts unbiased_merge_kernel handed over: no gather here); everything is dropped when the pixel
+// itself is shadowed.  LIGHT: see spatial_reuse_kernel.
+template <bool LIGHT>
+__global__ void __launch_bounds__(kThreads) unbiased_finalize_kernel(PassParams p, PackedReservoir *__restrict__ out, int numNeighbors,
+                                                                    const int *__restrict__ neighborPix, const uint32_t *__restrict__ neighborM,
+                                                                    const unsigned char *__restrict__ shadowed, restir_lighting_uniforms lu,
+                                                                    void *__restrict__ outPixels, int outFormat) {
 	int x, y;
 	if (!pixel_of_thread(p.band, x, y)) {
 		return;
@@ -632,17 +594,17 @@ __global__ void __launch_bounds__(kThreads) unbiased_finalize_kernel(PassParams 
 	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0;
 	unsigned long long id = tile_pixel_id();
 	const int *slots = neighborPix + id * (unsigned long long)numNeighbors;
+	const uint32_t *ms = neighborM + id * (unsigned long long)(numNeighbors + 1);
 	const unsigned char *bits = shadowed + id * (unsigned long long)(numNeighbors + 1);
 	float4 *o = reinterpret_cast<float4 *>(out + pix);
 	float4 b = o[1]; // pHat, sumWeights, w, M of the merged reservoir
-	uint32_t numSamples = __float_as_uint(__ldg(reinterpret_cast<const float4 *>(in + pix) + 1).w); // own M before the merge, :126
+	uint32_t numSamples = ms[numNeighbors]; // own M before the merge, :126
 #pragma unroll 1
 	for (int j = 0; j < numNeighbors; ++j) {
-		int n = __ldg(slots + j);
-		if (n < 0 || (vis && bits[j] != 0)) {
+		if (slots[j] < 0 || (vis && bits[j] != 0)) {
 			continue;
 		}
-		numSamples += __float_as_uint(__ldg(reinterpret_cast<const float4 *>(in + n) + 1).w);
+		numSamples += ms[j];
 	}
 	if (vis && bits[numNeighbors] != 0) {                                         // :157-166
 		numSamples = 0;
@@ -654,8 +616,16 @@ __global__ void __launch_bounds__(kThreads) unbiased_finalize_kernel(PassParams 
 		b.y = 0.0f;
 	}
 	o[1] = b;
+	if (LIGHT) {
+		float4 a = o[0];
+		PackedReservoir r;
+		r.px = a.x; r.py = a.y; r.pz = a.z; r.lightIndex = __float_as_int(a.w);
+		r.pHat = b.x; r.sumWeights = b.y; r.w = b.z; r.M = __float_as_uint(b.w);
+		shade_pixel(p, lu, pix, r, outPixels, outFormat);
+	}
 }
 
+// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // lighting.frag:43-71,103 (debugMode 0)
 __device__ __forceinline__ float srgb_encode(float c) {
@@ -663,15 +633,10 @@ __device__ __forceinline__ float srgb_encode(float c) {
 	return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
 }
 
-__global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir_lighting_uniforms lu,
-                                                           const PackedReservoir *__restrict__ reservoirs, void *__restrict__ outPixels,
-                                                           int outFormat) {
-	int x, y;
-	if (!pixel_of_thread(p.band, x, y)) {
-		return;
-	}
+// lighting.frag:43-71,103 for one pixel whose final reservoir is `r`
+__device__ __forceinline__ void shade_pixel(const PassParams &p, const restir_lighting_uniforms &lu, size_t pix, const PackedReservoir &r,
+                                            void *__restrict__ outPixels, int outFormat) {
 	const SceneView &sc = p.scene;
-	size_t pix = local_index(p.band, x, y);
 	float albedoA;
 	f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, &albedoA);
 	f3 normal = fetch_normal(p.cur, pix);
@@ -681,7 +646,6 @@ __global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir
 	f3 cam = mk3(lu.cameraPos[0], lu.cameraPos[1], lu.cameraPos[2]);
 	Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
 
-	PackedReservoir r = load_reservoir(reservoirs, pix);
 	f3 emission = mk3(0.0f, 0.0f, 0.0f);                                           // :55-60 (out-of-range reads give 0)
 	if (r.lightIndex < 0) {
 		int ti = -1 - r.lightIndex;
@@ -713,6 +677,17 @@ __global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir
 		q.w = 255;
 		reinterpret_cast<uchar4 *>(outPixels)[pix] = q;
 	}
+}
+
+__global__ void __launch_bounds__(kThreads) lighting_kernel(PassParams p, restir_lighting_uniforms lu,
+                                                           const PackedReservoir *__restrict__ reservoirs, void *__restrict__ outPixels,
+                                                           int outFormat) {
+	int x, y;
+	if (!pixel_of_thread(p.band, x, y)) {
+		return;
+	}
+	size_t pix = local_index(p.band, x, y);
+	shade_pixel(p, lu, pix, load_reservoir(reservoirs, pix), outPixels, outFormat);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -890,30 +865,37 @@ PassGrid pass_grid(const Band &b) {
 	return PassGrid{g.x, g.y, g.x * 4u, 256ull * g.x * g.y};
 }
 
-void launch_omni_candidates(const PassParams &p, PackedReservoir *out, bool scalar, cudaStream_t s) {
-	if (scalar) {
-		omni_candidates_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
-	} else {
-		omni_candidates_paired_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
-	}
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s) {
+	omni_candidates_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out);
 }
 void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s) {
 	LcgJump jump = lcg_jump((uint64_t)p.u.initialLightSampleCount * draws_per_candidate(p.scene.pointCount != 0));
 	omni_temporal_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out, prev, shadowed, jump);
 }
-void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s) {
-	spatial_reuse_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter);
-}
-void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix, cudaStream_t s) {
-	switch (numNeighbors) {
-	case 3: unbiased_merge_kernel<3><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
-	case 5: unbiased_merge_kernel<5><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
-	default: unbiased_merge_kernel<0><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix); break;
+void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, const restir_lighting_uniforms *lu,
+                          void *outPixels, int fmt, cudaStream_t s) {
+	if (lu) {
+		spatial_reuse_kernel<true><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter, *lu, outPixels, fmt);
+	} else {
+		spatial_reuse_kernel<false><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter, restir_lighting_uniforms{}, nullptr, 0);
 	}
 }
-void launch_unbiased_finalize(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, const int *neighborPix,
-                              const unsigned char *shadowed, cudaStream_t s) {
-	unbiased_finalize_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix, shadowed);
+void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix,
+                           uint32_t *neighborM, cudaStream_t s) {
+	switch (numNeighbors) {
+	case 3: unbiased_merge_kernel<3><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix, neighborM); break;
+	case 5: unbiased_merge_kernel<5><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix, neighborM); break;
+	default: unbiased_merge_kernel<0><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, numNeighbors, neighborPix, neighborM); break;
+	}
+}
+void launch_unbiased_finalize(const PassParams &p, PackedReservoir *out, int numNeighbors, const int *neighborPix, const uint32_t *neighborM,
+                              const unsigned char *shadowed, const restir_lighting_uniforms *lu, void *outPixels, int fmt, cudaStream_t s) {
+	if (lu) {
+		unbiased_finalize_kernel<true><<<tile_grid(p.band), kThreads, 0, s>>>(p, out, numNeighbors, neighborPix, neighborM, shadowed, *lu, outPixels, fmt);
+	} else {
+		unbiased_finalize_kernel<false><<<tile_grid(p.band), kThreads, 0, s>>>(p, out, numNeighbors, neighborPix, neighborM, shadowed,
+		                                                                      restir_lighting_uniforms{}, nullptr, 0);
+	}
 }
 void launch_lighting(const PassParams &p, const restir_lighting_uniforms &lu, const PackedReservoir *res, void *out, int fmt, cudaStream_t s) {
 	lighting_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, lu, res, out, fmt);
@@ -945,13 +927,14 @@ cudaError_t preload_pixel_kernels() {
 	cudaFuncAttributes a;
 	cudaError_t e = cudaSuccess;
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_candidates_kernel);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_candidates_paired_kernel);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_temporal_kernel);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel<false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel<true>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<0>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<3>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<5>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_finalize_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_finalize_kernel<false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_finalize_kernel<true>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lighting_kernel);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, raycast_gbuffer_kernel);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unpack_reservoirs_kernel);

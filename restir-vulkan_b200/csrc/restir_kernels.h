@@ -48,14 +48,17 @@ PassGrid pass_grid(const Band &b);
 
 // restirOmni.glsl:108-142 (candidates) and :148-209 (apply visibility, temporal reuse); between the two the
 // trace kernel runs in kTracePixel mode on `out`.
-void launch_omni_candidates(const PassParams &p, PackedReservoir *out, bool scalar, cudaStream_t s); // scalar: one candidate per iteration (A/B)
+void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s);
 void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s);
-void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, cudaStream_t s);
+// lu != null: the lighting pass of the same pixels follows inside the kernel (restir_frame_lit), written to outPixels in format fmt
+void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, const restir_lighting_uniforms *lu,
+                          void *outPixels, int fmt, cudaStream_t s);
 // unbiasedReuse.glsl:84-124 (merge) and :126-182 (normalisation from the visibility bits); the trace kernel
-// runs in kTraceUnbiased mode between them.
-void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix, cudaStream_t s);
-void launch_unbiased_finalize(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, const int *neighborPix,
-                              const unsigned char *shadowed, cudaStream_t s);
+// runs in kTraceUnbiased mode between them.  neighborM: [pixel id][numNeighbors + 1] sample counts handed from the merge to the normalisation.
+void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix,
+                           uint32_t *neighborM, cudaStream_t s);
+void launch_unbiased_finalize(const PassParams &p, PackedReservoir *out, int numNeighbors, const int *neighborPix, const uint32_t *neighborM,
+                              const unsigned char *shadowed, const restir_lighting_uniforms *lu, void *outPixels, int fmt, cudaStream_t s);
 void launch_lighting(const PassParams &p, const restir_lighting_uniforms &lu, const PackedReservoir *res, void *out, int fmt, cudaStream_t s);
 void launch_raycast_gbuffer(const SceneView &sc, const Band &band, const RaycastCamera &cam, const int *triMaterial, const uint4 *materialTable,
                             void *albedo, void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
@@ -85,8 +88,5 @@ cudaError_t launch_halo_wait(const unsigned long long *flagA, const unsigned lon
 cudaError_t preload_pixel_kernels();
 cudaError_t preload_trace_kernels();
 cudaError_t preload_halo_kernels();
-
-// restir_selftest.cu: mismatch[0..3] = div2, rcp2, sqrt2, evaluate_phat2 results differing from the scalar policy; [4] = values compared
-void launch_selftest_packed(uint64_t n, uint32_t seed, unsigned long long *mismatch, cudaStream_t s);
 
 } // namespace restir

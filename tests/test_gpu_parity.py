@@ -267,30 +267,6 @@ def test_ray_elision_is_exact(name):
     assert walked[1] < walked[0]
 
 
-def test_packed_arithmetic_matches_scalar_policy():
-    """restir_math2.cuh (two values per FADD2/FMUL2/FFMA2 issue slot) against restir_math.cuh on the device: packed
-    division, reciprocal, square root and evaluatePHat must give the scalar policy's bits on every operand pair."""
-    _torch()
-    ctx = capi.RestirContext(0)
-    div, rcp, sqrt, phat, compared = ctx.selftest_packed_math(1 << 24, seed=7)
-    ctx.close()
-    assert compared == 2 << 24
-    assert (div, rcp, sqrt, phat) == (0, 0, 0, 0)
-
-
-@pytest.mark.parametrize("name", ["procedural:point", "procedural:tri"])
-def test_paired_candidate_kernel_is_bit_identical(name, monkeypatch):
-    """The opt-in two-candidates-per-iteration kernel (RESTIR_CANDIDATES_PAIRED=1) against the oracle, odd candidate
-    count included."""
-    _torch()
-    monkeypatch.setenv("RESTIR_CANDIDATES_PAIRED", "1")
-    scene = _scene(name)
-    w, h = 160, 90
-    for candidates in (32, 7):
-        case = ph.Case(scene, w, h, _cams(name, 2, w, h), unbiased=False, candidates=candidates)
-        ph.assert_frames_match(ph.run_cuda(case), ph.run_oracle(case), f"{name} paired candidates={candidates}")
-
-
 # ---- boundary behaviour ---------------------------------------------------------------------------------
 
 def test_reservoir_upload_download_round_trip():

@@ -104,6 +104,40 @@ def test_full_size_determinism_and_counters(unbiased):
     assert (r["w"] > 0).mean() > 0.3 and np.isfinite(r["w"]).all()
 
 
+@pytest.mark.parametrize("unbiased,iterations,fmt", [(True, 1, "rgba8"), (True, 1, "f32"), (False, 1, "rgba8"), (False, 2, "f32"), (False, 0, "f32")])
+def test_frame_lit_equals_frame_then_lighting(unbiased, iterations, fmt):
+    """restir_frame_lit (lighting fused into the kernel that produces the final reservoir) against restir_frame followed by
+    restir_pass_lighting: same reservoirs, same image, bit for bit, over a 3-frame sequence with temporal history."""
+    torch = _torch()
+    scene, (pos, look) = _scene_full()
+    w, h = 640, 360
+    dtype, out_format = (torch.uint8, capi.RESTIR_OUT_RGBA8_SRGB) if fmt == "rgba8" else (torch.float32, capi.RESTIR_OUT_RGBA32F)
+    images, finals, launches = [], [], []
+    for fused in (False, True):
+        d = DeviceFrames(scene, pos, look, w, h)
+        d.ctx.set_unbiased_neighbors(5)
+        img = torch.zeros((h, w, 4), dtype=dtype, device="cuda")
+        torch.cuda.synchronize()
+        d.ctx.counters(reset=True)
+        for f in range(3):
+            d.set(f)
+            if fused:
+                d.ctx.frame_lit(f & 1, unbiased, iterations, img, out_format)
+            else:
+                d.ctx.frame(f & 1, unbiased, iterations)
+                d.ctx.pass_lighting(f & 1, f & 1, img, out_format)
+        d.ctx.synchronize()
+        launches.append(d.ctx.counters()["kernel_launches"])
+        images.append(img.cpu().numpy().copy())
+        finals.append(d.ctx.download_reservoirs(0))
+        d.ctx.close()
+    assert np.array_equal(finals[0].view(np.uint8), finals[1].view(np.uint8))
+    assert np.array_equal(images[0].view(np.uint8), images[1].view(np.uint8))
+    assert images[0].view(np.uint8).any()
+    if unbiased or iterations > 0:
+        assert launches[1] == launches[0] - 3    # one kernel per frame less
+
+
 def test_degenerate_parameters_are_identities():
     """spatialNeighbors = 0 makes the spatial pass a copy; no flags => no rays and temporal off equals a
     first frame; M after pass 1 equals the candidate count on every non-background pixel."""
