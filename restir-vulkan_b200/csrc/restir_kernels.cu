@@ -214,18 +214,19 @@ __host__ __device__ inline uint32_t draws_per_candidate(bool pointMode) { return
 //   * a point light behind the surface has pHat = +0 (restirUtils.glsl:8-10) and, for prob > 0, weight +0:
 //     sumWeights and the selection are unchanged and only M and the RNG advance (reservoir.glsl:6-26).
 //
-// RESTIR_CANDIDATES_SKIP_AHEAD (point lights): such candidates cost ~25 instructions, the others ~290, and which
-// is which differs from lane to lane.  In a plain loop a lane whose light is behind its surface idles through the
-// other lanes' evaluation (r1 capture M: 23.8 of 32 lanes).  Here every lane first runs ahead, on its own, over the
-// candidates that need no evaluation, until it holds one that does; then the warp evaluates one candidate per lane
-// together.  The expensive part runs max-over-lanes(front-facing candidates) times instead of `count` times — the
-// pixels of an 8x4 tile lie on the same surface and turn their back on about the same lights.  Each lane's draws
-// stay in the reference's order (r1, r2, update draw per candidate).
+// RESTIR_CANDIDATES_SKIP_AHEAD 1 (experiment, off; point lights): such candidates cost ~25 instructions, the others ~290,
+// and which is which differs from lane to lane: in the plain loop a lane whose light is behind its surface idles through
+// the other lanes' evaluation (r1 capture M: 23.8 of 32 lanes).  With the switch on every lane first runs ahead, on its
+// own, over the candidates that need no evaluation until it holds one that does, then the warp evaluates one candidate
+// per lane together: the expensive part runs max-over-lanes(front-facing candidates) times instead of `count` times.
+// Measured on B200 (profiles/r2_b_summary.md): 0.708 -> 0.950 ms on Sponza / 200 lights — with a quarter of the
+// candidates back-facing, almost every round has some lane that runs ahead two or three times, so the ~35-instruction
+// draw-and-fetch part is issued 2.5 times per round at a few lanes, which costs more than the 4 rounds it saves.
 #ifndef RESTIR_TEMPORAL_MIN_BLOCKS
 #define RESTIR_TEMPORAL_MIN_BLOCKS 5 // latency-bound gathers: 0.111 -> 0.099 ms; the candidate loop is issue-bound and loses with fewer registers (0.707 -> 0.744 at 5)
 #endif
 #ifndef RESTIR_CANDIDATES_SKIP_AHEAD
-#define RESTIR_CANDIDATES_SKIP_AHEAD 1
+#define RESTIR_CANDIDATES_SKIP_AHEAD 0
 #endif
 // no minimum CTA count here: the loop is issue-bound, 64 registers (4 CTAs/SM) is what ptxas picks on its own and both 72 and 51 lose
 __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
