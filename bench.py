@@ -695,6 +695,52 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
             e2e_ms, e2e_rays = float(tt[0]), float(tt[1])
         e2e = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": e2e_ms / steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        # the same with the G-buffer made on the device (restir_pass_gbuffer: gBuffer.vert / gBuffer.frag by ray casting, textures
+        # included): what crosses PCIe per step is the camera and the two uniform blocks in, the image out
+        if fixtures.gbuffer_inputs_available(cfg["scene"]) and cam_key == cfg["scene"] and not cfg["lights"]:
+            fixtures.load_gbuffer_inputs(cfg["scene"]).upload(ctx)
+
+            def e2e_step_device(f):
+                i = f & 1
+                if copy_done[i] is not None:
+                    stream.wait_event(copy_done[i])
+                ctx.pass_gbuffer(i, cams[i])
+                render(f, out_imgs[i])
+                lit = torch.cuda.Event()
+                lit.record(stream)
+                side.wait_event(lit)
+                with torch.cuda.stream(side):
+                    host_outs[i].copy_(out_imgs[i], non_blocking=True)
+                    copy_done[i] = torch.cuda.Event()
+                    copy_done[i].record(side)
+
+            for _ in range(3):
+                e2e_step_device(frame_no)
+                frame_no += 1
+            barrier()
+            ctx.counters(reset=True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record(stream)
+            for _ in range(steps):
+                e2e_step_device(frame_no)
+                frame_no += 1
+            e2e_drain()
+            b.record(stream)
+            barrier()
+            c3 = ctx.counters(reset=True, check=False)
+            tt = torch.tensor([a.elapsed_time(b), float(c3["shadow_rays"])], dtype=torch.float64, device=dev)
+            if world > 1:
+                mx = tt.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                sm_ = tt.clone()
+                dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+                tt = torch.stack([mx[0], sm_[1]])
+            e2e["device_gbuffer"] = {"value": float(tt[1]) / (float(tt[0]) * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": float(tt[0]) / steps,
+                                     "h2d_bytes_per_step": 128 + 96 + 44, "d2h_bytes_per_step": int(d2h),
+                                     "note": "every step: restir_pass_gbuffer (gBuffer.vert / gBuffer.frag by ray casting on the device, the scene's "
+                                             "textures reduced to <= 256 texels a side) -> restir_frame_lit -> image to the host; no G-buffer crosses PCIe; "
+                                             "the textured G-buffer is a different input from the factor-only fixture of the other legs"}
         for s in (0, 1):
             ctx.bind_gbuffer(s, *gb[s])
         del host_gb, host_outs

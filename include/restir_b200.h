@@ -100,6 +100,37 @@ int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format for
  * The observable order is the in-order one. */
 int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *host_planes);
 
+/* ---- the G-buffer pass ------------------------------------------------------ */
+
+typedef struct restir_camera { /* src/camera.h:7-13 */
+	float position[3], lookAt[3], worldUp[3];
+	float zNear, zFar, fovYRadians, aspectRatio;
+} restir_camera;
+
+/* Replaces: the vertex / index / matrix buffers of SceneBuffers (src/sceneBuffers.h:173-203, 225-230) and the draw
+ * list of GBufferPass::issueCommands (src/passes/gBufferPass.cpp:135-152), plus the vertex stage gBuffer.vert:22-34,
+ * which runs here once per upload: every triangle gets its three world-space normals (transformInverseTransposed,
+ * normalised), tangents (transform, normalised, w kept) and texture coordinates.  The triangles of the draws, in draw
+ * order, must be the triangles of restir_upload_bvh (AabbTree::build collects them in exactly this order,
+ * src/aabbTreeBuilder.cpp:59-76): call restir_upload_bvh first.  Host pointers. */
+int restir_upload_geometry(restir_context *ctx, const restir_vertex *vertices, uint64_t n_vertices, const uint32_t *indices, uint64_t n_indices,
+                           const restir_draw *draws, const restir_model_matrices *matrices, uint32_t n_draws);
+/* Replaces: the material uniform buffer (sceneBuffers.h:205-222), the texture images (sceneBuffers.h:126-171) and the
+ * per-material descriptor sets (gBufferPass.cpp:193-247).  Textures are sampled like the reference's samplers as far as
+ * this producer goes: repeat wrap, bilinear, level 0 of what is uploaded (no mip chain, no anisotropy).  Host pointers. */
+int restir_upload_materials(restir_context *ctx, const restir_material_uniforms *uniforms, const restir_material_textures *bindings,
+                            uint32_t n_materials, const restir_texture *textures, uint32_t n_textures);
+/* Replaces: GBufferPass::issueCommands (gBufferPass.cpp:116-157) running gBuffer.vert / gBuffer.frag:27-80 into G-buffer
+ * slot `slot`, for the camera whose projectionViewMatrix the reference writes into the pass's uniform buffer
+ * (src/app.cpp:802-806, src/camera.h:25-50).  B200 has no rasteriser: primary visibility is a closest-hit ray cast
+ * through each pixel centre against the uploaded tree (back faces culled, ALPHA_MODE_MASK fragments below the cutoff
+ * discarded, near / far planes as clip planes, depth test LESS = nearest hit, ties to the earlier draw).  The planes are
+ * context-owned, in the formats of RESTIR_GBUFFER_NVIDIA_DEFAULT with the pass's clears, and are bound to the slot
+ * like restir_upload_gbuffer's — a full frame then needs no G-buffer traffic over PCIe at all. */
+int restir_pass_gbuffer(restir_context *ctx, int slot, const restir_camera *camera);
+/* The device planes of a slot the context owns (restir_pass_gbuffer / restir_upload_gbuffer), rows [alloc_begin, alloc_end). */
+int restir_gbuffer_device_planes(restir_context *ctx, int slot, restir_gbuffer_planes *out);
+
 /* ---- uniforms ------------------------------------------------------------------------------------ */
 
 /* Replaces: the mapped write of the RestirUniforms UBO each frame (src/app.cpp:775-826, initial values
@@ -284,10 +315,6 @@ int restir_create_alias_table(const restir_point_light *point, uint64_t n_point,
 
 /* ---- fixture tool (synthesises INPUTS; not part of the reference's hot path) ------------------ */
 
-typedef struct restir_camera { /* src/camera.h:7-13 */
-	float position[3], lookAt[3], worldUp[3];
-	float zNear, zFar, fovYRadians, aspectRatio;
-} restir_camera;
 /* src/camera.h:25-50: column-major projectionViewMatrix. */
 int restir_camera_matrix(const restir_camera *camera, float out_pv[16]);
 /* Primary-visibility ray cast of the uploaded BVH into the five G-buffer planes (DEVICE pointers, rows

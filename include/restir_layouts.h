@@ -134,6 +134,73 @@ typedef struct restir_gbuffer_planes {
 	const void *depth;
 } restir_gbuffer_planes;
 
+/* ---- what the G-buffer pass binds (src/passes/gBufferPass.cpp:116-157), for restir_pass_gbuffer --------------------
+ * reference: src/vertex.h (vec4 position, normal, tangent, color; vec2 uv; 16-byte aligned => 80 bytes).  The vertex
+ * shader reads position.xyz, normal.xyz, tangent.xyzw and uv (gBuffer.vert:12-16); color is carried and unused. */
+typedef struct restir_vertex {
+	float position[4];
+	float normal[4];
+	float tangent[4];
+	float color[4];
+	float uv[2];
+	float pad_[2];
+} restir_vertex;
+
+/* One drawIndexed of GBufferPass::issueCommands (gBufferPass.cpp:135-152): the GltfPrimMesh fields it uses.  Draw d uses
+ * matrices[d] (the dynamic offset is i * sizeof(ModelMatrices)). */
+typedef struct restir_draw {
+	uint32_t firstIndex;
+	uint32_t indexCount;
+	uint32_t vertexOffset;
+	int32_t materialIndex;
+} restir_draw;
+
+/* reference: sceneStructs.glsl:1-4, filled at sceneBuffers.h:225-230 (column-major) */
+typedef struct restir_model_matrices {
+	float transform[16];
+	float transformInverseTransposed[16];
+} restir_model_matrices;
+
+#define RESTIR_SHADING_MODEL_METALLIC_ROUGHNESS 0
+#define RESTIR_SHADING_MODEL_SPECULAR_GLOSSINESS 1
+#define RESTIR_ALPHA_MODE_OPAQUE 0
+#define RESTIR_ALPHA_MODE_MASK 1
+#define RESTIR_ALPHA_MODE_BLEND 2
+/* reference: sceneStructs.glsl:15-34, filled at sceneBuffers.h:205-222 */
+typedef struct restir_material_uniforms {
+	float colorParam[4];    /* baseColorFactor | diffuseFactor */
+	float materialParam[4]; /* (-, roughnessFactor, metallicFactor, -) | (specularFactor.rgb, glossinessFactor) */
+	float emissiveFactor[4];
+	int32_t shadingModel;
+	int32_t alphaMode;
+	float alphaCutoff;
+	float normalTextureScale;
+} restir_material_uniforms;
+
+/* The four combined image samplers of a material's descriptor set (gBuffer.frag:11-14, written at
+ * gBufferPass.cpp:200-247): indices into the texture array, -1 = the default texture of that binding
+ * (white 255,255,255,255; for `normal` 127,127,255,255 — sceneBuffers.h:153-170). */
+typedef struct restir_material_textures {
+	int32_t albedo;   /* baseColor | diffuse */
+	int32_t normal;
+	int32_t material; /* metallicRoughness | specularGlossiness */
+	int32_t emissive;
+} restir_material_textures;
+
+/* One texture image: R8G8B8A8_UNORM as SceneBuffers uploads it (sceneBuffers.h:126), level 0, tightly packed rows. */
+typedef struct restir_texture {
+	const void *rgba8;
+	uint32_t width, height;
+} restir_texture;
+
+RESTIR_STATIC_ASSERT(sizeof(restir_vertex) == 80, "Vertex is 80 bytes");
+RESTIR_STATIC_ASSERT(offsetof(restir_vertex, uv) == 64, "Vertex.uv");
+RESTIR_STATIC_ASSERT(sizeof(restir_draw) == 16, "draw record is 16 bytes");
+RESTIR_STATIC_ASSERT(sizeof(restir_model_matrices) == 128, "ModelMatrices is 128 bytes");
+RESTIR_STATIC_ASSERT(sizeof(restir_material_uniforms) == 64, "MaterialUniforms is 64 bytes");
+RESTIR_STATIC_ASSERT(offsetof(restir_material_uniforms, emissiveFactor) == 32, "MaterialUniforms.emissiveFactor");
+RESTIR_STATIC_ASSERT(offsetof(restir_material_uniforms, shadingModel) == 48, "MaterialUniforms.shadingModel");
+RESTIR_STATIC_ASSERT(offsetof(restir_material_uniforms, normalTextureScale) == 60, "MaterialUniforms.normalTextureScale");
 RESTIR_STATIC_ASSERT(sizeof(restir_light_sample) == 48, "LightSample is 48 bytes");
 RESTIR_STATIC_ASSERT(offsetof(restir_light_sample, normal) == 16, "LightSample.normal");
 RESTIR_STATIC_ASSERT(offsetof(restir_light_sample, lightIndex) == 32, "LightSample.lightIndex");

@@ -261,6 +261,43 @@ def raycast_gbuffer(scene, tri_material, material_table, cam, w, h, rows=None):
     return g
 
 
+class GBufferInputs:
+    """What the G-buffer pass binds, as numpy arrays in the reference's layouts (include/restir_layouts.h):
+    vertices (V,80)u8, indices (I,)u32, draws (D,4)u32, matrices (D,128)u8, uniforms (M,64)u8, bindings (M,4)i32,
+    textures: list of (h,w,4)u8."""
+
+    def __init__(self, vertices, indices, draws, matrices, uniforms, bindings, textures):
+        self.vertices = np.ascontiguousarray(vertices).view(np.uint8).reshape(-1, 80)
+        self.indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        self.draws = np.ascontiguousarray(draws).view(np.uint32).reshape(-1, 4)
+        self.matrices = np.ascontiguousarray(matrices).view(np.uint8).reshape(-1, 128)
+        self.uniforms = np.ascontiguousarray(uniforms).view(np.uint8).reshape(-1, 64)
+        self.bindings = np.ascontiguousarray(bindings, np.int32).reshape(-1, 4)
+        self.textures = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        n_tris = int(self.draws[:, 1].sum()) // 3
+        self.attrs = np.zeros((n_tris, 32), np.float32)
+        self.tri_material = np.zeros(n_tris, np.int32)
+        lib().oracle_vertex_stage(_p(self.vertices), _p(self.indices), _p(self.draws), _p(self.matrices), C.c_uint32(self.draws.shape[0]),
+                                  _p(self.attrs), _p(self.tri_material))
+        table, first = [], 0
+        for t in self.textures:
+            table.append((first, t.shape[1], t.shape[0], 0))
+            first += t.shape[0] * t.shape[1]
+        self.texture_table = np.asarray(table, np.uint32).reshape(-1, 4)
+        self.texels = np.concatenate([t.reshape(-1) for t in self.textures]) if self.textures else np.zeros(4, np.uint8)
+
+
+def gbuffer_pass(scene, inputs, cam, w, h, rows=None):
+    """CPU twin of restir_pass_gbuffer (gBuffer.vert / gBuffer.frag by ray casting, oracle_gbuffer_pass)."""
+    y0, y1 = rows or (0, h)
+    g = GBuffer(w, h)
+    lib().oracle_gbuffer_pass(C.byref(scene.c), _p(inputs.attrs), _p(inputs.tri_material), _p(inputs.uniforms), _p(inputs.bindings),
+                              C.c_int(inputs.uniforms.shape[0]), _p(inputs.texels), _p(inputs.texture_table), C.c_int(len(inputs.textures)),
+                              C.byref(cam), C.c_int(w), C.c_int(h), C.c_int(y0), C.c_int(y1), _p(g.albedo), _p(g.normal), _p(g.material),
+                              _p(g.world_pos), _p(g.depth))
+    return g
+
+
 def num_threads():
     return lib().oracle_num_threads()
 

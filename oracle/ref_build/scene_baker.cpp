@@ -12,8 +12,10 @@
 //   light selection + alias table     src/sceneBuffers.h:78-84
 //   SSBO blob packing                 src/sceneBuffers.h:100-124, 241-270 (count @0, array @16)
 //   material parameter packing        src/sceneBuffers.h:205-222
+//   G-buffer pass inputs              src/sceneBuffers.h:126-233 (vertices, indices, matrices, material uniforms, textures),
+//                                     src/passes/gBufferPass.cpp:132-152 (draws), :193-247 (which texture a material binds)
 //
-// usage: scene_baker gltf <file.gltf> <outdir>
+// usage: scene_baker gltf <file.gltf> <outdir> [texture limit: also dump the G-buffer pass inputs, textures reduced to <= limit texels a side]
 //        scene_baker soup <file.soup> <outdir>      (procedural triangle soup, see tests/scenes.py)
 //        scene_baker randlights <n> <minx miny minz maxx maxy maxz> <out.bin>
 
@@ -70,7 +72,129 @@ template <typename T> static void writeBlob(const std::string &path, const std::
 
 static bool skipImage(tinygltf::Image*, const int, std::string*, std::string*, int, int,
                       const unsigned char*, int, void*) {
-	return true; // factor-only fixtures: pixels are never read
+	return true; // scenes baked without their textures
+}
+
+// ---- what GBufferPass binds (src/passes/gBufferPass.cpp:116-157), for the G-buffer producer and its oracle twin -------
+struct BakedVertex { // src/vertex.h
+	nvmath::vec4 position, normal, tangent, color;
+	nvmath::vec2 uv;
+};
+static_assert(sizeof(BakedVertex) == 80, "Vertex is 80 bytes");
+
+// Textures larger than `limit` texels on a side are halved (2x2 box, rounded) until they fit: the snapshot that travels to
+// the GPU box stays small.  The producer samples whatever level it is given as level 0.
+static void dumpGBufferInputs(const nvh::GltfScene &scene, const std::string &out, int textureLimit) {
+	// vertices, sceneBuffers.h:173-193
+	std::vector<BakedVertex> vertices(scene.m_positions.size());
+	std::memset(vertices.data(), 0, vertices.size() * sizeof(BakedVertex));
+	for (std::size_t i = 0; i < scene.m_positions.size(); ++i) {
+		BakedVertex &v = vertices[i];
+		v.position = scene.m_positions[i];
+		if (i < scene.m_normals.size()) {
+			v.normal = scene.m_normals[i];
+		}
+		if (i < scene.m_colors0.size()) {
+			v.color = scene.m_colors0[i];
+		} else {
+			v.color = nvmath::vec4(1.0f, 0.0f, 1.0f, 1.0f);
+		}
+		if (i < scene.m_texcoords0.size()) {
+			v.uv = scene.m_texcoords0[i];
+		}
+		if (i < scene.m_tangents.size()) {
+			v.tangent = scene.m_tangents[i];
+		}
+	}
+	writeFile(out + "/vertices.bin", vertices.data(), vertices.size() * sizeof(BakedVertex));
+	writeFile(out + "/indices.u32", scene.m_indices.data(), scene.m_indices.size() * 4);
+
+	// draws (gBufferPass.cpp:132-152) and matrices (sceneBuffers.h:225-230)
+	std::vector<uint32_t> draws;
+	std::vector<shader::ModelMatrices> matrices(scene.m_nodes.size());
+	for (std::size_t i = 0; i < scene.m_nodes.size(); ++i) {
+		const nvh::GltfPrimMesh &mesh = scene.m_primMeshes[scene.m_nodes[i].primMesh];
+		draws.push_back(mesh.firstIndex);
+		draws.push_back(mesh.indexCount);
+		draws.push_back(mesh.vertexOffset);
+		draws.push_back(static_cast<uint32_t>(mesh.materialIndex));
+		matrices[i].transform = scene.m_nodes[i].worldMatrix;
+		matrices[i].transformInverseTransposed = nvmath::transpose(nvmath::invert(matrices[i].transform));
+	}
+	static_assert(sizeof(shader::ModelMatrices) == 128 && sizeof(shader::MaterialUniforms) == 64);
+	writeFile(out + "/draws.u32", draws.data(), draws.size() * 4);
+	writeFile(out + "/matrices.bin", matrices.data(), matrices.size() * sizeof(shader::ModelMatrices));
+
+	// material uniforms (sceneBuffers.h:205-222; the mapped memory the reference leaves untouched reads as zero here) and
+	// the texture each binding of a material's descriptor set gets (gBufferPass.cpp:200-247; -1 = default white / default normal)
+	std::vector<shader::MaterialUniforms> uniforms(scene.m_materials.size());
+	std::memset(uniforms.data(), 0, uniforms.size() * sizeof(shader::MaterialUniforms));
+	std::vector<int32_t> bindings;
+	for (std::size_t i = 0; i < scene.m_materials.size(); ++i) {
+		const nvh::GltfMaterial &mat = scene.m_materials[i];
+		shader::MaterialUniforms &outMat = uniforms[i];
+		outMat.emissiveFactor = mat.emissiveFactor;
+		outMat.shadingModel = mat.shadingModel;
+		outMat.alphaMode = mat.alphaMode;
+		outMat.alphaCutoff = mat.alphaCutoff;
+		outMat.normalTextureScale = mat.normalTextureScale;
+		switch (outMat.shadingModel) {
+		case SHADING_MODEL_METALLIC_ROUGHNESS:
+			outMat.colorParam = mat.pbrBaseColorFactor;
+			outMat.materialParam.y = mat.pbrRoughnessFactor;
+			outMat.materialParam.z = mat.pbrMetallicFactor;
+			bindings.push_back(mat.pbrBaseColorTexture);
+			bindings.push_back(mat.normalTexture);
+			bindings.push_back(mat.pbrMetallicRoughnessTexture);
+			break;
+		case SHADING_MODEL_SPECULAR_GLOSSINESS:
+			outMat.colorParam = mat.khrDiffuseFactor;
+			outMat.materialParam = mat.khrSpecularFactor;
+			outMat.materialParam.w = mat.khrGlossinessFactor;
+			bindings.push_back(mat.khrDiffuseTexture);
+			bindings.push_back(mat.normalTexture);
+			bindings.push_back(mat.khrSpecularGlossinessTexture);
+			break;
+		default:
+			bindings.insert(bindings.end(), {-1, -1, -1});
+		}
+		bindings.push_back(mat.emissiveTexture);
+	}
+	writeFile(out + "/material_uniforms.bin", uniforms.data(), uniforms.size() * sizeof(shader::MaterialUniforms));
+	writeFile(out + "/material_textures.i32", bindings.data(), bindings.size() * 4);
+
+	// textures: RGBA8 as the reference's loader decodes them (tinygltf + stb_image, 4 components), reduced to <= textureLimit
+	std::vector<uint32_t> index;
+	std::vector<unsigned char> pixels;
+	index.push_back(static_cast<uint32_t>(scene.m_textures.size()));
+	for (const tinygltf::Image &img : scene.m_textures) {
+		int w = img.width, h = img.height;
+		std::vector<unsigned char> cur(img.image.begin(), img.image.end());
+		if (img.component != 4 || img.bits != 8 || cur.size() != std::size_t(w) * h * 4) {
+			std::cerr << "scene_baker: texture " << img.uri << " is not RGBA8 after decoding\n";
+			std::exit(3);
+		}
+		while (std::max(w, h) > textureLimit && w % 2 == 0 && h % 2 == 0) {
+			std::vector<unsigned char> half(std::size_t(w / 2) * (h / 2) * 4);
+			for (int y = 0; y < h / 2; ++y) {
+				for (int x = 0; x < w / 2; ++x) {
+					for (int c = 0; c < 4; ++c) {
+						unsigned s = cur[(std::size_t(2 * y) * w + 2 * x) * 4 + c] + cur[(std::size_t(2 * y) * w + 2 * x + 1) * 4 + c] +
+						             cur[(std::size_t(2 * y + 1) * w + 2 * x) * 4 + c] + cur[(std::size_t(2 * y + 1) * w + 2 * x + 1) * 4 + c];
+						half[(std::size_t(y) * (w / 2) + x) * 4 + c] = static_cast<unsigned char>((s + 2) / 4);
+					}
+				}
+			}
+			cur.swap(half);
+			w /= 2;
+			h /= 2;
+		}
+		index.push_back(static_cast<uint32_t>(w));
+		index.push_back(static_cast<uint32_t>(h));
+		pixels.insert(pixels.end(), cur.begin(), cur.end());
+	}
+	writeFile(out + "/textures.idx", index.data(), index.size() * 4);
+	writeFile(out + "/textures.rgba8", pixels.data(), pixels.size());
 }
 
 static void dumpScene(nvh::GltfScene &scene, const std::string &out) {
@@ -148,11 +272,13 @@ static void dumpScene(nvh::GltfScene &scene, const std::string &out) {
 	);
 }
 
-static int bakeGltf(const std::string &filename, const std::string &out) {
+static int bakeGltf(const std::string &filename, const std::string &out, int textureLimit) {
 	tinygltf::Model tmodel;
 	tinygltf::TinyGLTF tcontext;
 	std::string warn, error;
-	tcontext.SetImageLoader(skipImage, nullptr);
+	if (textureLimit <= 0) {
+		tcontext.SetImageLoader(skipImage, nullptr);
+	}
 	if (!tcontext.LoadASCIIFromFile(&tmodel, &error, &warn, filename)) {
 		std::cerr << "scene_baker: cannot load " << filename << ": " << error << "\n";
 		return 1;
@@ -165,7 +291,13 @@ static int bakeGltf(const std::string &filename, const std::string &out) {
 		nvh::GltfAttributes::Color_0 | nvh::GltfAttributes::Tangent
 	);
 	scene.importMaterials(tmodel);
+	if (textureLimit > 0) {
+		scene.importTexutureImages(tmodel); // src/misc.cpp:319
+	}
 	dumpScene(scene, out);
+	if (textureLimit > 0) {
+		dumpGBufferInputs(scene, out, textureLimit);
+	}
 	return 0;
 }
 
@@ -254,8 +386,8 @@ static int bakeSoup(const std::string &filename, const std::string &out) {
 }
 
 int main(int argc, char **argv) {
-	if (argc == 4 && std::string(argv[1]) == "gltf") {
-		return bakeGltf(argv[2], argv[3]);
+	if ((argc == 4 || argc == 5) && std::string(argv[1]) == "gltf") {
+		return bakeGltf(argv[2], argv[3], argc == 5 ? std::stoi(argv[4]) : 0);
 	}
 	if (argc == 4 && std::string(argv[1]) == "soup") {
 		return bakeSoup(argv[2], argv[3]);
@@ -267,7 +399,7 @@ int main(int argc, char **argv) {
 		writeBlob(argv[9], generateRandomPointLights(n, mn, mx));
 		return 0;
 	}
-	std::cerr << "usage: scene_baker gltf <file.gltf> <outdir> | soup <file.soup> <outdir> | "
+	std::cerr << "usage: scene_baker gltf <file.gltf> <outdir> [texture limit] | soup <file.soup> <outdir> | "
 	             "randlights <n> <min xyz> <max xyz> <out.bin>\n";
 	return 64;
 }

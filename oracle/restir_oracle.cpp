@@ -1059,3 +1059,277 @@ int oracle_num_threads(void) {
 }
 
 } // extern "C"
+// ---------------------------------------------------------------------------------------------
+// The G-buffer pass: CPU twin of restir_pass_gbuffer.  Follows src/shaders/gBuffer.vert:22-34,
+// src/shaders/gBuffer.frag:27-80, src/passes/gBufferPass.cpp:116-157 (clears, draw order, depth test LESS) and
+// src/passes/pass.h:24-40 (back-face culling).  Primary visibility by ray casting, like oracle_raycast_gbuffer.
+// Texture policy: R8G8B8A8_UNORM (sceneBuffers.h:126), repeat wrap, bilinear at level 0, texel = code / 255, the two
+// lerps written out; sRGB attachment encode = largest code whose lower threshold (EOTF of the code midpoint, in double) the
+// value reaches; SNORM16 / UNORM16 = rintf of the clamped value.
+
+namespace {
+struct F4o {
+	float x, y, z, w;
+};
+struct GbTextures {
+	const uint8_t *texels;   // every texture's level 0, RGBA8, back to back
+	const uint32_t *table;   // per texture: first texel, width, height, -
+	int count;
+};
+V3 matMul(const float *m, V3 v, float w) { // column-major mat4 * (v, w), P4
+	return v3(((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * w, ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * w,
+	          ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * w);
+}
+F4o sampleTexture(const GbTextures &tx, int index, bool normalBinding, float u, float v) {
+	if (index < 0 || index >= tx.count) {
+		if (normalBinding) {
+			return F4o{127.0f / 255.0f, 127.0f / 255.0f, 1.0f, 1.0f};
+		}
+		return F4o{1.0f, 1.0f, 1.0f, 1.0f};
+	}
+	const uint32_t *d = tx.table + (size_t)index * 4;
+	const int W = (int)d[1], H = (int)d[2];
+	float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+	if (!(fabsf(x) < 1.0e9f) || !(fabsf(y) < 1.0e9f)) {
+		x = 0.0f;
+		y = 0.0f;
+	}
+	float fx = floorf(x), fy = floorf(y);
+	float ax = x - fx, ay = y - fy;
+	int x0 = (int)fx % W, y0 = (int)fy % H;
+	x0 = x0 < 0 ? x0 + W : x0;
+	y0 = y0 < 0 ? y0 + H : y0;
+	int x1 = x0 + 1 == W ? 0 : x0 + 1, y1 = y0 + 1 == H ? 0 : y0 + 1;
+	const uint8_t *t = tx.texels + (size_t)d[0] * 4;
+	const uint8_t *c00 = t + ((size_t)y0 * W + x0) * 4, *c10 = t + ((size_t)y0 * W + x1) * 4;
+	const uint8_t *c01 = t + ((size_t)y1 * W + x0) * 4, *c11 = t + ((size_t)y1 * W + x1) * 4;
+	float bx = 1.0f - ax, by = 1.0f - ay;
+	float r[4];
+	for (int k = 0; k < 4; ++k) {
+		float top = (float)c00[k] / 255.0f * bx + (float)c10[k] / 255.0f * ax;
+		float bot = (float)c01[k] / 255.0f * bx + (float)c11[k] / 255.0f * ax;
+		r[k] = top * by + bot * ay;
+	}
+	return F4o{r[0], r[1], r[2], r[3]};
+}
+struct SrgbThresholds {
+	float thr[256];
+	SrgbThresholds() {
+		thr[0] = -INFINITY;
+		for (int c = 1; c < 256; ++c) {
+			double e = (c - 0.5) / 255.0;
+			double lin = e <= 0.04045 ? e / 12.92 : pow((e + 0.055) / 1.055, 2.4);
+			float f = (float)lin;
+			if ((double)f < lin) f = nextafterf(f, INFINITY);
+			thr[c] = f;
+		}
+	}
+	uint8_t code(float c) const {
+		int best = 0;
+		for (int k = 255; k >= 1; --k) {
+			if (c >= thr[k]) {
+				best = k;
+				break;
+			}
+		}
+		return (uint8_t)best;
+	}
+};
+} // namespace
+
+extern "C" {
+
+// gBuffer.vert:22-34 per triangle corner, in draw order; out: nTris x 32 floats (N0 u0 | T0 | N1 u1 | T1 | N2 u2 | T2 | v0 v1 v2 - | -)
+void oracle_vertex_stage(const restir_vertex *vertices, const uint32_t *indices, const restir_draw *draws, const restir_model_matrices *matrices,
+                         uint32_t nDraws, float *attrs, int32_t *triMaterial) {
+	size_t t = 0;
+	for (uint32_t d = 0; d < nDraws; ++d) {
+		const restir_draw &dr = draws[d];
+		for (uint32_t i = 0; i < dr.indexCount; i += 3, ++t) {
+			float *o = attrs + t * 32;
+			std::memset(o, 0, 32 * sizeof(float));
+			for (int k = 0; k < 3; ++k) {
+				const restir_vertex &vx = vertices[(size_t)dr.vertexOffset + indices[dr.firstIndex + i + k]];
+				V3 n = normalize(matMul(matrices[d].transformInverseTransposed, v3(vx.normal[0], vx.normal[1], vx.normal[2]), 0.0f));
+				V3 tg = normalize(matMul(matrices[d].transform, v3(vx.tangent[0], vx.tangent[1], vx.tangent[2]), 0.0f));
+				o[8 * k + 0] = n.x; o[8 * k + 1] = n.y; o[8 * k + 2] = n.z; o[8 * k + 3] = vx.uv[0];
+				o[8 * k + 4] = tg.x; o[8 * k + 5] = tg.y; o[8 * k + 6] = tg.z; o[8 * k + 7] = vx.tangent[3];
+				o[24 + k] = vx.uv[1];
+			}
+			triMaterial[t] = dr.materialIndex;
+		}
+	}
+}
+
+void oracle_gbuffer_pass(const oracle_scene *s, const float *attrs, const int32_t *triMaterial, const restir_material_uniforms *uniforms,
+                         const restir_material_textures *bindings, int nMaterials, const uint8_t *texels, const uint32_t *textureTable,
+                         int nTextures, const oracle_camera *c, int W, int H, int y0, int y1, uint8_t *albedoOut, int16_t *normalOut,
+                         uint16_t *materialOut, float *worldPosOut, float *depthOut) {
+	static const SrgbThresholds srgb;
+	const restir_aabb_node *nodes = (const restir_aabb_node *)s->nodes;
+	const restir_triangle *tris = (const restir_triangle *)s->tris;
+	const GbTextures tx{texels, textureTable, nTextures};
+	V3 pos = v3(c->position[0], c->position[1], c->position[2]);
+	V3 fwd = normalize(v3(c->lookAt[0], c->lookAt[1], c->lookAt[2]) - pos);
+	V3 right = normalize(cross(fwd, v3(c->worldUp[0], c->worldUp[1], c->worldUp[2])));
+	V3 up = cross(right, fwd);
+	float f = 1.0f / tanf(0.5f * c->fovYRadians);
+	float sx = c->aspectRatio / f, sy = 1.0f / f;
+	float PV[16];
+	oracle_camera_matrix(c, PV);
+#pragma omp parallel for schedule(dynamic, 1)
+	for (int y = y0; y < y1; ++y) {
+		for (int x = 0; x < W; ++x) {
+			size_t pix = (size_t)y * W + x;
+			float ndcx = (((float)x + 0.5f) / (float)W) * 2.0f - 1.0f;
+			float ndcy = (((float)y + 0.5f) / (float)H) * 2.0f - 1.0f;
+			V3 dir = (fwd + right * (ndcx * sx)) - up * (ndcy * sy);
+			V3 inv = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+			float best = INFINITY, bu = 0, bv = 0;
+			int bestTri = -1;
+			int stack[64], top = 1;
+			stack[0] = 0;
+			while (top > 0) {
+				const restir_aabb_node &node = nodes[stack[--top]];
+				for (int side = 0; side < 2; ++side) {
+					const float *bmin = side ? node.rightAabbMin : node.leftAabbMin;
+					const float *bmax = side ? node.rightAabbMax : node.leftAabbMax;
+					int child = side ? node.rightChild : node.leftChild;
+					V3 t1 = v3((bmin[0] - pos.x) * inv.x, (bmin[1] - pos.y) * inv.y, (bmin[2] - pos.z) * inv.z);
+					V3 t2 = v3((bmax[0] - pos.x) * inv.x, (bmax[1] - pos.y) * inv.y, (bmax[2] - pos.z) * inv.z);
+					float rmin = fmaxf(fminf(t1.x, t2.x), fmaxf(fminf(t1.y, t2.y), fminf(t1.z, t2.z)));
+					float rmax = fminf(fmaxf(t1.x, t2.x), fminf(fmaxf(t1.y, t2.y), fmaxf(t1.z, t2.z)));
+					if (!(rmin <= best && rmax >= rmin && rmax > 0.0f)) {
+						continue;
+					}
+					if (child >= 0) {
+						if (top < 64) {
+							stack[top++] = child;
+						}
+						continue;
+					}
+					int ti = ~child;
+					const restir_triangle &tri = tris[ti];
+					V3 p1 = v3(tri.p1[0], tri.p1[1], tri.p1[2]);
+					V3 e1 = v3(tri.p2[0], tri.p2[1], tri.p2[2]) - p1;
+					V3 e2 = v3(tri.p3[0], tri.p3[1], tri.p3[2]) - p1;
+					if (!(dot(cross(e1, e2), dir) < 0.0f)) { // back-face culling, CCW front (pass.h:24-32)
+						continue;
+					}
+					V3 p = cross(dir, e2);
+					float fdet = 1.0f / dot(e1, p);
+					V3 sv = pos - p1;
+					float u_ = fdet * dot(sv, p);
+					if (u_ < 0.0f || u_ > 1.0f) {
+						continue;
+					}
+					V3 q = cross(sv, e1);
+					float v_ = fdet * dot(dir, q);
+					if (v_ < 0.0f || v_ + u_ > 1.0f) {
+						continue;
+					}
+					float t = fdet * dot(e2, q);
+					if (!(t >= c->zNear && t <= c->zFar) || !(t < best || (t == best && ti < bestTri))) { // clip planes; depth test LESS, earlier draw wins ties
+						continue;
+					}
+					int mi = triMaterial[ti];
+					if (mi >= 0 && mi < nMaterials && uniforms[mi].alphaMode == RESTIR_ALPHA_MODE_MASK) { // gBuffer.frag:29-34
+						const float *at = attrs + (size_t)ti * 32;
+						float w0 = (1.0f - u_) - v_;
+						float uu = (at[3] * w0 + at[11] * u_) + at[19] * v_, vw = (at[24] * w0 + at[25] * u_) + at[26] * v_;
+						float alpha = sampleTexture(tx, bindings[mi].albedo, false, uu, vw).w * uniforms[mi].colorParam[3];
+						if (alpha < uniforms[mi].alphaCutoff) {
+							continue;
+						}
+					}
+					best = t;
+					bestTri = ti;
+					bu = u_;
+					bv = v_;
+				}
+			}
+			uint8_t *a = albedoOut + pix * 4;
+			int16_t *nq = normalOut + pix * 4;
+			uint16_t *m = materialOut + pix * 2;
+			float *wp = worldPosOut + pix * 4;
+			if (bestTri < 0) { // clears: gBufferPass.cpp:117-123
+				a[0] = a[1] = a[2] = 0;
+				a[3] = 255;
+				nq[0] = nq[1] = nq[2] = 0;
+				nq[3] = 32767;
+				m[0] = m[1] = 0;
+				wp[0] = wp[1] = wp[2] = 0.0f;
+				wp[3] = 1.0f;
+				depthOut[pix] = 1.0f;
+				continue;
+			}
+			const restir_triangle &tri = tris[bestTri];
+			const float w0 = (1.0f - bu) - bv, w1 = bu, w2 = bv;
+			V3 hit = (v3(tri.p1[0], tri.p1[1], tri.p1[2]) * w0 + v3(tri.p2[0], tri.p2[1], tri.p2[2]) * w1) + v3(tri.p3[0], tri.p3[1], tri.p3[2]) * w2;
+			const float *at = attrs + (size_t)bestTri * 32;
+			V3 N = (v3(at[0], at[1], at[2]) * w0 + v3(at[8], at[9], at[10]) * w1) + v3(at[16], at[17], at[18]) * w2;
+			V3 T = (v3(at[4], at[5], at[6]) * w0 + v3(at[12], at[13], at[14]) * w1) + v3(at[20], at[21], at[22]) * w2;
+			float Tw = (at[7] * w0 + at[15] * w1) + at[23] * w2;
+			float u = (at[3] * w0 + at[11] * w1) + at[19] * w2, v = (at[24] * w0 + at[25] * w1) + at[26] * w2;
+			int mi = triMaterial[bestTri];
+			restir_material_uniforms mu;
+			std::memset(&mu, 0, sizeof(mu));
+			restir_material_textures mt{-1, -1, -1, -1};
+			if (mi >= 0 && mi < nMaterials) {
+				mu = uniforms[mi];
+				mt = bindings[mi];
+			}
+			F4o tex = sampleTexture(tx, mt.albedo, false, u, v);
+			V3 albedo = v3(tex.x * mu.colorParam[0], tex.y * mu.colorParam[1], tex.z * mu.colorParam[2]);              // :29
+			V3 bitangent = cross(N, T) * Tw;                                                                           // :40
+			F4o nt4 = sampleTexture(tx, mt.normal, true, u * mu.normalTextureScale, v * mu.normalTextureScale);
+			V3 nt = v3(nt4.x * 2.0f - 1.0f, nt4.y * 2.0f - 1.0f, nt4.z * 2.0f - 1.0f);                                 // :41
+			V3 outN = normalize((T * nt.x + bitangent * nt.y) + N * nt.z);                                             // :42
+			F4o mp4 = sampleTexture(tx, mt.material, false, u, v);
+			F4o mp{mp4.x * mu.materialParam[0], mp4.y * mu.materialParam[1], mp4.z * mu.materialParam[2], mp4.w * mu.materialParam[3]}; // :45
+			float roughness = 0.0f, metallic = 0.0f;
+			V3 outAlbedo = albedo;
+			if (mu.shadingModel == RESTIR_SHADING_MODEL_METALLIC_ROUGHNESS) {                                          // :48-50
+				roughness = mp.y;
+				metallic = mp.z;
+			} else if (mu.shadingModel == RESTIR_SHADING_MODEL_SPECULAR_GLOSSINESS) {                                  // :51-67
+				roughness = 1.0f - mp.w;
+				V3 average = (albedo + v3(mp.x, mp.y, mp.z)) * 0.5f;
+				V3 under = average * average - albedo * 0.04f;
+				V3 sqrtTerm = v3(sqrtf(under.x), sqrtf(under.y), sqrtf(under.z));
+				V3 metallicRgb = average * 25.0f - sqrtTerm;
+				metallic = ((metallicRgb.x + metallicRgb.y) + metallicRgb.z) / 3.0f;
+				outAlbedo = average + sqrtTerm;
+			}
+			uint8_t alphaCode = 0;
+			V3 em = v3(mu.emissiveFactor[0], mu.emissiveFactor[1], mu.emissiveFactor[2]);
+			if (sqrtf(dot(em, em)) > 0.0f) {                                                                           // :73-79
+				F4o et = sampleTexture(tx, mt.emissive, false, u, v);
+				outAlbedo = (v3(mu.colorParam[0], mu.colorParam[1], mu.colorParam[2]) * em) * v3(et.x, et.y, et.z);
+				alphaCode = 255;
+			}
+			a[0] = srgb.code(outAlbedo.x);
+			a[1] = srgb.code(outAlbedo.y);
+			a[2] = srgb.code(outAlbedo.z);
+			a[3] = alphaCode;
+			// NaN -> 0 in the fixed-point conversions (NVIDIA / D3D behaviour; Vulkan leaves it open): a zero tangent (MikkTSpace on
+			// degenerate texture coordinates) normalised in gBuffer.vert:30 poisons the normal, which is then stored as (0, 0, 0)
+			nq[0] = outN.x != outN.x ? 0 : (int16_t)rintf(clampf(outN.x, -1.0f, 1.0f) * 32767.0f);
+			nq[1] = outN.y != outN.y ? 0 : (int16_t)rintf(clampf(outN.y, -1.0f, 1.0f) * 32767.0f);
+			nq[2] = outN.z != outN.z ? 0 : (int16_t)rintf(clampf(outN.z, -1.0f, 1.0f) * 32767.0f);
+			nq[3] = 32767;
+			m[0] = (uint16_t)rintf(clampf(roughness, 0.0f, 1.0f) * 65535.0f);
+			m[1] = (uint16_t)rintf(clampf(metallic, 0.0f, 1.0f) * 65535.0f);
+			wp[0] = hit.x;
+			wp[1] = hit.y;
+			wp[2] = hit.z;
+			wp[3] = 1.0f;
+			float cz = ((PV[2] * hit.x + PV[6] * hit.y) + PV[10] * hit.z) + PV[14];
+			float cw = ((PV[3] * hit.x + PV[7] * hit.y) + PV[11] * hit.z) + PV[15];
+			depthOut[pix] = cz / cw;
+		}
+	}
+}
+
+} // extern "C"
+

@@ -61,7 +61,8 @@ assert RESERVOIR_DTYPE.itemsize == 64 and UNIFORMS_DTYPE.itemsize == 128 and LIG
 EXPORTS = [
     "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
-    "restir_upload_gbuffer", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
+    "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
+    "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
     "restir_set_traversal", "restir_set_ray_elision", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
@@ -86,6 +87,10 @@ class BandIpc(C.Structure):
 
 class GBufferPlanes(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("albedo", "normal", "material", "worldPos", "depth")]
+
+
+class Texture(C.Structure):
+    _fields_ = [("rgba8", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -340,6 +345,38 @@ class RestirContext:
             ptrs.append(_hp(a) if isinstance(a, np.ndarray) else _dp(a))
         pl = GBufferPlanes(*ptrs)
         self._check(self.lib.restir_upload_gbuffer(self._ctx, C.c_int(slot), C.c_int(0), C.byref(pl)))
+
+    # ---- the G-buffer pass (include/restir_b200.h) ----
+    def upload_geometry(self, vertices, indices, draws, matrices):
+        """vertices (V,80)u8, indices (I,)u32, draws (D,4)u32 {firstIndex, indexCount, vertexOffset, materialIndex}, matrices (D,128)u8."""
+        v = np.ascontiguousarray(vertices).view(np.uint8).reshape(-1, 80)
+        i = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        d = np.ascontiguousarray(draws).view(np.uint32).reshape(-1, 4)
+        m = np.ascontiguousarray(matrices).view(np.uint8).reshape(-1, 128)
+        assert d.shape[0] == m.shape[0]
+        self._check(self.lib.restir_upload_geometry(self._ctx, _hp(v), C.c_uint64(v.shape[0]), _hp(i), C.c_uint64(i.shape[0]), _hp(d), _hp(m),
+                                                    C.c_uint32(d.shape[0])))
+
+    def upload_materials(self, uniforms, bindings, textures):
+        """uniforms (M,64)u8, bindings (M,4)i32, textures: list of (h,w,4)u8 arrays (R8G8B8A8_UNORM, level 0)."""
+        u = np.ascontiguousarray(uniforms).view(np.uint8).reshape(-1, 64)
+        b = np.ascontiguousarray(bindings, np.int32).reshape(-1, 4)
+        keep = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        arr = (Texture * max(len(keep), 1))()
+        for k, t in enumerate(keep):
+            assert t.ndim == 3 and t.shape[2] == 4
+            arr[k] = Texture(t.ctypes.data, t.shape[1], t.shape[0])
+        self._check(self.lib.restir_upload_materials(self._ctx, _hp(u), _hp(b), C.c_uint32(u.shape[0]), arr if keep else None,
+                                                     C.c_uint32(len(keep))))
+
+    def pass_gbuffer(self, slot, cam):
+        self._check(self.lib.restir_pass_gbuffer(self._ctx, C.c_int(slot), C.byref(cam)))
+
+    def gbuffer_device_planes(self, slot):
+        """Device pointers (ints) of the context-owned planes of `slot`: albedo, normal, material, worldPos, depth."""
+        pl = GBufferPlanes()
+        self._check(self.lib.restir_gbuffer_device_planes(self._ctx, C.c_int(slot), C.byref(pl)))
+        return [pl.albedo, pl.normal, pl.material, pl.worldPos, pl.depth]
 
     def set_uniforms(self, uniforms):
         u = np.ascontiguousarray(uniforms)

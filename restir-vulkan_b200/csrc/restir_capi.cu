@@ -39,6 +39,16 @@ struct restir_context {
 	float4 *pointPosLum = nullptr, *triAux = nullptr;
 	int pointCount = 0, triCount = 0, aliasCount = 0;
 	float *srgbLut = nullptr;
+	// the G-buffer pass's scene (restir_upload_geometry / restir_upload_materials)
+	float4 *gbAttrs = nullptr;
+	int *gbTriMaterial = nullptr;
+	uint32_t gbTris = 0;
+	restir_material_uniforms *gbUniforms = nullptr;
+	restir_material_textures *gbBindings = nullptr;
+	uchar4 *gbTexels = nullptr;
+	uint4 *gbTextureTable = nullptr;
+	float *gbSrgbThresholds = nullptr;
+	int gbMaterials = 0, gbTextures = 0;
 
 	// screen
 	Band band{0, 0, 0, 0, 0, 0};
@@ -361,6 +371,49 @@ TraceParams traceParams(const restir_context *ctx) {
 
 } // namespace
 
+namespace {
+template <typename T> int uploadArray(restir_context *ctx, T *&dst, const T *src, size_t n, const char *what) {
+	freeDev(dst);
+	if (n == 0) {
+		return RESTIR_OK;
+	}
+	int rc = cudaCheck(ctx, cudaMalloc(&dst, n * sizeof(T)), what);
+	if (rc != RESTIR_OK) return rc;
+	return cudaCheck(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream), what);
+}
+
+
+struct H3 {
+	float x, y, z;
+};
+inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float hdot(H3 a, H3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return H3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline H3 hnorm(H3 v) {
+	float inv = 1.0f / sqrtf(hdot(v, v));
+	return H3{v.x * inv, v.y * inv, v.z * inv};
+}
+void cameraBasis(const restir_camera *c, H3 &pos, H3 &fwd, H3 &right, H3 &up) { // camera.h:25-28
+	pos = H3{c->position[0], c->position[1], c->position[2]};
+	fwd = hnorm(hsub(H3{c->lookAt[0], c->lookAt[1], c->lookAt[2]}, pos));
+	right = hnorm(hcross(fwd, H3{c->worldUp[0], c->worldUp[1], c->worldUp[2]}));
+	up = hcross(right, fwd);
+}
+
+void cameraBasisOf(const restir_camera *camera, RaycastCamera &rc) {
+	H3 pos, fwd, right, up;
+	cameraBasis(camera, pos, fwd, right, up);
+	float f = 1.0f / tanf(0.5f * camera->fovYRadians);
+	rc.pos[0] = pos.x; rc.pos[1] = pos.y; rc.pos[2] = pos.z;
+	rc.fwd[0] = fwd.x; rc.fwd[1] = fwd.y; rc.fwd[2] = fwd.z;
+	rc.right[0] = right.x; rc.right[1] = right.y; rc.right[2] = right.z;
+	rc.up[0] = up.x; rc.up[1] = up.y; rc.up[2] = up.z;
+	rc.sx = camera->aspectRatio / f;
+	rc.sy = 1.0f / f;
+	restir_camera_matrix(camera, rc.pv);
+}
+} // namespace
+
 extern "C" {
 
 int restir_create(restir_context **out, int device, void *stream) {
@@ -393,6 +446,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		if ((rc = cudaCheck(ctx, preload_pixel_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_trace_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_gbuffer_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->haloTicket, sizeof(unsigned)), "cudaMalloc halo ticket")) != RESTIR_OK) break;
@@ -449,6 +503,13 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->pointPosLum);
 	freeDev(ctx->triAux);
 	freeDev(ctx->srgbLut);
+	freeDev(ctx->gbAttrs);
+	freeDev(ctx->gbTriMaterial);
+	freeDev(ctx->gbUniforms);
+	freeDev(ctx->gbBindings);
+	freeDev(ctx->gbTexels);
+	freeDev(ctx->gbTextureTable);
+	freeDev(ctx->gbSrgbThresholds);
 	freeDev(ctx->staging);
 	freeDev(ctx->counters);
 	for (auto &r : ctx->reservoirs) {
@@ -497,6 +558,9 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	freeDev(ctx->treeBlock);
 	ctx->image = ctx->triEdges = nullptr;
 	ctx->nNodes = ctx->nTris = 0;
+	freeDev(ctx->gbAttrs); // per-triangle attributes belong to the previous triangle list
+	freeDev(ctx->gbTriMaterial);
+	ctx->gbTris = 0;
 	const bool useImage = info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
 	const size_t triBytes = (size_t)n_triangles * sizeof(restir_triangle);
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
@@ -686,6 +750,174 @@ int restir_upload_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format f
 	int rc = restir_bind_gbuffer(ctx, slot, format, &dev);
 	ctx->uploadPending[slot] = rc == RESTIR_OK;
 	return rc;
+}
+
+// ---- the G-buffer pass -----------------------------------------------------------------------------------------------
+
+int restir_upload_geometry(restir_context *ctx, const restir_vertex *vertices, uint64_t n_vertices, const uint32_t *indices, uint64_t n_indices,
+                           const restir_draw *draws, const restir_model_matrices *matrices, uint32_t n_draws) {
+	ENTER(ctx);
+	if (ctx->nodes == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_geometry: call restir_upload_bvh first (the draws' triangles are the tree's triangles)");
+	}
+	if (!vertices || !indices || !draws || !matrices || n_vertices == 0 || n_indices == 0 || n_draws == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_geometry: empty geometry");
+	}
+	// the draws, validated (the kernels trust them), and which draw every triangle belongs to
+	std::vector<uint32_t> triDraw, drawFirstTri(n_draws);
+	std::vector<int> triMaterial;
+	for (uint32_t d = 0; d < n_draws; ++d) {
+		const restir_draw &dr = draws[d];
+		if (dr.indexCount % 3 != 0 || (uint64_t)dr.firstIndex + dr.indexCount > n_indices) {
+			return fail(ctx, RESTIR_E_INVALID, "restir_upload_geometry: draw %u reads indices [%u, %u + %u) of %llu", d, dr.firstIndex, dr.firstIndex,
+			            dr.indexCount, (unsigned long long)n_indices);
+		}
+		for (uint32_t i = 0; i < dr.indexCount; ++i) {
+			if ((uint64_t)dr.vertexOffset + indices[dr.firstIndex + i] >= n_vertices) {
+				return fail(ctx, RESTIR_E_INVALID, "restir_upload_geometry: draw %u addresses vertex %llu of %llu", d,
+				            (unsigned long long)dr.vertexOffset + indices[dr.firstIndex + i], (unsigned long long)n_vertices);
+			}
+		}
+		drawFirstTri[d] = (uint32_t)triDraw.size();
+		triDraw.insert(triDraw.end(), dr.indexCount / 3, d);
+		triMaterial.insert(triMaterial.end(), dr.indexCount / 3, dr.materialIndex);
+	}
+	if (triDraw.size() != ctx->nTris) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_geometry: the draws make %zu triangles, the uploaded tree has %u", triDraw.size(), ctx->nTris);
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	restir_vertex *dV = nullptr;
+	uint32_t *dI = nullptr, *dTriDraw = nullptr, *dFirst = nullptr;
+	restir_draw *dD = nullptr;
+	restir_model_matrices *dM = nullptr;
+	int rc = RESTIR_OK;
+	do {
+		if ((rc = uploadArray(ctx, dV, vertices, (size_t)n_vertices, "vertices")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, dI, indices, (size_t)n_indices, "indices")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, dD, draws, (size_t)n_draws, "draws")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, dM, matrices, (size_t)n_draws, "matrices")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, dTriDraw, triDraw.data(), triDraw.size(), "triangle -> draw")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, dFirst, drawFirstTri.data(), drawFirstTri.size(), "draw -> first triangle")) != RESTIR_OK) break;
+		if ((rc = uploadArray(ctx, ctx->gbTriMaterial, triMaterial.data(), triMaterial.size(), "triangle materials")) != RESTIR_OK) break;
+		freeDev(ctx->gbAttrs);
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->gbAttrs, (size_t)ctx->nTris * 8 * sizeof(float4)), "triangle attributes")) != RESTIR_OK) break;
+		beforeLaunch(ctx, "vertex_stage_kernel"); // gBuffer.vert, once per upload
+		launch_vertex_stage(dV, dI, dD, dM, dTriDraw, dFirst, ctx->nTris, ctx->gbAttrs, ctx->stream);
+		if ((rc = afterLaunch(ctx, "vertex_stage_kernel")) != RESTIR_OK) break;
+		rc = cudaCheck(ctx, cudaStreamSynchronize(ctx->stream), "vertex stage");
+	} while (false);
+	freeDev(dV);
+	freeDev(dI);
+	freeDev(dD);
+	freeDev(dM);
+	freeDev(dTriDraw);
+	freeDev(dFirst);
+	ctx->gbTris = rc == RESTIR_OK ? ctx->nTris : 0;
+	return rc;
+}
+
+int restir_upload_materials(restir_context *ctx, const restir_material_uniforms *uniforms, const restir_material_textures *bindings,
+                            uint32_t n_materials, const restir_texture *textures, uint32_t n_textures) {
+	ENTER(ctx);
+	if (!uniforms || !bindings || n_materials == 0 || (n_textures != 0 && textures == nullptr)) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_upload_materials: no materials");
+	}
+	std::vector<uint4> table(n_textures);
+	size_t texels = 0;
+	for (uint32_t t = 0; t < n_textures; ++t) {
+		if (textures[t].rgba8 == nullptr || textures[t].width == 0 || textures[t].height == 0 || textures[t].width > 32768 || textures[t].height > 32768) {
+			return fail(ctx, RESTIR_E_INVALID, "restir_upload_materials: texture %u is empty or larger than 32768 texels a side", t);
+		}
+		if (texels > 0xffffffffull) {
+			return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_upload_materials: more than 2^32 texels");
+		}
+		table[t] = make_uint4((unsigned)texels, textures[t].width, textures[t].height, 0u);
+		texels += (size_t)textures[t].width * textures[t].height;
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	int rc;
+	if ((rc = uploadArray(ctx, ctx->gbUniforms, uniforms, n_materials, "material uniforms")) != RESTIR_OK) return rc;
+	if ((rc = uploadArray(ctx, ctx->gbBindings, bindings, n_materials, "material textures")) != RESTIR_OK) return rc;
+	if ((rc = uploadArray(ctx, ctx->gbTextureTable, table.data(), table.size(), "texture table")) != RESTIR_OK) return rc;
+	freeDev(ctx->gbTexels);
+	if (texels) {
+		CU(ctx, cudaMalloc(&ctx->gbTexels, texels * sizeof(uchar4)));
+		for (uint32_t t = 0; t < n_textures; ++t) {
+			CU(ctx, cudaMemcpyAsync(ctx->gbTexels + table[t].x, textures[t].rgba8, (size_t)table[t].y * table[t].z * 4, cudaMemcpyHostToDevice, ctx->stream));
+		}
+	}
+	if (ctx->gbSrgbThresholds == nullptr) {
+		// the smallest float that an R8G8B8A8_SRGB attachment stores as code c (round to nearest in the encoded domain): the
+		// EOTF of the midpoint between codes c - 1 and c, in double, rounded up to float
+		float thr[256];
+		thr[0] = -INFINITY;
+		for (int c = 1; c < 256; ++c) {
+			double e = (c - 0.5) / 255.0;
+			double lin = e <= 0.04045 ? e / 12.92 : std::pow((e + 0.055) / 1.055, 2.4);
+			float f = (float)lin;
+			if ((double)f < lin) f = std::nextafterf(f, INFINITY);
+			thr[c] = f;
+		}
+		float *d = nullptr;
+		if ((rc = uploadArray(ctx, d, thr, 256, "sRGB thresholds")) != RESTIR_OK) return rc;
+		ctx->gbSrgbThresholds = d;
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->gbMaterials = (int)n_materials;
+	ctx->gbTextures = (int)n_textures;
+	return RESTIR_OK;
+}
+
+int restir_pass_gbuffer(restir_context *ctx, int slot, const restir_camera *camera) {
+	ENTER(ctx);
+	if (slot < 0 || slot > 1 || camera == nullptr || ctx->band.W == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_pass_gbuffer: bad slot, null camera or restir_resize not called");
+	}
+	if (ctx->nodes == nullptr || ctx->gbAttrs == nullptr || ctx->gbTris != ctx->nTris || ctx->gbUniforms == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_pass_gbuffer: upload the BVH, the geometry (restir_upload_geometry) and the materials (restir_upload_materials) first");
+	}
+	// the planes are the context's: allocated on first use, bound to the slot like restir_upload_gbuffer's.  An upload still in
+	// flight into them (copy stream) is ordered before this pass.
+	int rc;
+	if ((rc = waitUpload(ctx, slot)) != RESTIR_OK) return rc;
+	const size_t px = ctx->allocPixels();
+	for (int k = 0; k < 5; ++k) {
+		if (ctx->ownedPlanes[slot][k] == nullptr) {
+			CU(ctx, cudaMalloc(&ctx->ownedPlanes[slot][k], px * kPlaneBytes[k]));
+		}
+	}
+	RaycastCamera cam;
+	cameraBasisOf(camera, cam);
+	GBufferScene g{};
+	g.attrs = ctx->gbAttrs;
+	g.triMaterial = ctx->gbTriMaterial;
+	g.uniforms = ctx->gbUniforms;
+	g.bindings = ctx->gbBindings;
+	g.texels = ctx->gbTexels;
+	g.textureTable = ctx->gbTextureTable;
+	g.srgbThresholds = ctx->gbSrgbThresholds;
+	g.nMaterials = ctx->gbMaterials;
+	g.nTextures = ctx->gbTextures;
+	Band full = ctx->band; // every row the context holds: the reuse passes gather from the halo rows
+	full.rowBegin = full.allocBegin;
+	full.rowEnd = full.allocEnd;
+	beforeLaunch(ctx, "gbuffer_kernel");
+	launch_gbuffer(sceneView(ctx), g, full, cam, camera->zNear, camera->zFar, ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1],
+	               ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3], ctx->ownedPlanes[slot][4], ctx->stream);
+	if ((rc = afterLaunch(ctx, "gbuffer_kernel")) != RESTIR_OK) return rc;
+	restir_gbuffer_planes dev{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],
+	                          ctx->ownedPlanes[slot][4]};
+	return restir_bind_gbuffer(ctx, slot, RESTIR_GBUFFER_NVIDIA_DEFAULT, &dev);
+}
+
+int restir_gbuffer_device_planes(restir_context *ctx, int slot, restir_gbuffer_planes *out) {
+	ENTER(ctx);
+	if (slot < 0 || slot > 1 || out == nullptr || ctx->ownedPlanes[slot][0] == nullptr) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_gbuffer_device_planes: slot %d has no context-owned planes", slot);
+	}
+	*out = restir_gbuffer_planes{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],
+	                             ctx->ownedPlanes[slot][4]};
+	return RESTIR_OK;
 }
 
 int restir_set_uniforms(restir_context *ctx, const restir_uniforms *u) {
@@ -1225,25 +1457,6 @@ int restir_profile_end(restir_context *ctx, restir_kernel_time *out, uint32_t ca
 
 // ---- fixture tool ------------------------------------------------------------------------------
 
-namespace {
-struct H3 {
-	float x, y, z;
-};
-inline H3 hsub(H3 a, H3 b) { return H3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline float hdot(H3 a, H3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-inline H3 hcross(H3 a, H3 b) { return H3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
-inline H3 hnorm(H3 v) {
-	float inv = 1.0f / sqrtf(hdot(v, v));
-	return H3{v.x * inv, v.y * inv, v.z * inv};
-}
-void cameraBasis(const restir_camera *c, H3 &pos, H3 &fwd, H3 &right, H3 &up) { // camera.h:25-28
-	pos = H3{c->position[0], c->position[1], c->position[2]};
-	fwd = hnorm(hsub(H3{c->lookAt[0], c->lookAt[1], c->lookAt[2]}, pos));
-	right = hnorm(hcross(fwd, H3{c->worldUp[0], c->worldUp[1], c->worldUp[2]}));
-	up = hcross(right, fwd);
-}
-} // namespace
-
 int restir_camera_matrix(const restir_camera *c, float out_pv[16]) {
 	if (c == nullptr || out_pv == nullptr) {
 		return RESTIR_E_INVALID;
@@ -1280,16 +1493,7 @@ int restir_tools_raycast_gbuffer(restir_context *ctx, const restir_camera *camer
 		return fail(ctx, RESTIR_E_INVALID, "raycast: null argument");
 	}
 	RaycastCamera rc;
-	H3 pos, fwd, right, up;
-	cameraBasis(camera, pos, fwd, right, up);
-	float f = 1.0f / tanf(0.5f * camera->fovYRadians);
-	rc.pos[0] = pos.x; rc.pos[1] = pos.y; rc.pos[2] = pos.z;
-	rc.fwd[0] = fwd.x; rc.fwd[1] = fwd.y; rc.fwd[2] = fwd.z;
-	rc.right[0] = right.x; rc.right[1] = right.y; rc.right[2] = right.z;
-	rc.up[0] = up.x; rc.up[1] = up.y; rc.up[2] = up.z;
-	rc.sx = camera->aspectRatio / f;
-	rc.sy = 1.0f / f;
-	restir_camera_matrix(camera, rc.pv);
+	cameraBasisOf(camera, rc);
 	Band full = ctx->band; // the fixture covers every row the context holds, halo included
 	full.rowBegin = full.allocBegin;
 	full.rowEnd = full.allocEnd;

@@ -68,6 +68,23 @@ void launch_derive_triangle_edges(const float4 *tris, uint32_t n, float4 *out, c
 void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
                                 cudaStream_t s);
 
+// ---- the G-buffer pass (restir_gbuffer.cu) ------------------------------------------------------------------------
+struct GBufferScene {
+	const float4 *attrs;                       // per triangle, 8 x float4: what gBuffer.vert hands to the rasteriser (vertex_stage_kernel)
+	const int *triMaterial;                    // per triangle: the material index of its draw
+	const restir_material_uniforms *uniforms;  // per material
+	const restir_material_textures *bindings;  // per material
+	const uchar4 *texels;                      // every texture's level 0, back to back
+	const uint4 *textureTable;                 // per texture: (first texel, width, height, -)
+	const float *srgbThresholds;               // 256 floats: the smallest value that encodes to each 8-bit sRGB code
+	int nMaterials, nTextures;
+};
+void launch_vertex_stage(const restir_vertex *vertices, const uint32_t *indices, const restir_draw *draws, const restir_model_matrices *matrices,
+                         const uint32_t *triDraw, const uint32_t *drawFirstTri, uint32_t nTris, float4 *attrs, cudaStream_t s);
+void launch_gbuffer(const SceneView &sc, const GBufferScene &g, const Band &band, const RaycastCamera &cam, float zNear, float zFar, void *albedo,
+                    void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
+cudaError_t preload_gbuffer_kernels();
+
 // ---- halo exchange over peer memory (restir_halo.cu) ----------------------------------------------------------
 // side 0 = the neighbour that owns the rows above this band, side 1 = the rows below.
 struct HaloPush {

@@ -104,6 +104,113 @@ def with_point_lights(scene, positions, colours):
                      scene.ref)
 
 
+# ---- what the G-buffer pass binds ------------------------------------------------------------------------
+
+class GBufferPassInputs:
+    """Vertices, indices, draws, matrices, material uniforms, texture bindings and textures in the reference's layouts
+    (include/restir_layouts.h): the arguments of restir_upload_geometry / restir_upload_materials."""
+
+    def __init__(self, vertices, indices, draws, matrices, uniforms, bindings, textures):
+        self.vertices, self.indices, self.draws, self.matrices = vertices, indices, draws, matrices
+        self.uniforms, self.bindings, self.textures = uniforms, bindings, textures
+
+    def upload(self, ctx):
+        ctx.upload_geometry(self.vertices, self.indices, self.draws, self.matrices)
+        ctx.upload_materials(self.uniforms, self.bindings, self.textures)
+
+
+def gbuffer_inputs_available(name):
+    return os.path.exists(os.path.join(BAKED_DIR, name, "vertices.bin"))
+
+
+def load_gbuffer_inputs(name):
+    """scenes/_baked/<name>: what SceneBuffers / GBufferPass bind, dumped by oracle/_ref/scene_baker from the reference's own
+    loader (textures reduced to <= 256 texels a side by the baker, to keep the snapshot small)."""
+    d = os.path.join(BAKED_DIR, name)
+    f = lambda n, dt: np.fromfile(os.path.join(d, n), dtype=dt)
+    idx = f("textures.idx", np.uint32)
+    texels = f("textures.rgba8", np.uint8)
+    textures, first = [], 0
+    for k in range(int(idx[0])):
+        w, h = int(idx[1 + 2 * k]), int(idx[2 + 2 * k])
+        textures.append(texels[first: first + w * h * 4].reshape(h, w, 4))
+        first += w * h * 4
+    return GBufferPassInputs(f("vertices.bin", np.uint8).reshape(-1, 80), f("indices.u32", np.uint32), f("draws.u32", np.uint32).reshape(-1, 4),
+                             f("matrices.bin", np.uint8).reshape(-1, 128), f("material_uniforms.bin", np.uint8).reshape(-1, 64),
+                             f("material_textures.i32", np.int32).reshape(-1, 4), textures)
+
+
+def procedural_gbuffer_inputs(scene, seed=1, texture_size=32):
+    """G-buffer pass inputs for a procedural scene (make_procedural): unshared vertices with smooth-ish normals, tangents and
+    texture coordinates, one draw per run of equal material ids under a non-trivial model matrix pair, random textures, one
+    alpha-masked material and one specular-glossiness material — every branch of gBuffer.frag gets pixels."""
+    rng = np.random.default_rng(seed)
+    tris = scene.triangles.view(np.float32).reshape(-1, 3, 4)[:, :, :3]
+    n_tris = tris.shape[0]
+    e1, e2 = tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+    fn = np.cross(e1, e2)
+    fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-20)
+    verts = np.zeros((n_tris * 3, 20), np.float32)
+    pos = tris.reshape(-1, 3)
+    verts[:, 0:3] = pos
+    verts[:, 3] = 1.0
+    nrm = np.repeat(fn, 3, axis=0) + rng.uniform(-0.15, 0.15, (n_tris * 3, 3)).astype(np.float32)   # perturbed: interpolation matters
+    verts[:, 4:7] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    tang = np.repeat(e1 / np.maximum(np.linalg.norm(e1, axis=1, keepdims=True), 1e-20), 3, axis=0)
+    verts[:, 8:11] = tang
+    verts[:, 11] = np.where(rng.uniform(size=n_tris * 3) < 0.5, -1.0, 1.0)
+    verts[:, 12:16] = 1.0
+    verts[:, 16:18] = pos[:, [0, 2]] * 0.37 + pos[:, [1]] * 0.21                                      # world-space planar mapping
+    # draws: runs of equal material; the model matrix is the identity for positions' sake (the tree holds world-space
+    # triangles) but the normal matrix is exercised with a non-uniform scale pair that cancels for normals: M = S, MIT = S^-T = S^-1
+    mats = scene.tri_material
+    draws, matrices = [], []
+    t = 0
+    while t < n_tris:
+        e = t
+        while e < n_tris and mats[e] == mats[t]:
+            e += 1
+        draws.append((t * 3, (e - t) * 3, 0, int(mats[t])))
+        m = np.zeros((2, 4, 4), np.float32)
+        m[0] = np.eye(4, dtype=np.float32)
+        m[1] = np.eye(4, dtype=np.float32)
+        matrices.append(m.reshape(-1))
+        t = e
+    indices = np.arange(n_tris * 3, dtype=np.uint32)
+    n_mat = scene.materials.shape[0]
+    uniforms = np.zeros((n_mat, 16), np.float32)
+    for i, row in enumerate(scene.materials):
+        uniforms[i, 0:4] = row[0:4]
+        uniforms[i, 4:8] = row[4:8]
+        uniforms[i, 8:11] = row[8:11]
+        uniforms[i, 15] = 1.0 + 0.5 * (i % 3)                                                         # normalTextureScale
+    uniforms_i = uniforms.view(np.int32)
+    for i, row in enumerate(scene.materials):
+        uniforms_i[i, 12] = int(row[11])
+        uniforms_i[i, 13] = int(row[12])
+        uniforms[i, 14] = row[13]
+    if n_mat > 6:
+        uniforms_i[5, 13] = 1                                                                         # ALPHA_MODE_MASK, cutoff 0.5: holes from the texture's alpha
+        uniforms[5, 14] = 0.5
+        uniforms_i[6, 12] = 1                                                                         # specular-glossiness
+        uniforms[6, 4:8] = (0.6, 0.5, 0.4, 0.7)
+    textures = []
+    for k in range(6):
+        t_ = rng.integers(0, 256, (texture_size, texture_size * (1 + k % 2), 4), dtype=np.uint8)
+        if k == 1:
+            t_[..., 0:2] = rng.integers(96, 160, t_[..., 0:2].shape, dtype=np.uint8)                  # a plausible normal map
+            t_[..., 2] = 255
+        textures.append(t_)
+    bindings = np.full((n_mat, 4), -1, np.int32)
+    for i in range(n_mat):
+        if i % 2 == 0:
+            bindings[i] = (0 + (i % 3) * 2 % 6, 1, 2, 3)
+    if n_mat > 5:
+        bindings[5] = (4, -1, -1, -1)
+    return GBufferPassInputs(verts.view(np.uint8).reshape(-1, 80), indices, np.asarray(draws, np.uint32), np.asarray(matrices, np.float32).view(np.uint8).reshape(-1, 128),
+                             uniforms.view(np.uint8).reshape(-1, 64), bindings, textures)
+
+
 # ---- material -> G-buffer codes (src/shaders/gBuffer.frag:27-79 with all textures = 1) -------------
 
 def _srgb_encode8(c):

@@ -163,6 +163,25 @@ public:
 	}
 };
 
+// GBufferPass (gBufferPass.h / gBufferPass.cpp:116-157): scene / sceneBuffers / descriptorSets -> the geometry and materials
+// uploaded once (restir_upload_geometry, restir_upload_materials); the uniform's projectionViewMatrix -> the camera it is made of
+class GBufferPass {
+public:
+	int gBuffer = 0;
+	restir_camera camera{};
+
+	static void uploadScene(const Device &dev, const std::vector<restir_vertex> &vertices, const std::vector<uint32_t> &indices,
+	                        const std::vector<restir_draw> &draws, const std::vector<restir_model_matrices> &matrices,
+	                        const std::vector<restir_material_uniforms> &materials, const std::vector<restir_material_textures> &bindings,
+	                        const std::vector<restir_texture> &textures) {
+		dev.check(restir_upload_geometry(dev.get(), vertices.data(), vertices.size(), indices.data(), indices.size(), draws.data(), matrices.data(),
+		                                 (uint32_t)draws.size()));
+		dev.check(restir_upload_materials(dev.get(), materials.data(), bindings.data(), (uint32_t)materials.size(), textures.data(),
+		                                  (uint32_t)textures.size()));
+	}
+	void issueCommands(const Device &dev) const { dev.check(restir_pass_gbuffer(dev.get(), gBuffer, &camera)); }
+};
+
 // LightingPass (lightingPass.h): descriptorSet -> {gBuffer, reservoirs}; the framebuffer becomes a device image
 class LightingPass {
 public:
