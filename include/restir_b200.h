@@ -65,6 +65,15 @@ int restir_synchronize(restir_context *ctx);
  * (src/passes/restirPass.h:221-237).  Bytes exactly as AabbTree::build produces them: n_nodes x 80, n_tris x 48. */
 int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles);
 
+/* Replaces: AabbTree::build (src/aabbTreeBuilder.cpp:52-214) + AabbTreeBuffers::create in one call, ON THE DEVICE
+ * (rebuild for dynamic geometry): uploads the n x 48-byte world-space triangles (HOST pointer, the
+ * reference's order), builds the tree with the library's kernels — the reference's breadth-first build one queue generation
+ * per round of launches, byte-identical to restir_build_aabb_tree and to the reference's own output — and installs it as the
+ * context's tree like restir_upload_bvh.  nodes_out: NULL, or HOST memory for the (n - 1) x 80-byte nodes.
+ * restir_get_bvh_info then reports depth and upper bounds of the stack occupancies.  RESTIR_E_UNSUPPORTED for non-finite
+ * coordinates (build those on the host). */
+int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t n_triangles, void *nodes_out);
+
 /* Replaces: the three light SSBOs of SceneBuffers (src/sceneBuffers.h:100-124, 241-270) +
  * initializeStaticDescriptorSetFor (restirPass.h:120-150).  Blobs = {int32 count; pad to 16; array}. */
 int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t point_bytes, const void *tri_blob,

@@ -59,7 +59,7 @@ assert RESERVOIR_DTYPE.itemsize == 64 and UNIFORMS_DTYPE.itemsize == 128 and LIG
 
 # every symbol include/restir_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh",
+    "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh", "restir_build_bvh_device",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
     "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
@@ -309,6 +309,13 @@ class RestirContext:
         nodes = np.ascontiguousarray(nodes).view(np.uint8).reshape(-1, 80)
         tris = np.ascontiguousarray(triangles).view(np.uint8).reshape(-1, 48)
         self._check(self.lib.restir_upload_bvh(self._ctx, _hp(nodes), C.c_uint32(nodes.shape[0]), _hp(tris), C.c_uint32(tris.shape[0])))
+
+    def build_bvh_device(self, triangles, want_nodes=True):
+        """restir_build_bvh_device: AabbTree::build on the GPU; returns the (T-1,80)u8 nodes when want_nodes."""
+        tris = np.ascontiguousarray(triangles).view(np.uint8).reshape(-1, 48)
+        nodes = np.zeros((tris.shape[0] - 1, 80), np.uint8) if want_nodes else None
+        self._check(self.lib.restir_build_bvh_device(self._ctx, _hp(tris), C.c_uint32(tris.shape[0]), _hp(nodes) if want_nodes else None))
+        return nodes
 
     def upload_lights(self, point_blob, tri_blob, alias_blob):
         pb, tb, ab = (np.ascontiguousarray(b, np.uint8) for b in (point_blob, tri_blob, alias_blob))

@@ -447,6 +447,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		if ((rc = cudaCheck(ctx, preload_trace_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_gbuffer_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_bvh_build_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->haloTicket, sizeof(unsigned)), "cudaMalloc halo ticket")) != RESTIR_OK) break;
@@ -581,6 +582,76 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->nNodes = n_nodes;
+	ctx->nTris = n_triangles;
+	ctx->imageInfo = info;
+	return RESTIR_OK;
+}
+
+int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t n_triangles, void *nodes_out) {
+	ENTER(ctx);
+	if (triangles == nullptr || n_triangles < 2) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_build_bvh_device: at least two triangles (the reference asserts on one, aabbTreeBuilder.cpp:212)");
+	}
+	if (n_triangles > (1u << 30)) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_build_bvh_device: more than 2^30 triangles");
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	freeDev(ctx->nodes);
+	freeDev(ctx->tris);
+	freeDev(ctx->treeBlock);
+	ctx->image = ctx->triEdges = nullptr;
+	ctx->nNodes = ctx->nTris = 0;
+	freeDev(ctx->gbAttrs);
+	freeDev(ctx->gbTriMaterial);
+	ctx->gbTris = 0;
+	const uint32_t nNodes = n_triangles - 1;
+	const size_t triBytes = (size_t)n_triangles * sizeof(restir_triangle);
+	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)nNodes * sizeof(restir_aabb_node)));
+	CU(ctx, cudaMalloc(&ctx->tris, triBytes));
+	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, triBytes, cudaMemcpyHostToDevice, ctx->stream));
+	void *scratch = nullptr;
+	CU(ctx, cudaMalloc(&scratch, bvh_build_scratch_bytes(n_triangles)));
+	int levels = 0;
+	unsigned nonFinite = 0;
+	beforeLaunch(ctx, "bvh_build (all kernels)");
+	cudaError_t e = build_aabb_tree_device(ctx->tris, n_triangles, reinterpret_cast<restir_aabb_node *>(ctx->nodes), scratch, &levels, &nonFinite,
+	                                       ctx->stream);
+	int rc = afterLaunch(ctx, "bvh_build (all kernels)");
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(scratch);
+	if (e != cudaSuccess) return cudaCheck(ctx, e, "restir_build_bvh_device");
+	if (rc != RESTIR_OK) return rc;
+	if (nonFinite != 0) {
+		freeDev(ctx->nodes);
+		freeDev(ctx->tris);
+		return fail(ctx, RESTIR_E_UNSUPPORTED,
+		            "restir_build_bvh_device: %u non-finite vertex coordinates (the reference's min / max folds depend on the order NaN is met in: "
+		            "build such input with restir_build_aabb_tree on the host)", nonFinite);
+	}
+	// a tree built here is a tree over [0, n) by construction; a walk in any order holds at most one pending sibling per level
+	TraversalImageInfo info;
+	info.reachableNodes = nNodes;
+	info.depth = levels - 1;
+	info.referenceStackBound = info.anyOrderStackBound = std::max(1, levels - 1); // upper bounds (restir_check_aabb_tree computes the exact ones)
+	info.usable = levels - 1 <= 32 && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	if (info.usable) {
+		const size_t imageBytes = ((size_t)nNodes * 64 + 255) & ~(size_t)255;
+		const size_t edgeBytes = (size_t)n_triangles * 64;
+		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes));
+		ctx->treeBlockBytes = imageBytes + edgeBytes;
+		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
+		ctx->triEdges = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
+		launch_bvh_image(reinterpret_cast<const restir_aabb_node *>(ctx->nodes), nNodes, ctx->image, ctx->stream);
+		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, ctx->stream);
+		CU(ctx, cudaGetLastError());
+	} else {
+		info.why = "deeper than the 32-entry stack";
+	}
+	if (nodes_out != nullptr) {
+		CU(ctx, cudaMemcpyAsync(nodes_out, ctx->nodes, (size_t)nNodes * sizeof(restir_aabb_node), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->nNodes = nNodes;
 	ctx->nTris = n_triangles;
 	ctx->imageInfo = info;
 	return RESTIR_OK;

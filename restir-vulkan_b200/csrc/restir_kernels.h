@@ -85,6 +85,32 @@ void launch_gbuffer(const SceneView &sc, const GBufferScene &g, const Band &band
                     void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
 cudaError_t preload_gbuffer_kernels();
 
+// ---- AabbTree::build on the device (restir_bvh_build.cu) ---------------------------------------------------------------
+struct BvhLeaves { // aabbTreeBuilder.cpp:28-32 as arrays; `bin` is shared by both copies
+	float *lo[3], *hi[3], *cen[3];
+	int *geom;
+	unsigned *bin;
+};
+struct BvhJob { // one BuildStep of the reference's queue (aabbTreeBuilder.cpp:19-27)
+	long long slot; // where the id of the node (or leaf) of this range is written: node * 2 + (0 left | 1 right); -1: the root
+	int beg, end;
+	int node;       // id of the node this range makes; -1: a single leaf
+	int split;      // ordinal among the ranges of this level that split (> 2 leaves); -1: finished
+	int pivot, keepOrder;
+};
+struct BvhJobState { // reductions of one splitting range: (float key, leaf position) pairs, see restir_bvh_build.cu
+	unsigned long long cenMin[3], cenMax[3], geoMin[3], geoMax[3];
+	unsigned long long binMin[12][3], binMax[12][3];
+	unsigned binCount[12];
+	float outerArea, axisLo, binWidth;
+	int axis, bestSplit;
+};
+size_t bvh_build_scratch_bytes(unsigned n);
+cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_node *nodes, void *scratch, int *levelsOut, unsigned *nonFinite,
+                                   cudaStream_t s);
+void launch_bvh_image(const restir_aabb_node *nodes, unsigned n, float4 *image, cudaStream_t s);
+cudaError_t preload_bvh_build_kernels();
+
 // ---- halo exchange over peer memory (restir_halo.cu) ----------------------------------------------------------
 // side 0 = the neighbour that owns the rows above this band, side 1 = the rows below.
 struct HaloPush {
