@@ -372,6 +372,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         c.upload_bvh(scene.nodes, scene.triangles)
         c.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
+        c.set_spatial_staging(args.spatial_staging == "on")
         return c
 
     ctx = new_context()
@@ -889,6 +890,8 @@ def main():
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo rows pushed by the library's own kernels into the neighbours' memory (default), or NCCL send/recv "
                          "between the passes (bands.exchange_halo)")
+    ap.add_argument("--spatial-staging", default="off", choices=["off", "on"],
+                    help="biased spatial pass: gate data staged in shared memory (restir_set_spatial_staging) or read directly (A/B)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep bands of equal height instead of equal measured cost")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skips the CPU baseline and the oracle parity samples")
     ap.add_argument("--no-e2e", action="store_true")

@@ -176,6 +176,11 @@ int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
  * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every
  * ray instead (A/B measurements and the tests that require both settings to give identical bits).  Default: 1. */
 int restir_set_ray_elision(restir_context *ctx, int enable);
+/* No reference equivalent.  The biased spatial pass tests every neighbour's depth and normal before it merges the neighbour's
+ * reservoir (spatialReuse.comp:62-70).  enable != 0: the CTA stages the depth and normal texels of its 32x8 tile and the
+ * 31-pixel apron in shared memory first (79 KB) and the gates read those; 0 (default): every gate reads its two texels
+ * through L1/L2 directly.  Same results bit for bit; which one is faster is a measurement (profiles/r2_e_summary.md). */
+int restir_set_spatial_staging(restir_context *ctx, int enable);
 /* The same checks restir_upload_bvh runs, on the host and without a context (no GPU needed): RESTIR_E_INVALID
  * and a message for an upload that would be rejected; otherwise RESTIR_OK, `out` filled (traversal says which
  * walk such an upload would get) and, for the reference-order fallback, the reason in `message`.  The

@@ -63,7 +63,7 @@ EXPORTS = [
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
     "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
-    "restir_set_traversal", "restir_set_ray_elision", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
+    "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
@@ -400,6 +400,9 @@ class RestirContext:
 
     def set_ray_elision(self, enable):
         self._check(self.lib.restir_set_ray_elision(self._ctx, C.c_int(1 if enable else 0)))
+
+    def set_spatial_staging(self, enable):
+        self._check(self.lib.restir_set_spatial_staging(self._ctx, C.c_int(1 if enable else 0)))
 
     def set_traversal(self, mode):
         """Takes effect at the next upload_bvh."""

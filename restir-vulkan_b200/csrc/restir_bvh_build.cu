@@ -556,10 +556,10 @@ size_t bvh_build_scratch_bytes(unsigned n) {
 	const size_t jobs = 2 * ((size_t)n + 2) * sizeof(BvhJob) + 2 * ((size_t)n + 2) * sizeof(unsigned) * 2;         // two levels, flags + scans
 	const size_t state = ((size_t)n / 3 + 2) * sizeof(BvhJobState);                                                // splitting ranges have >= 3 leaves
 	const size_t tmp = (2 * ((size_t)n / kScanBlock + 4) + 2 * ((size_t)n / kScanBlock / kScanBlock + 4) + 8) * sizeof(unsigned);
-	return leaves + perLeaf + jobs + state + tmp + 4096;
+	return leaves + perLeaf + jobs + state + tmp + 64 * 256; // every sub-array starts on a 256-byte boundary (about 40 of them)
 }
 
-// Builds the tree over `tris` (device, n x 3 float4) into `nodes` (device, (n - 1) x 80 bytes).  levels = queue generations.
+// Builds the tree over `tris` (device, n x 3 float4) into `nodes` (device, (n - 1) x 80 bytes).  levelsOut = level of the deepest leaf (root node = level 0).
 cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_node *nodes, void *scratch, int *levelsOut, unsigned *nonFinite,
                                    cudaStream_t s) {
 	unsigned char *p = static_cast<unsigned char *>(scratch);
@@ -619,6 +619,9 @@ cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_n
 		if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
 		firstNode += (int)totals[0];
 		if (totals[1] == 0) {
+			if (totals[0] == 0) {
+				--levels; // a generation of single leaves only: they hang one level higher than a generation that still makes nodes
+			}
 			break;
 		}
 		bvh_leaf_bounds_kernel<<<grid(n), tb, 0, s>>>(in, jobOf[cur & 1], J, n, state);

@@ -35,6 +35,8 @@ struct restir_context {
 	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
 	int smCount = 0;
+	void *bvhScratch = nullptr; // restir_build_bvh_device: kept between builds (a rebuild per frame must not pay for cudaMalloc)
+	size_t bvhScratchBytes = 0;
 	unsigned char *pointBlob = nullptr, *triBlob = nullptr, *aliasBlob = nullptr;
 	float4 *pointPosLum = nullptr, *triAux = nullptr;
 	int pointCount = 0, triCount = 0, aliasCount = 0;
@@ -90,6 +92,7 @@ struct restir_context {
 	uint32_t unbiasedNeighbors = 3; // unbiasedReuse.glsl:48
 	int traversal = RESTIR_TRAVERSAL_AUTO;
 	int rayElision = 1; // restir_set_ray_elision
+	bool spatialStaging = false; // restir_set_spatial_staging
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
 	uint64_t launches = 0;
 
@@ -494,6 +497,7 @@ void restir_destroy(restir_context *ctx) {
 	dropProfile(ctx);
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
+	freeDev(ctx->bvhScratch);
 	freeDev(ctx->treeBlock); // image + triEdges
 	freeDev(ctx->shadowed);
 	freeDev(ctx->neighborPix);
@@ -609,8 +613,13 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)nNodes * sizeof(restir_aabb_node)));
 	CU(ctx, cudaMalloc(&ctx->tris, triBytes));
 	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, triBytes, cudaMemcpyHostToDevice, ctx->stream));
-	void *scratch = nullptr;
-	CU(ctx, cudaMalloc(&scratch, bvh_build_scratch_bytes(n_triangles)));
+	if (ctx->bvhScratchBytes < bvh_build_scratch_bytes(n_triangles)) {
+		freeDev(ctx->bvhScratch);
+		ctx->bvhScratchBytes = 0;
+		CU(ctx, cudaMalloc(&ctx->bvhScratch, bvh_build_scratch_bytes(n_triangles)));
+		ctx->bvhScratchBytes = bvh_build_scratch_bytes(n_triangles);
+	}
+	void *scratch = ctx->bvhScratch;
 	int levels = 0;
 	unsigned nonFinite = 0;
 	beforeLaunch(ctx, "bvh_build (all kernels)");
@@ -618,7 +627,6 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	                                       ctx->stream);
 	int rc = afterLaunch(ctx, "bvh_build (all kernels)");
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	cudaFree(scratch);
 	if (e != cudaSuccess) return cudaCheck(ctx, e, "restir_build_bvh_device");
 	if (rc != RESTIR_OK) return rc;
 	if (nonFinite != 0) {
@@ -631,9 +639,9 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	// a tree built here is a tree over [0, n) by construction; a walk in any order holds at most one pending sibling per level
 	TraversalImageInfo info;
 	info.reachableNodes = nNodes;
-	info.depth = levels - 1;
-	info.referenceStackBound = info.anyOrderStackBound = std::max(1, levels - 1); // upper bounds (restir_check_aabb_tree computes the exact ones)
-	info.usable = levels - 1 <= 32 && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	info.depth = levels;
+	info.referenceStackBound = info.anyOrderStackBound = std::max(1, levels); // upper bounds (restir_check_aabb_tree computes the exact ones)
+	info.usable = levels <= 32 && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
 	if (info.usable) {
 		const size_t imageBytes = ((size_t)nNodes * 64 + 255) & ~(size_t)255;
 		const size_t edgeBytes = (size_t)n_triangles * 64;
@@ -1135,6 +1143,12 @@ int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *p
 	return ensureHandOver(ctx, pass_grid(ctx->band), ctx->unbiasedNeighbors + 1, ctx->unbiasedNeighbors);
 }
 
+int restir_set_spatial_staging(restir_context *ctx, int enable) {
+	ENTER(ctx);
+	ctx->spatialStaging = enable != 0;
+	return RESTIR_OK;
+}
+
 int restir_set_ray_elision(restir_context *ctx, int enable) {
 	ENTER(ctx);
 	ctx->rayElision = enable ? 1 : 0;
@@ -1273,7 +1287,7 @@ int passSpatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer,
 	const char *name = lit_out ? "spatial_reuse_kernel+lighting" : "spatial_reuse_kernel";
 	beforeLaunch(ctx, name);
 	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, lit_out ? &ctx->lighting : nullptr, lit_out, lit_format,
-	                     ctx->stream);
+	                     ctx->spatialStaging, ctx->stream);
 	if ((rc = afterLaunch(ctx, name)) != RESTIR_OK) return rc;
 	if ((rc = haloPush(ctx, out_buffer)) != RESTIR_OK) return rc;
 	return markReadIfOwned(ctx, gbuffer);

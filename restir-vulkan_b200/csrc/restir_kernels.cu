@@ -491,6 +491,83 @@ __global__ void __launch_bounds__(kThreads, RESTIR_SPATIAL_MIN_BLOCKS) spatial_r
 	add_counter(p.counters, kCounterHaloMiss, haloMiss);
 }
 
+// The same pass with the gate data staged in shared memory (north-star design): the CTA first copies the raw depth
+// and the packed normal of its 32x8 tile and the +-31-pixel apron around it ((32 + 62) x (8 + 62) texels x 12 bytes = 79 KB),
+// then every neighbour's gate (:62-70) reads shared memory; the reservoirs of accepted neighbours are still gathered from
+// L2.  Same arithmetic, same bits.  A/B against the direct kernel: profiles/r2_e_summary.md; selected by
+// restir_set_spatial_staging (default: whichever won).
+constexpr int kApron = 31, kStageW = kTileW + 2 * kApron, kStageH = kTileH + 2 * kApron;
+constexpr size_t kStageBytes = (size_t)kStageW * kStageH * (sizeof(float) + sizeof(short4));
+template <bool LIGHT>
+__global__ void __launch_bounds__(kThreads, 2) spatial_reuse_staged_kernel(PassParams p, const PackedReservoir *__restrict__ in,
+                                                                         PackedReservoir *__restrict__ out, int iter, restir_lighting_uniforms lu,
+                                                                         void *__restrict__ outPixels, int outFormat) {
+	extern __shared__ __align__(16) unsigned char stage[];
+	short4 *sNormal = reinterpret_cast<short4 *>(stage);
+	float *sDepth = reinterpret_cast<float *>(stage + (size_t)kStageW * kStageH * sizeof(short4));
+	const int x0 = (int)blockIdx.x * kTileW - kApron, y0 = p.band.rowBegin + (int)blockIdx.y * kTileH - kApron;
+	for (int t = threadIdx.x; t < kStageW * kStageH; t += kThreads) {
+		int sy = t / kStageW, sx = t - sy * kStageW;
+		int gx = max(0, min(x0 + sx, p.band.W - 1)), gy = max(0, min(y0 + sy, p.band.H - 1));
+		if (gy >= p.band.allocBegin && gy < p.band.allocEnd) { // rows outside the band's memory are never read back (halo miss, below)
+			size_t g = local_index(p.band, gx, gy);
+			sNormal[t] = __ldg(p.cur.normal + g);
+			sDepth[t] = __ldg(p.cur.depth + g);
+		}
+	}
+	__syncthreads();
+	int x, y;
+	bool active = pixel_of_thread(p.band, x, y);
+	unsigned haloMiss = 0;
+	if (active) {
+		const SceneView &sc = p.scene;
+		size_t pix = local_index(p.band, x, y);
+		f3 albedo = fetch_albedo(p.cur, sc.srgbLut, pix, nullptr);
+		f3 normal = fetch_normal(p.cur, pix);
+		float roughness, metallic;
+		fetch_material(p.cur, pix, roughness, metallic);
+		f3 worldPos = fetch_world_pos(p.cur, pix);
+		float worldDepth = __ldg(p.cur.depth + pix);
+		float albedoLum = luminance3(albedo.x, albedo.y, albedo.z);
+		f3 cam = mk3(p.u.cameraPos[0], p.u.cameraPos[1], p.u.cameraPos[2]);
+		Surface sf = make_surface(worldPos, normal, cam, roughness, metallic);
+		float sinThr, cosThr;
+		sincos_policy(p.u.spatialNormalThreshold * 0.017453292519943295f, sinThr, cosThr); // :67
+
+		PackedReservoir res = load_reservoir(in, pix);
+		Pcg32 rng = pcg_seed(p.u.frame * 31u + (uint32_t)iter, (uint32_t)y * 10007u + (uint32_t)x); // :47
+		const uint32_t k = p.u.spatialNeighbors;
+		for (uint32_t i = 0; i < k; ++i) {
+			float angle = (pcg_float(rng) * 2.0f) * RESTIR_PI_F;                  // :52
+			float radius = sqrtf(pcg_float(rng)) * p.u.spatialRadius;             // :53
+			float sn, cs;
+			sincos_policy(angle, sn, cs);
+			int nx = x + (int)floorf(cs * radius), ny = y + (int)floorf(sn * radius); // :55-57
+			nx = max(0, min(nx, p.band.W - 1));
+			ny = max(0, min(ny, p.band.H - 1));
+			if (ny < p.band.allocBegin || ny >= p.band.allocEnd) {
+				haloMiss = 1;
+				continue;
+			}
+			// the clamped neighbour is inside the staged rectangle: |offset| <= 30 and clamping moves it towards the pixel
+			const int st = (ny - y0) * kStageW + (nx - x0);
+			float nDepth = sDepth[st];
+			short4 nq = sNormal[st];
+			f3 nNor = mk3(fmaxf((float)nq.x / 32767.0f, -1.0f), fmaxf((float)nq.y / 32767.0f, -1.0f), fmaxf((float)nq.z / 32767.0f, -1.0f));
+			if (fabsf(nDepth - worldDepth) > p.u.spatialPosThreshold * fabsf(worldDepth) || dot3(nNor, normal) < cosThr) { // :65-70
+				continue;
+			}
+			PackedReservoir other = load_reservoir(in, local_index(p.band, nx, ny));
+			combine_reservoirs(res, other, sc, sf, albedoLum, rng);               // :72-83
+		}
+		store_reservoir(out, pix, res);
+		if (LIGHT) {
+			shade_pixel(p, lu, pix, res, outPixels, outFormat);
+		}
+	}
+	add_counter(p.counters, kCounterHaloMiss, haloMiss);
+}
+
 // ------------------------------------------------------------------------------------------------
 // unbiasedReuse.glsl:50-124: merge the neighbours' reservoirs (no rejection), then decide which neighbours
 // take part in the normalisation (:135-138, sample in front of the neighbour's surface).  Writes the merged
@@ -874,7 +951,22 @@ void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const Packe
 	omni_temporal_kernel<<<tile_grid(p.band), kThreads, 0, s>>>(p, out, prev, shadowed, jump);
 }
 void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, const restir_lighting_uniforms *lu,
-                          void *outPixels, int fmt, cudaStream_t s) {
+                          void *outPixels, int fmt, bool staged, cudaStream_t s) {
+	// the staged apron is sized for the reference's radius (30) and G-buffer planes that exist
+	if (staged && p.u.spatialRadius <= 30.0f && p.u.spatialRadius >= 0.0f && p.cur.normal != nullptr) {
+		static bool configured = false;
+		if (!configured) {
+			cudaFuncSetAttribute(spatial_reuse_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes);
+			cudaFuncSetAttribute(spatial_reuse_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes);
+			configured = true;
+		}
+		if (lu) {
+			spatial_reuse_staged_kernel<true><<<tile_grid(p.band), kThreads, kStageBytes, s>>>(p, in, out, iter, *lu, outPixels, fmt);
+		} else {
+			spatial_reuse_staged_kernel<false><<<tile_grid(p.band), kThreads, kStageBytes, s>>>(p, in, out, iter, restir_lighting_uniforms{}, nullptr, 0);
+		}
+		return;
+	}
 	if (lu) {
 		spatial_reuse_kernel<true><<<tile_grid(p.band), kThreads, 0, s>>>(p, in, out, iter, *lu, outPixels, fmt);
 	} else {
@@ -931,6 +1023,8 @@ cudaError_t preload_pixel_kernels() {
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, omni_temporal_kernel);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel<false>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_kernel<true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_staged_kernel<false>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, spatial_reuse_staged_kernel<true>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<0>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<3>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, unbiased_merge_kernel<5>);

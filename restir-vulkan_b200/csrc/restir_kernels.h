@@ -51,8 +51,9 @@ PassGrid pass_grid(const Band &b);
 void launch_omni_candidates(const PassParams &p, PackedReservoir *out, cudaStream_t s);
 void launch_omni_temporal(const PassParams &p, PackedReservoir *out, const PackedReservoir *prev, const unsigned char *shadowed, cudaStream_t s);
 // lu != null: the lighting pass of the same pixels follows inside the kernel (restir_frame_lit), written to outPixels in format fmt
+// staged: the gate data (depth, normal) of the tile and its apron go through shared memory first (spatial_reuse_staged_kernel)
 void launch_spatial_reuse(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int iter, const restir_lighting_uniforms *lu,
-                          void *outPixels, int fmt, cudaStream_t s);
+                          void *outPixels, int fmt, bool staged, cudaStream_t s);
 // unbiasedReuse.glsl:84-124 (merge) and :126-182 (normalisation from the visibility bits); the trace kernel
 // runs in kTraceUnbiased mode between them.  neighborM: [pixel id][numNeighbors + 1] sample counts handed from the merge to the normalisation.
 void launch_unbiased_merge(const PassParams &p, const PackedReservoir *in, PackedReservoir *out, int numNeighbors, int *neighborPix,

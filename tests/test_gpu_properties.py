@@ -138,6 +138,48 @@ def test_frame_lit_equals_frame_then_lighting(unbiased, iterations, fmt):
         assert launches[1] == launches[0] - 3    # one kernel per frame less
 
 
+@pytest.mark.parametrize("size,neighbors,radius", [((640, 360), 4, 30.0), ((333, 97), 5, 30.0), ((640, 360), 4, 12.5), ((64, 40), 16, 30.0)])
+def test_staged_spatial_pass_is_bit_identical(size, neighbors, radius):
+    """restir_set_spatial_staging: the biased spatial pass with its gate data staged in shared memory (tile + 31-pixel apron)
+    against the direct kernel — same reservoirs, same image — on frames whose tiles hang over every screen edge, and as two
+    bands (the staged rectangle reaches into the halo rows)."""
+    torch = _torch()
+    scene, (pos, look) = _scene_full()
+    w, h = size
+    results = []
+    for staged in (False, True):
+        d = DeviceFrames(scene, pos, look, w, h)
+        d.ctx.set_spatial_staging(staged)
+        img = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        for f in range(3):
+            d.set(f, spatialNeighbors=neighbors, spatialRadius=radius)
+            d.ctx.frame_lit(f & 1, False, 1, img, capi.RESTIR_OUT_RGBA32F)
+        d.ctx.synchronize()
+        results.append((d.ctx.download_reservoirs(0), img.cpu().numpy().copy()))
+        d.ctx.close()
+    assert np.array_equal(results[0][0].view(np.uint8), results[1][0].view(np.uint8))
+    assert np.array_equal(results[0][1].view(np.uint8), results[1][1].view(np.uint8))
+    if h >= 97:
+        halo = 40
+        bounds = [0, h // 2 + 3, h]
+        parts = [DeviceFrames(scene, pos, look, w, h, band=(bounds[r], bounds[r + 1]), halo=halo) for r in range(2)]
+        for r, part in enumerate(parts):
+            part.ctx.set_spatial_staging(True)
+            part.ctx.band_connect(0, parts[0].ctx.band_local_peer() if r == 1 else None)
+            part.ctx.band_connect(1, parts[1].ctx.band_local_peer() if r == 0 else None)
+        for f in range(3):
+            for part in parts:
+                part.set(f, spatialNeighbors=neighbors, spatialRadius=radius)
+                part.ctx.frame(f & 1, False, 1)
+        got = np.concatenate([part.owned(part.ctx.download_reservoirs(0)) for part in parts])
+        for part in parts:
+            c = part.ctx.counters()
+            assert c["halo_misses"] == 0
+            part.ctx.close()
+        assert np.array_equal(got.view(np.uint8), results[0][0].view(np.uint8))
+
+
 def test_degenerate_parameters_are_identities():
     """spatialNeighbors = 0 makes the spatial pass a copy; no flags => no rays and temporal off equals a
     first frame; M after pass 1 equals the candidate count on every non-background pixel."""
