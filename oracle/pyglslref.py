@@ -111,3 +111,70 @@ def lighting_pass(scene, lighting_uniforms, cur, reservoirs, rows=None):
     reservoirs = np.ascontiguousarray(reservoirs)
     lib().glslref_lighting_pass(C.byref(scene.c), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(y0), C.c_int(y1))
     return out
+
+
+# ---- the same sources under the switches the authors ship: RESERVOIR_SIZE 2 / 4, UNBIASED_MIS (oracle/ref_build/Makefile) -----
+
+class Variant:
+    """libglslref_<name>.so: the reference's shaders transliterated with `#define RESERVOIR_SIZE n` and / or `#define UNBIASED_MIS`."""
+
+    def __init__(self, reservoir_size=1, unbiased_mis=False):
+        self.n, self.mis = int(reservoir_size), bool(unbiased_mis)
+        name = f"rs{self.n}" + ("_mis" if self.mis else "")
+        self.so = SO if (self.n, self.mis) == (1, False) else os.path.join(_HERE, "_ref", f"libglslref_{name}.so")
+        self.dtype = self.RESERVOIR_DTYPE = po.variant_reservoir_dtype(self.n, self.mis)
+        self.UNIFORMS_DTYPE, self.LIGHTING_UNIFORMS_DTYPE = UNIFORMS_DTYPE, LIGHTING_UNIFORMS_DTYPE
+        self._lib = None
+
+    def available(self):
+        return os.path.exists(self.so)
+
+    def lib(self):
+        if self._lib is None:
+            self._lib = C.CDLL(self.so)
+            self._lib.glslref_unbiased_pass.restype = C.c_int
+            self._lib.glslref_set_num_threads(C.c_int(os.cpu_count() or 1))
+            assert self._lib.glslref_reservoir_bytes() == self.dtype.itemsize
+        return self._lib
+
+    def restir_pass(self, scene, uniforms, cur, prev, prev_reservoirs, rows=None):
+        w, h = _size(uniforms)
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        u = np.ascontiguousarray(uniforms)
+        prev_reservoirs = np.ascontiguousarray(prev_reservoirs)
+        assert prev_reservoirs.dtype == self.dtype
+        self.lib().glslref_restir_pass(C.byref(scene.c), _p(u), C.byref(cur.c), C.byref(prev.c) if prev is not None else None,
+                                       _p(prev_reservoirs), _p(out), C.c_int(y0), C.c_int(y1))
+        return out, None
+
+    def spatial_pass(self, uniforms, cur, reservoirs, iteration, rows=None):
+        w, h = _size(uniforms)
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        u = np.ascontiguousarray(uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        self.lib().glslref_spatial_pass(_p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(iteration), C.c_int(y0), C.c_int(y1))
+        return out
+
+    def unbiased_pass(self, scene, uniforms, cur, reservoirs, num_neighbors=3, rows=None):
+        w, h = _size(uniforms)
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        u = np.ascontiguousarray(uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        rc = self.lib().glslref_unbiased_pass(C.byref(scene.c), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(num_neighbors),
+                                              C.c_int(y0), C.c_int(y1))
+        if rc != 0:
+            raise ValueError(f"libglslref is compiled for NUM_NEIGHBORS 3 (as shipped) and 5, not {num_neighbors}")
+        return out, None
+
+    def lighting_pass(self, scene, lighting_uniforms, cur, reservoirs, rows=None):
+        w, h = int(lighting_uniforms["bufferSize"][0]), int(lighting_uniforms["bufferSize"][1])
+        y0, y1 = rows or (0, h)
+        out = np.zeros((h, w, 4), np.float32)
+        u = np.ascontiguousarray(lighting_uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        self.lib().glslref_lighting_pass(C.byref(scene.c), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(y0), C.c_int(y1))
+        return out
+

@@ -304,3 +304,77 @@ def num_threads():
 
 def set_num_threads(n):
     lib().oracle_set_num_threads(C.c_int(int(n)))
+
+
+# ---- the reference's compile-time variants: RESERVOIR_SIZE > 1, UNBIASED_MIS (restirStructs.glsl:16-17) -----------------
+
+def variant_reservoir_dtype(reservoir_size, unbiased_mis):
+    """std430 Reservoir under the two switches: RESERVOIR_SIZE samples of 48 (64 with sumPHat) bytes + numStreamSamples padded to 16."""
+    sample = [("position_emissionLum", "<f4", (4,)), ("normal", "<f4", (4,)), ("lightIndex", "<i4"), ("pHat", "<f4"), ("sumWeights", "<f4"),
+              ("w", "<f4")]
+    if unbiased_mis:
+        sample += [("sumPHat", "<f4"), ("_pad", "<u4", (3,))]
+    dt = np.dtype([("samples", np.dtype(sample), (reservoir_size,)), ("M", "<u4"), ("_pad", "<u4", (3,))])
+    assert dt.itemsize == reservoir_size * (64 if unbiased_mis else 48) + 16
+    return dt
+
+
+class Variant:
+    """The oracle's passes for one (RESERVOIR_SIZE, UNBIASED_MIS): same call shapes as the module-level functions."""
+
+    def __init__(self, reservoir_size=1, unbiased_mis=False):
+        self.n, self.mis = int(reservoir_size), bool(unbiased_mis)
+        self.dtype = self.RESERVOIR_DTYPE = variant_reservoir_dtype(self.n, self.mis)
+        self.UNIFORMS_DTYPE, self.LIGHTING_UNIFORMS_DTYPE = UNIFORMS_DTYPE, LIGHTING_UNIFORMS_DTYPE
+        assert lib().oracle_variant_reservoir_bytes(C.c_int(self.n), C.c_int(self.mis)) == self.dtype.itemsize
+
+    def _v(self):
+        return C.c_int(self.n), C.c_int(1 if self.mis else 0)
+
+    def restir_pass(self, scene, uniforms, cur, prev, prev_reservoirs, rows=None):
+        w, h = int(uniforms["screenSize"][0]), int(uniforms["screenSize"][1])
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        rays = C.c_uint64(0)
+        u = np.ascontiguousarray(uniforms)
+        prev_reservoirs = np.ascontiguousarray(prev_reservoirs)
+        assert prev_reservoirs.dtype == self.dtype and prev_reservoirs.size == w * h
+        rc = lib().oracle_restir_pass_variant(*self._v(), C.byref(scene.c), _p(u), C.byref(cur.c), C.byref(prev.c) if prev is not None else None,
+                                              _p(prev_reservoirs), _p(out), C.c_int(y0), C.c_int(y1), C.byref(rays))
+        assert rc == 0
+        return out, rays.value
+
+    def spatial_pass(self, uniforms, cur, reservoirs, iteration, rows=None):
+        w, h = int(uniforms["screenSize"][0]), int(uniforms["screenSize"][1])
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        u = np.ascontiguousarray(uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        assert reservoirs.dtype == self.dtype
+        rc = lib().oracle_spatial_pass_variant(*self._v(), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(iteration), C.c_int(y0), C.c_int(y1))
+        assert rc == 0
+        return out
+
+    def unbiased_pass(self, scene, uniforms, cur, reservoirs, num_neighbors=3, rows=None):
+        w, h = int(uniforms["screenSize"][0]), int(uniforms["screenSize"][1])
+        y0, y1 = rows or (0, h)
+        out = np.zeros(w * h, self.dtype)
+        rays = C.c_uint64(0)
+        u = np.ascontiguousarray(uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        assert reservoirs.dtype == self.dtype
+        rc = lib().oracle_unbiased_pass_variant(*self._v(), C.byref(scene.c), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(num_neighbors),
+                                                C.c_int(y0), C.c_int(y1), C.byref(rays))
+        assert rc == 0
+        return out, rays.value
+
+    def lighting_pass(self, scene, lighting_uniforms, cur, reservoirs, rows=None):
+        w, h = int(lighting_uniforms["bufferSize"][0]), int(lighting_uniforms["bufferSize"][1])
+        y0, y1 = rows or (0, h)
+        out = np.zeros((h, w, 4), np.float32)
+        u = np.ascontiguousarray(lighting_uniforms)
+        reservoirs = np.ascontiguousarray(reservoirs)
+        assert reservoirs.dtype == self.dtype
+        rc = lib().oracle_lighting_pass_variant(*self._v(), C.byref(scene.c), _p(u), C.byref(cur.c), _p(reservoirs), _p(out), C.c_int(y0), C.c_int(y1))
+        assert rc == 0
+        return out

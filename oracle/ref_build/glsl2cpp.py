@@ -19,7 +19,9 @@ file, so compiler diagnostics (and gdb) cite /root/reference/src/shaders/...:lin
      g++ goes right to left: a statement with more than one `randFloat(...)` call gets the draws hoisted
      into temporaries, in source order, on the same line (restirOmni.glsl:111 and :125);
   6. optional `--define NAME=VALUE` rewrites the value of an existing `#define NAME ...` line (used for
-     the north-star's 5-neighbour variant of unbiasedReuse.glsl:47 `#define NUM_NEIGHBORS 3`).
+     the north-star's 5-neighbour variant of unbiasedReuse.glsl:47 `#define NUM_NEIGHBORS 3` and for
+     restirStructs.glsl:17 `#define RESERVOIR_SIZE 1`); `--enable NAME` uncomments a switch the authors ship
+     commented out (restirStructs.glsl:16 `/*#define UNBIASED_MIS*/`).
 
 GLSL types and built-ins (vec3, swizzles, dot, normalize, texelFetch, ...) come from glsl_shim.h.
 """
@@ -82,7 +84,9 @@ def sequence_draws(code, line_no):
     return indent + decl + RAND_CALL.sub(lambda m: next(it), code).lstrip()
 
 
-def translate(text, ref_path, defines):
+def translate(text, ref_path, defines, enables=()):
+    for name in enables:
+        text = re.sub(r"/\*\s*#\s*define\s+" + re.escape(name) + r"\s*\*/", "#define " + name, text)
     text = LAYOUT.sub(translate_layout, text)
     out = [f'#line 1 "{ref_path}"']
     for no, line in enumerate(text.split("\n"), 1):
@@ -107,6 +111,11 @@ def main():
         k, v = args[i + 1].split("=", 1)
         defines[k] = v
         del args[i:i + 2]
+    enables = []
+    while "--enable" in args:
+        i = args.index("--enable")
+        enables.append(args[i + 1])
+        del args[i:i + 2]
     src_root, out_root = args
     n = 0
     for dirpath, _, files in os.walk(src_root):
@@ -120,7 +129,7 @@ def main():
             with open(p) as fh:
                 text = fh.read()
             with open(q, "w") as fh:
-                fh.write(translate(text, os.path.abspath(p), defines))
+                fh.write(translate(text, os.path.abspath(p), defines, enables))
             n += 1
     print(f"glsl2cpp: {n} shader files -> {out_root}")
 

@@ -44,7 +44,16 @@ namespace lighting {
 using namespace glsl;
 
 // layouts the bindings below rely on
-static_assert(sizeof(omni::Reservoir) == 64 && sizeof(omni::LightSample) == 48, "Reservoir layout");
+// (the variant builds — RESERVOIR_SIZE / UNBIASED_MIS set in the transliterated restirStructs.glsl — state their own sizes)
+#ifndef GLSLREF_RESERVOIR_BYTES
+#	define GLSLREF_RESERVOIR_BYTES 64
+#	define GLSLREF_SAMPLE_BYTES 48
+#endif
+static_assert(sizeof(omni::Reservoir) == GLSLREF_RESERVOIR_BYTES && sizeof(omni::LightSample) == GLSLREF_SAMPLE_BYTES, "Reservoir layout");
+static_assert(sizeof(spatial::Reservoir) == GLSLREF_RESERVOIR_BYTES && sizeof(unbiased3::Reservoir) == GLSLREF_RESERVOIR_BYTES &&
+                  sizeof(unbiased5::Reservoir) == GLSLREF_RESERVOIR_BYTES && sizeof(lighting::Reservoir) == GLSLREF_RESERVOIR_BYTES,
+              "Reservoir layout");
+extern "C" int glslref_reservoir_bytes(void) { return GLSLREF_RESERVOIR_BYTES; }
 static_assert(sizeof(omni::RestirUniforms) == 128, "RestirUniforms layout");
 static_assert(sizeof(lighting::LightingPassUniforms) == 96, "LightingPassUniforms layout");
 static_assert(sizeof(omni::AabbTreeNode) == 80 && sizeof(omni::Triangle) == 48, "AabbTree layout");

@@ -1333,3 +1333,482 @@ void oracle_gbuffer_pass(const oracle_scene *s, const float *attrs, const int32_
 
 } // extern "C"
 
+
+// ---------------------------------------------------------------------------------------------
+// The reference's compile-time variants: RESERVOIR_SIZE > 1 and UNBIASED_MIS
+// (include/structs/restirStructs.glsl:16-17, 26; include/reservoir.glsl under both switches;
+// restirOmni.glsl:149-160, 195-205; spatialReuse.comp:73-83; unbiasedReuse.glsl:74-82, 96-121, 132-181;
+// lighting.frag:53-68).  Restated for every (RESERVOIR_SIZE, UNBIASED_MIS) as templates; (1, off) is the
+// configuration the rest of this file restates and must agree with it bit for bit (tests/test_variants.py);
+// the other instantiations are pinned against the reference's shader sources compiled with the same defines
+// (oracle/ref_build, libglslref_rs<N>[_mis].so).  Records are the reference's std430 structs:
+// LightSample 48 bytes (64 with sumPHat), Reservoir = RESERVOIR_SIZE samples + numStreamSamples padded to 16.
+
+namespace {
+
+template <bool MIS> struct SampleV {
+	float position_emissionLum[4];
+	float normal[4];
+	int32_t lightIndex;
+	float pHat, sumWeights, w;
+};
+template <> struct SampleV<true> {
+	float position_emissionLum[4];
+	float normal[4];
+	int32_t lightIndex;
+	float pHat, sumWeights, w;
+	float sumPHat;
+	float pad_[3];
+};
+template <int N, bool MIS> struct ReservoirV {
+	SampleV<MIS> samples[N];
+	uint32_t numStreamSamples;
+	uint32_t pad_[3];
+};
+static_assert(sizeof(ReservoirV<1, false>) == 64 && sizeof(ReservoirV<2, false>) == 112 && sizeof(ReservoirV<1, true>) == 80 &&
+                  sizeof(ReservoirV<2, true>) == 144,
+              "std430 sizes of Reservoir under RESERVOIR_SIZE / UNBIASED_MIS");
+
+inline float &sumPHatOf(SampleV<true> &s) { return s.sumPHat; }
+inline float sumPHatOf(const SampleV<true> &s) { return s.sumPHat; }
+inline float &sumPHatOf(SampleV<false> &) {
+	static thread_local float unused;
+	return unused;
+}
+inline float sumPHatOf(const SampleV<false> &) { return 0.0f; }
+template <bool MIS> inline V3 posOf(const SampleV<MIS> &s) { return v3(s.position_emissionLum[0], s.position_emissionLum[1], s.position_emissionLum[2]); }
+template <bool MIS> inline V3 normalOf(const SampleV<MIS> &s) { return v3(s.normal[0], s.normal[1], s.normal[2]); }
+
+// reservoir.glsl:6-26
+template <int N, bool MIS>
+void updateReservoirAtV(ReservoirV<N, MIS> &res, int i, float weight, V3 position, const float normal[4], float emissionLum, int lightIdx,
+                        float pHat, float w, float sumPHat, Rand &rand) {
+	SampleV<MIS> &s = res.samples[i];
+	s.sumWeights = s.sumWeights + weight;
+	float replacePossibility = weight / s.sumWeights;
+	if (randFloat(rand) < replacePossibility) {
+		s.position_emissionLum[0] = position.x;
+		s.position_emissionLum[1] = position.y;
+		s.position_emissionLum[2] = position.z;
+		s.position_emissionLum[3] = emissionLum;
+		std::memcpy(s.normal, normal, 16);
+		s.lightIndex = lightIdx;
+		s.pHat = pHat;
+		s.w = w;
+		if (MIS) {
+			sumPHatOf(s) = sumPHatOf(s) + sumPHat; // :22-24
+		}
+	}
+}
+// reservoir.glsl:28-42
+template <int N, bool MIS>
+void addSampleToReservoirV(ReservoirV<N, MIS> &res, V3 position, const float normal[4], float emissionLum, int lightIdx, float pHat,
+                           float sampleP, Rand &rand) {
+	float weight = pHat / sampleP;
+	res.numStreamSamples += 1;
+	for (int i = 0; i < N; ++i) {
+		float w = (res.samples[i].sumWeights + weight) / ((float)res.numStreamSamples * pHat);
+		updateReservoirAtV(res, i, weight, position, normal, emissionLum, lightIdx, pHat, w, pHat, rand);
+	}
+}
+// reservoir.glsl:44-64
+template <int N, bool MIS> void combineReservoirsV(ReservoirV<N, MIS> &self, const ReservoirV<N, MIS> &other, const float pHat[N], Rand &rand) {
+	self.numStreamSamples += other.numStreamSamples;
+	for (int i = 0; i < N; ++i) {
+		const SampleV<MIS> &o = other.samples[i];
+		float weight = (pHat[i] * o.w) * (float)other.numStreamSamples;
+		if (weight > 0.0f) {
+			// reservoir.glsl:54-58: under UNBIASED_MIS the call site lists `other.sumPHat` BEFORE `other.w`, the signature (:6-11) has them
+			// the other way round — the selected sample's w becomes the neighbour's sumPHat and its sumPHat grows by the neighbour's w.
+			// Reproduced, not fixed (the unbiased pass, unbiasedReuse.glsl:108-121, passes them in signature order).
+			if (MIS) {
+				updateReservoirAtV(self, i, weight, posOf(o), o.normal, o.position_emissionLum[3], o.lightIndex, pHat[i], sumPHatOf(o), o.w, rand);
+			} else {
+				updateReservoirAtV(self, i, weight, posOf(o), o.normal, o.position_emissionLum[3], o.lightIndex, pHat[i], o.w, 0.0f, rand);
+			}
+		}
+		if (self.samples[i].w > 0.0f) {
+			self.samples[i].w = self.samples[i].sumWeights / ((float)self.numStreamSamples * self.samples[i].pHat);
+		}
+	}
+}
+
+// restirOmni.glsl:86-212
+template <int N, bool MIS>
+void restirPassV(const oracle_scene *s, const restir_uniforms *u, const oracle_gbuffer *cur, const oracle_gbuffer *prev, const void *prevFrameReservoirs,
+                 void *reservoirsOut, int y0, int y1, uint64_t *rays) {
+	typedef ReservoirV<N, MIS> R;
+	const R *prevRes = (const R *)prevFrameReservoirs;
+	R *reservoirs = (R *)reservoirsOut;
+	Scene sc = makeScene(s->nodes, s->tris, s->pointBlob, s->triBlob, s->aliasBlob);
+	GBuffer g = toG(cur), pg = toG(prev);
+	const int W = (int)u->screenSize[0], H = (int)u->screenSize[1];
+	const V3 camPos = v3(u->cameraPos[0], u->cameraPos[1], u->cameraPos[2]);
+	const float *M = u->prevFrameProjectionViewMatrix;
+	uint64_t rayCount = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rayCount)
+	for (int y = y0; y < y1; ++y) {
+		for (int x = 0; x < W; ++x) {
+			size_t pix = (size_t)y * W + x;
+			V3 albedo = fetchAlbedo(g, pix, nullptr);
+			V3 normal = fetchNormal(g, pix);
+			float roughness, metallic;
+			fetchMaterial(g, pix, &roughness, &metallic);
+			V3 worldPos = fetchWorldPos(g, pix);
+			float albedoLum = luminance(albedo.x, albedo.y, albedo.z);
+			R res;
+			std::memset(&res, 0, sizeof(res)); // newReservoir; fields GLSL leaves unset are zero (Appendix B.2)
+			Rand rand = seedRand(u->frame, (uint32_t)((uint32_t)y * 10007u + (uint32_t)x));
+			if (dot(normal, normal) != 0.0f) {
+				for (uint32_t i = 0; i < u->initialLightSampleCount; ++i) {
+					int selected_idx;
+					float lightSampleProb;
+					float r1 = randFloat(rand);
+					float r2 = randFloat(rand);
+					aliasTableSample(sc, r1, r2, &selected_idx, &lightSampleProb);
+					V3 lightSamplePos;
+					float lightNormal[4];
+					float lightSampleLum;
+					int lightSampleIndex;
+					if (sc.pointCount != 0) {
+						const restir_point_light &light = sc.pointLights[selected_idx];
+						lightSamplePos = v3(light.pos[0], light.pos[1], light.pos[2]);
+						lightSampleLum = light.color_luminance[3];
+						lightSampleIndex = selected_idx;
+						lightNormal[0] = lightNormal[1] = lightNormal[2] = lightNormal[3] = 0.0f;
+					} else {
+						const restir_tri_light &light = sc.triLights[selected_idx];
+						float r3 = randFloat(rand);
+						float r4 = randFloat(rand);
+						lightSamplePos = pickPointOnTriangle(r3, r4, v3(light.p1[0], light.p1[1], light.p1[2]), v3(light.p2[0], light.p2[1], light.p2[2]),
+						                                     v3(light.p3[0], light.p3[1], light.p3[2]));
+						lightSampleLum = light.emission_luminance[3];
+						lightSampleIndex = -1 - selected_idx;
+						V3 wi = normalize(worldPos - lightSamplePos);
+						V3 ln = v3(light.normalArea[0], light.normalArea[1], light.normalArea[2]);
+						lightSampleProb = lightSampleProb / (fabsf(dot(wi, ln)) * light.normalArea[3]);
+						lightNormal[0] = ln.x;
+						lightNormal[1] = ln.y;
+						lightNormal[2] = ln.z;
+						lightNormal[3] = 1.0f;
+					}
+					float pHat = evaluatePHat(worldPos, lightSamplePos, camPos, normal, v3(lightNormal[0], lightNormal[1], lightNormal[2]),
+					                          lightNormal[3] > 0.5f, albedoLum, lightSampleLum, roughness, metallic);
+					addSampleToReservoirV(res, lightSamplePos, lightNormal, lightSampleLum, lightSampleIndex, pHat, lightSampleProb, rand);
+				}
+			}
+			if ((u->flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0) { // :148-160
+				for (int i = 0; i < N; ++i) {
+					bool shadowed = testVisibility(sc, worldPos, posOf(res.samples[i]), nullptr);
+					rayCount++;
+					if (shadowed) {
+						res.samples[i].w = 0.0f;
+						res.samples[i].sumWeights = 0.0f;
+						if (MIS) {
+							sumPHatOf(res.samples[i]) = 0.0f;
+						}
+					}
+				}
+			}
+			if ((u->flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0) { // :163-209
+				float px = ((M[0] * worldPos.x + M[4] * worldPos.y) + M[8] * worldPos.z) + M[12] * 1.0f;
+				float py = ((M[1] * worldPos.x + M[5] * worldPos.y) + M[9] * worldPos.z) + M[13] * 1.0f;
+				float pw = ((M[3] * worldPos.x + M[7] * worldPos.y) + M[11] * worldPos.z) + M[15] * 1.0f;
+				float invW = 1.0f / pw;
+				px = px * invW;
+				py = py * invW;
+				px = ((px + 1.0f) * 0.5f) * (float)W;
+				py = ((py + 1.0f) * 0.5f) * (float)H;
+				if (px > 0.0f && py > 0.0f && px < (float)W && py < (float)H) {
+					int fx = (int)px, fy = (int)py;
+					size_t ppix = (size_t)fy * W + fx;
+					V3 positionDiff = worldPos - fetchWorldPos(pg, ppix);
+					if (dot(positionDiff, positionDiff) < 0.01f) {
+						V3 albedoDiff = albedo - fetchAlbedo(pg, ppix, nullptr);
+						if (dot(albedoDiff, albedoDiff) < 0.01f) {
+							float normalDot = dot(normal, fetchNormal(pg, ppix));
+							if (normalDot > 0.5f) {
+								R p = prevRes[ppix];
+								uint32_t cap = u->temporalSampleCountMultiplier * res.numStreamSamples;
+								if (p.numStreamSamples > cap) {
+									p.numStreamSamples = cap;
+								}
+								float pHat[N];
+								for (int i = 0; i < N; ++i) {
+									pHat[i] = evaluatePHat(worldPos, posOf(p.samples[i]), camPos, normal, normalOf(p.samples[i]), p.samples[i].normal[3] > 0.5f,
+									                       albedoLum, p.samples[i].position_emissionLum[3], roughness, metallic);
+								}
+								combineReservoirsV(res, p, pHat, rand);
+							}
+						}
+					}
+				}
+			}
+			reservoirs[pix] = res;
+		}
+	}
+	if (rays) {
+		*rays += rayCount;
+	}
+}
+
+// spatialReuse.comp:30-86
+template <int N, bool MIS>
+void spatialPassV(const restir_uniforms *u, const oracle_gbuffer *cur, const void *in, void *out, int iter, int y0, int y1) {
+	typedef ReservoirV<N, MIS> R;
+	const R *reservoirs = (const R *)in;
+	R *result = (R *)out;
+	GBuffer g = toG(cur);
+	const int W = (int)u->screenSize[0], H = (int)u->screenSize[1];
+	const V3 camPos = v3(u->cameraPos[0], u->cameraPos[1], u->cameraPos[2]);
+	float sinThr, cosThr;
+	det_sincos(u->spatialNormalThreshold * 0.017453292519943295f, &sinThr, &cosThr);
+#pragma omp parallel for schedule(dynamic, 1)
+	for (int y = y0; y < y1; ++y) {
+		for (int x = 0; x < W; ++x) {
+			size_t pix = (size_t)y * W + x;
+			V3 albedo = fetchAlbedo(g, pix, nullptr);
+			V3 normal = fetchNormal(g, pix);
+			float roughness, metallic;
+			fetchMaterial(g, pix, &roughness, &metallic);
+			V3 worldPos = fetchWorldPos(g, pix);
+			float worldDepth = g.depth[pix];
+			float albedoLum = luminance(albedo.x, albedo.y, albedo.z);
+			R res = reservoirs[pix];
+			Rand rand = seedRand((uint32_t)(u->frame * 31u + (uint32_t)iter), (uint32_t)((uint32_t)y * 10007u + (uint32_t)x));
+			for (uint32_t i = 0; i < u->spatialNeighbors; ++i) {
+				float angle = (randFloat(rand) * 2.0f) * kPi;
+				float radius = sqrtf(randFloat(rand)) * u->spatialRadius;
+				float sn, cs;
+				det_sincos(angle, &sn, &cs);
+				int nx = x + (int)floorf(cs * radius), ny = y + (int)floorf(sn * radius);
+				nx = nx < 0 ? 0 : (nx > W - 1 ? W - 1 : nx);
+				ny = ny < 0 ? 0 : (ny > H - 1 ? H - 1 : ny);
+				size_t npix = (size_t)ny * W + nx;
+				float neighborDepth = g.depth[npix];
+				V3 neighborNor = fetchNormal(g, npix);
+				if (fabsf(neighborDepth - worldDepth) > u->spatialPosThreshold * fabsf(worldDepth) || dot(neighborNor, normal) < cosThr) {
+					continue;
+				}
+				const R &randRes = reservoirs[npix];
+				float newPHats[N]; // :73-80
+				for (int j = 0; j < N; ++j) {
+					newPHats[j] = evaluatePHat(worldPos, posOf(randRes.samples[j]), camPos, normal, normalOf(randRes.samples[j]),
+					                           randRes.samples[j].normal[3] > 0.5f, albedoLum, randRes.samples[j].position_emissionLum[3], roughness, metallic);
+				}
+				combineReservoirsV(res, randRes, newPHats, rand);
+			}
+			result[pix] = res;
+		}
+	}
+}
+
+// unbiasedReuse.glsl:50-185
+template <int N, bool MIS>
+void unbiasedPassV(const oracle_scene *s, const restir_uniforms *u, const oracle_gbuffer *cur, const void *in, void *out, int numNeighbors, int y0,
+                   int y1, uint64_t *rays) {
+	typedef ReservoirV<N, MIS> R;
+	const R *reservoirs = (const R *)in;
+	R *result = (R *)out;
+	Scene sc = makeScene(s->nodes, s->tris, nullptr, nullptr, nullptr);
+	GBuffer g = toG(cur);
+	const int W = (int)u->screenSize[0], H = (int)u->screenSize[1];
+	const V3 camPos = v3(u->cameraPos[0], u->cameraPos[1], u->cameraPos[2]);
+	const int NN = numNeighbors > 0 ? (numNeighbors > 16 ? 16 : numNeighbors) : 3;
+	uint64_t rayCount = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rayCount)
+	for (int y = y0; y < y1; ++y) {
+		for (int x = 0; x < W; ++x) {
+			size_t pix = (size_t)y * W + x;
+			V3 albedo = fetchAlbedo(g, pix, nullptr);
+			V3 normal = fetchNormal(g, pix);
+			float roughness, metallic;
+			fetchMaterial(g, pix, &roughness, &metallic);
+			V3 worldPos = fetchWorldPos(g, pix);
+			float albedoLum = luminance(albedo.x, albedo.y, albedo.z);
+			R res = reservoirs[pix];
+			Rand rand = seedRand((uint32_t)(u->frame * 17u), (uint32_t)((uint32_t)y * 10007u + (uint32_t)x));
+			size_t neighborPix[16];
+			float neighborSumPHat[N][16]; // :74-82
+			float originalSumPHat[N];
+			uint32_t neighborNumSamples[16];
+			uint32_t originalNumSamples = res.numStreamSamples;
+			for (int i = 0; i < N; ++i) {
+				originalSumPHat[i] = sumPHatOf(res.samples[i]);
+			}
+			for (int i = 0; i < NN; ++i) { // :84-124
+				float angle = (randFloat(rand) * 2.0f) * kPi;
+				float radius = sqrtf(randFloat(rand)) * u->spatialRadius;
+				float sn, cs;
+				det_sincos(angle, &sn, &cs);
+				int nx = x + (int)roundf(cs * radius), ny = y + (int)roundf(sn * radius);
+				nx = nx < 0 ? 0 : (nx > W - 1 ? W - 1 : nx);
+				ny = ny < 0 ? 0 : (ny > H - 1 ? H - 1 : ny);
+				size_t npix = (size_t)ny * W + nx;
+				const R &randRes = reservoirs[npix];
+				neighborPix[i] = npix;
+				for (int j = 0; j < N; ++j) {
+					neighborSumPHat[j][i] = sumPHatOf(randRes.samples[j]);
+				}
+				neighborNumSamples[i] = randRes.numStreamSamples;
+				res.numStreamSamples += randRes.numStreamSamples;
+				for (int j = 0; j < N; ++j) {
+					const SampleV<MIS> &o = randRes.samples[j];
+					float newPHat = evaluatePHat(worldPos, posOf(o), camPos, normal, normalOf(o), o.normal[3] > 0.5f, albedoLum, o.position_emissionLum[3],
+					                             roughness, metallic);
+					float weight = (newPHat * o.w) * (float)randRes.numStreamSamples;
+					if (weight > 0.0f) {
+						updateReservoirAtV(res, j, weight, posOf(o), o.normal, o.position_emissionLum[3], o.lightIndex, newPHat, o.w, sumPHatOf(o), rand);
+					}
+				}
+			}
+			V3 neighborWorldPos[16], neighborNormal[16]; // :126-130
+			for (int i = 0; i < NN; ++i) {
+				neighborWorldPos[i] = fetchWorldPos(g, neighborPix[i]);
+				neighborNormal[i] = fetchNormal(g, neighborPix[i]);
+			}
+			for (int i = 0; i < N; ++i) { // :132-182
+				SampleV<MIS> &smp = res.samples[i];
+				V3 lightPos = posOf(smp);
+				float sumPHat = originalSumPHat[i];
+				uint32_t numSamples = originalNumSamples;
+				for (int j = 0; j < NN; ++j) {
+					if (dot(lightPos - neighborWorldPos[j], neighborNormal[j]) < 0.0f) {
+						continue;
+					}
+					if ((u->flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0) {
+						bool shadowed = testVisibility(sc, neighborWorldPos[j], lightPos, nullptr);
+						rayCount++;
+						if (shadowed) {
+							continue;
+						}
+					}
+					sumPHat = sumPHat + neighborSumPHat[i][j];
+					numSamples += neighborNumSamples[j];
+				}
+				if ((u->flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0) {
+					bool shadowed = testVisibility(sc, worldPos, lightPos, nullptr);
+					rayCount++;
+					if (shadowed) {
+						sumPHat = 0.0f;
+						numSamples = 0;
+					}
+				}
+				if (MIS ? (sumPHat > 0.0f) : (numSamples > 0)) {
+					if (MIS) {
+						smp.w = (smp.sumWeights * smp.pHat) / (sumPHat * smp.pHat); // :169
+					} else {
+						smp.w = smp.sumWeights / ((float)numSamples * smp.pHat);
+					}
+				} else {
+					smp.w = 0.0f;
+					smp.sumWeights = 0.0f;
+					if (MIS) {
+						sumPHatOf(smp) = 0.0f;
+					}
+				}
+			}
+			result[pix] = res;
+		}
+	}
+	if (rays) {
+		*rays += rayCount;
+	}
+}
+
+// lighting.frag:43-71,103
+template <int N, bool MIS>
+void lightingPassV(const oracle_scene *s, const restir_lighting_uniforms *u, const oracle_gbuffer *cur, const void *in, float *outRgba, int y0, int y1) {
+	typedef ReservoirV<N, MIS> R;
+	const R *reservoirs = (const R *)in;
+	Scene sc = makeScene(nullptr, nullptr, s->pointBlob, s->triBlob, nullptr);
+	GBuffer g = toG(cur);
+	const int W = (int)u->bufferSize[0];
+	const V3 camPos = v3(u->cameraPos[0], u->cameraPos[1], u->cameraPos[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+	for (int y = y0; y < y1; ++y) {
+		for (int x = 0; x < W; ++x) {
+			size_t pix = (size_t)y * W + x;
+			float albedoA;
+			V3 albedo = fetchAlbedo(g, pix, &albedoA);
+			V3 normal = fetchNormal(g, pix);
+			float roughness, metallic;
+			fetchMaterial(g, pix, &roughness, &metallic);
+			V3 worldPos = fetchWorldPos(g, pix);
+			const R &r = reservoirs[pix];
+			V3 c = v3(0, 0, 0);
+			for (int i = 0; i < N; ++i) { // :53-67
+				const SampleV<MIS> &smp = r.samples[i];
+				V3 emission = v3(0, 0, 0);
+				if (smp.lightIndex < 0) {
+					if (-1 - smp.lightIndex < sc.triCount) {
+						const restir_tri_light &l = sc.triLights[-1 - smp.lightIndex];
+						emission = v3(l.emission_luminance[0], l.emission_luminance[1], l.emission_luminance[2]);
+					}
+				} else if (smp.lightIndex < sc.pointCount) {
+					const restir_point_light &l = sc.pointLights[smp.lightIndex];
+					emission = v3(l.color_luminance[0], l.color_luminance[1], l.color_luminance[2]);
+				}
+				V3 pHat = evaluatePHatFull(worldPos, posOf(smp), camPos, normal, normalOf(smp), smp.normal[3] > 0.5f, albedo, emission, roughness, metallic);
+				c = c + pHat * smp.w;
+			}
+			c = c * (1.0f / (float)N); // :68, P3
+			if (albedoA > 0.5f) {
+				c = albedo;
+			}
+			if (u->gamma != 1.0f) {
+				float e = 1.0f / u->gamma;
+				c = v3(powf(c.x, e), powf(c.y, e), powf(c.z, e));
+			}
+			float *o = outRgba + pix * 4;
+			o[0] = c.x;
+			o[1] = c.y;
+			o[2] = c.z;
+			o[3] = 1.0f;
+		}
+	}
+}
+
+} // namespace
+
+#define ORACLE_VARIANT_DISPATCH(CALL)                         \
+	switch (reservoirSize * 2 + (unbiasedMis ? 1 : 0)) {     \
+	case 2: CALL(1, false); return 0;                        \
+	case 3: CALL(1, true); return 0;                         \
+	case 4: CALL(2, false); return 0;                        \
+	case 5: CALL(2, true); return 0;                         \
+	case 8: CALL(4, false); return 0;                        \
+	case 9: CALL(4, true); return 0;                         \
+	default: return -1;                                      \
+	}
+
+extern "C" {
+
+int oracle_variant_reservoir_bytes(int reservoirSize, int unbiasedMis) { return reservoirSize * (unbiasedMis ? 64 : 48) + 16; }
+
+int oracle_restir_pass_variant(int reservoirSize, int unbiasedMis, const oracle_scene *s, const restir_uniforms *u, const oracle_gbuffer *cur,
+                               const oracle_gbuffer *prev, const void *prevFrameReservoirs, void *reservoirs, int y0, int y1, uint64_t *rays) {
+#define CALL(N, M) restirPassV<N, M>(s, u, cur, prev, prevFrameReservoirs, reservoirs, y0, y1, rays)
+	ORACLE_VARIANT_DISPATCH(CALL)
+#undef CALL
+}
+int oracle_spatial_pass_variant(int reservoirSize, int unbiasedMis, const restir_uniforms *u, const oracle_gbuffer *cur, const void *in, void *out,
+                                int iter, int y0, int y1) {
+#define CALL(N, M) spatialPassV<N, M>(u, cur, in, out, iter, y0, y1)
+	ORACLE_VARIANT_DISPATCH(CALL)
+#undef CALL
+}
+int oracle_unbiased_pass_variant(int reservoirSize, int unbiasedMis, const oracle_scene *s, const restir_uniforms *u, const oracle_gbuffer *cur,
+                                 const void *in, void *out, int numNeighbors, int y0, int y1, uint64_t *rays) {
+#define CALL(N, M) unbiasedPassV<N, M>(s, u, cur, in, out, numNeighbors, y0, y1, rays)
+	ORACLE_VARIANT_DISPATCH(CALL)
+#undef CALL
+}
+int oracle_lighting_pass_variant(int reservoirSize, int unbiasedMis, const oracle_scene *s, const restir_lighting_uniforms *u, const oracle_gbuffer *cur,
+                                 const void *in, float *outRgba, int y0, int y1) {
+#define CALL(N, M) lightingPassV<N, M>(s, u, cur, in, outRgba, y0, y1)
+	ORACLE_VARIANT_DISPATCH(CALL)
+#undef CALL
+}
+
+} // extern "C"

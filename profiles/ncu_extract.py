@@ -43,7 +43,10 @@ def main():
                 label = TRACE_ORDER[n_trace % 2]
                 n_trace += 1
         else:
+            fused = "<(bool)1>" in label or "<true>" in label     # the lighting pass runs inside this kernel (restir_frame_lit)
             label = label.split("<")[0]
+            if fused and label in ("unbiased_finalize_kernel", "spatial_reuse_kernel", "spatial_reuse_staged_kernel"):
+                label += "+lighting"
         lines.append("-----")
         lines.append(f"{'Kernel':90s} {label}   [{name[:100]}]")
         for m in METRICS:

@@ -171,7 +171,7 @@ def run_oracle(case, rows=None, passes=None):
     data_po, po = po, (passes or po)
     gb = case.gbuffers()
     n = case.w * case.h
-    frame_bufs = [np.zeros(n, data_po.RESERVOIR_DTYPE), np.zeros(n, data_po.RESERVOIR_DTYPE)]  # app.h:264-284 zero-filled
+    frame_bufs = [np.zeros(n, po.RESERVOIR_DTYPE), np.zeros(n, po.RESERVOIR_DTYPE)]  # app.h:264-284 zero-filled
     out = []
     for f in range(len(case.cameras)):
         i, p = f & 1, (f & 1) ^ 1
