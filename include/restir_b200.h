@@ -147,6 +147,24 @@ int restir_gbuffer_device_planes(restir_context *ctx, int slot, restir_gbuffer_p
 int restir_set_uniforms(restir_context *ctx, const restir_uniforms *uniforms);
 /* Replaces: the LightingPassUniforms UBO write (src/app.cpp:793-800). */
 int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_uniforms *uniforms);
+/* Replaces: the compile-time switches of include/structs/restirStructs.glsl:16-17 — `#define RESERVOIR_SIZE 1` and the
+ * commented-out `#define UNBIASED_MIS` — and the choice between split and single-kernel passes the authors measured
+ * (media/milestone3, slides 6-7).
+ *   reservoir_size  RESERVOIR_SIZE: 1 (as shipped), 2 or 4 samples per reservoir, each streamed with its own random draw
+ *                   (reservoir.glsl:28-42) and traced with its own shadow rays (restirOmni.glsl:149-160, unbiasedReuse.glsl:132-166);
+ *   unbiased_mis    != 0: UNBIASED_MIS — LightSample carries sumPHat and the unbiased pass normalises by the sum of target pdfs
+ *                   instead of sample counts (unbiasedReuse.glsl:74-82, 134-181), including the reference's own argument order at
+ *                   reservoir.glsl:54-58;
+ *   fused_passes    != 0: every pass is ONE kernel that traces its shadow rays inline, like the reference's shaders, also for the
+ *                   shipped configuration (1, off) — by default that one runs on the tuned path, whose passes are cut at their rays.
+ * Anything but (1, 0, 0) runs on the generic kernels (csrc/restir_generic.cu), whose three reservoir buffers hold the reference's
+ * own std430 records: LightSample 48 bytes (64 with sumPHat), Reservoir = reservoir_size samples + numStreamSamples padded to 16,
+ * i.e. reservoir_size * (48 | 64) + 16 bytes — what restir_download_reservoirs / restir_upload_reservoirs then move and
+ * restir_get_reservoir_bytes reports.  Changing the record reallocates and zero-fills the buffers like restir_resize.  Not
+ * available on connected bands (RESTIR_E_UNSUPPORTED).  Results: bit-identical to the reference's shader sources compiled with
+ * the same defines (tests/test_variants.py). */
+int restir_set_reservoir_variant(restir_context *ctx, uint32_t reservoir_size, int unbiased_mis, int fused_passes);
+int restir_get_reservoir_bytes(const restir_context *ctx, size_t *bytes);
 /* The unbiased pass's neighbour count is a compile-time 3 in the reference (unbiasedReuse.glsl:48) and
  * ignores uniforms.spatialNeighbors; this overrides it (1..16) for the north-star's 5-neighbour runs. */
 int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);

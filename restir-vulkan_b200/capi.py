@@ -62,7 +62,8 @@ EXPORTS = [
     "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh", "restir_build_bvh_device",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
-    "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors",
+    "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
+    "restir_get_reservoir_bytes",
     "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
@@ -395,6 +396,28 @@ class RestirContext:
         assert u.dtype == LIGHTING_UNIFORMS_DTYPE
         self._check(self.lib.restir_set_lighting_uniforms(self._ctx, _hp(u)))
 
+    def set_reservoir_variant(self, reservoir_size=1, unbiased_mis=False, fused_passes=False):
+        """RESERVOIR_SIZE / UNBIASED_MIS / one kernel per shader (restir_set_reservoir_variant)."""
+        self._check(self.lib.restir_set_reservoir_variant(self._ctx, C.c_uint32(reservoir_size), C.c_int(1 if unbiased_mis else 0),
+                                                          C.c_int(1 if fused_passes else 0)))
+        self._variant = (int(reservoir_size), bool(unbiased_mis), bool(fused_passes))
+
+    def reservoir_bytes(self):
+        n = C.c_size_t()
+        self._check(self.lib.restir_get_reservoir_bytes(self._ctx, C.byref(n)))
+        return n.value
+
+    def reservoir_dtype(self):
+        """numpy dtype of what download_reservoirs returns: the reference's std430 Reservoir under the context's variant."""
+        n, mis, fused = getattr(self, "_variant", (1, False, False))
+        if (n, mis) == (1, False):
+            return RESERVOIR_DTYPE
+        sample = [("position_emissionLum", "<f4", (4,)), ("normal", "<f4", (4,)), ("lightIndex", "<i4"), ("pHat", "<f4"), ("sumWeights", "<f4"),
+                  ("w", "<f4")]
+        if mis:
+            sample += [("sumPHat", "<f4"), ("_pad", "<u4", (3,))]
+        return np.dtype([("samples", np.dtype(sample), (n,)), ("M", "<u4"), ("_pad", "<u4", (3,))])
+
     def set_unbiased_neighbors(self, n):
         self._check(self.lib.restir_set_unbiased_neighbors(self._ctx, C.c_uint32(n)))
 
@@ -443,13 +466,15 @@ class RestirContext:
                                               C.c_int(out_format)))
 
     def download_reservoirs(self, buffer):
-        out = np.zeros(self.alloc_rows() * self.width, RESERVOIR_DTYPE)
+        dt = self.reservoir_dtype()
+        assert dt.itemsize == self.reservoir_bytes()
+        out = np.zeros(self.alloc_rows() * self.width, dt)
         self._check(self.lib.restir_download_reservoirs(self._ctx, C.c_int(buffer), _hp(out)))
         return out
 
     def upload_reservoirs(self, buffer, reservoirs):
         r = np.ascontiguousarray(reservoirs)
-        assert r.dtype == RESERVOIR_DTYPE and r.size == self.alloc_rows() * self.width
+        assert r.dtype.itemsize == self.reservoir_bytes() and r.size == self.alloc_rows() * self.width
         self._check(self.lib.restir_upload_reservoirs(self._ctx, C.c_int(buffer), _hp(r)))
 
     def reservoir_device_ptr(self, buffer):

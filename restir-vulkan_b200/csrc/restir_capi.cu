@@ -55,6 +55,13 @@ struct restir_context {
 	// screen
 	Band band{0, 0, 0, 0, 0, 0};
 	PackedReservoir *reservoirs[3] = {nullptr, nullptr, nullptr};
+	// restir_set_reservoir_variant: RESERVOIR_SIZE, UNBIASED_MIS, one kernel per shader.  `generic` = anything but the shipped
+	// configuration on the tuned path; its three buffers hold the reference's std430 records instead of packed ones.
+	int variantN = 1;
+	bool variantMis = false, fusedPasses = false;
+	unsigned char *genericReservoirs[3] = {nullptr, nullptr, nullptr};
+	bool generic() const { return variantN != 1 || variantMis || fusedPasses; }
+	size_t reservoirBytes() const { return generic() ? generic_reservoir_bytes(variantN, variantMis) : sizeof(restir_reservoir); }
 	GBufferView gbuf[2] = {};
 	void *ownedPlanes[2][5] = {};
 	// restir_upload_gbuffer copies on its own stream, so the upload of frame f+1 runs under the reuse and
@@ -164,6 +171,7 @@ SceneView sceneView(const restir_context *ctx) {
 	v.nodes = ctx->nodes;
 	v.tris = ctx->tris;
 	v.image = ctx->image;
+	v.triEdges = ctx->triEdges;
 	v.pointLights = ctx->pointBlob ? reinterpret_cast<const restir_point_light *>(ctx->pointBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.triLights = ctx->triBlob ? reinterpret_cast<const restir_tri_light *>(ctx->triBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
 	v.alias = ctx->aliasBlob ? reinterpret_cast<const restir_alias_column *>(ctx->aliasBlob + RESTIR_BLOB_HEADER_BYTES) : nullptr;
@@ -179,7 +187,7 @@ SceneView sceneView(const restir_context *ctx) {
 }
 
 int checkBuffer(restir_context *ctx, int b) {
-	if (b < 0 || b > 2 || ctx->reservoirs[b] == nullptr) {
+	if (b < 0 || b > 2 || (ctx->generic() ? ctx->genericReservoirs[b] == nullptr : ctx->reservoirs[b] == nullptr)) {
 		return fail(ctx, RESTIR_E_INVALID, "reservoir buffer id %d invalid or restir_resize not called", b);
 	}
 	return RESTIR_OK;
@@ -451,6 +459,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_gbuffer_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_bvh_build_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_generic_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->haloTicket, sizeof(unsigned)), "cudaMalloc halo ticket")) != RESTIR_OK) break;
@@ -518,6 +527,9 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->staging);
 	freeDev(ctx->counters);
 	for (auto &r : ctx->reservoirs) {
+		freeDev(r);
+	}
+	for (auto &r : ctx->genericReservoirs) {
 		freeDev(r);
 	}
 	if (ctx->ownStream && ctx->stream) {
@@ -702,6 +714,9 @@ int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t poi
 	for (auto &r : ctx->reservoirs) {
 		if (r) CU(ctx, cudaMemsetAsync(r, 0, ctx->allocPixels() * sizeof(PackedReservoir), ctx->stream));
 	}
+	for (auto &r : ctx->genericReservoirs) {
+		if (r) CU(ctx, cudaMemsetAsync(r, 0, ctx->allocPixels() * ctx->reservoirBytes(), ctx->stream));
+	}
 	freeDev(ctx->pointPosLum);
 	freeDev(ctx->triAux);
 	if (ctx->pointCount) CU(ctx, cudaMalloc(&ctx->pointPosLum, sizeof(float4) * (size_t)ctx->pointCount));
@@ -730,6 +745,9 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 	for (auto &r : ctx->reservoirs) {
 		freeDev(r);
 	}
+	for (auto &r : ctx->genericReservoirs) {
+		freeDev(r);
+	}
 	freeDev(ctx->staging);
 	ctx->stagingPixels = 0;
 	Band b;
@@ -740,10 +758,18 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 	b.allocBegin = (int)(row_begin > halo ? row_begin - halo : 0);
 	b.allocEnd = (int)((uint64_t)row_end + halo < height ? row_end + halo : height);
 	ctx->band = b;
-	size_t bytes = ctx->allocPixels() * sizeof(PackedReservoir);
-	for (auto &r : ctx->reservoirs) { // app.h:264-284: three buffers, zero-filled
-		CU(ctx, cudaMalloc(&r, bytes));
-		CU(ctx, cudaMemsetAsync(r, 0, bytes, ctx->stream));
+	if (ctx->generic()) {
+		size_t bytes = ctx->allocPixels() * ctx->reservoirBytes();
+		for (auto &r : ctx->genericReservoirs) { // app.h:264-284: three buffers, zero-filled
+			CU(ctx, cudaMalloc(&r, bytes));
+			CU(ctx, cudaMemsetAsync(r, 0, bytes, ctx->stream));
+		}
+	} else {
+		size_t bytes = ctx->allocPixels() * sizeof(PackedReservoir);
+		for (auto &r : ctx->reservoirs) { // app.h:264-284: three buffers, zero-filled
+			CU(ctx, cudaMalloc(&r, bytes));
+			CU(ctx, cudaMemsetAsync(r, 0, bytes, ctx->stream));
+		}
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	return RESTIR_OK;
@@ -1022,6 +1048,46 @@ int restir_set_lighting_uniforms(restir_context *ctx, const restir_lighting_unif
 	return RESTIR_OK;
 }
 
+int restir_set_reservoir_variant(restir_context *ctx, uint32_t reservoir_size, int unbiased_mis, int fused_passes) {
+	ENTER(ctx);
+	if (!generic_variant_supported((int)reservoir_size, unbiased_mis != 0)) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "RESERVOIR_SIZE %u is not built (1, 2 and 4 are)", reservoir_size);
+	}
+	if (bandConnected(ctx)) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_set_reservoir_variant on connected bands: the halo kernels move packed reservoirs");
+	}
+	const bool was = ctx->generic();
+	const size_t before = ctx->reservoirBytes();
+	ctx->variantN = (int)reservoir_size;
+	ctx->variantMis = unbiased_mis != 0;
+	ctx->fusedPasses = fused_passes != 0;
+	if (ctx->band.W != 0 && (was != ctx->generic() || before != ctx->reservoirBytes())) {
+		// the three buffers change their record: reallocated and zero-filled like a resize (bound G-buffers are kept)
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		for (auto &r : ctx->reservoirs) freeDev(r);
+		for (auto &r : ctx->genericReservoirs) freeDev(r);
+		freeDev(ctx->staging);
+		ctx->stagingPixels = 0;
+		const size_t bytes = ctx->allocPixels() * (ctx->generic() ? ctx->reservoirBytes() : sizeof(PackedReservoir));
+		for (int b = 0; b < 3; ++b) {
+			void *ptr = nullptr;
+			CU(ctx, cudaMalloc(&ptr, bytes));
+			CU(ctx, cudaMemsetAsync(ptr, 0, bytes, ctx->stream));
+			if (ctx->generic()) ctx->genericReservoirs[b] = static_cast<unsigned char *>(ptr); else ctx->reservoirs[b] = static_cast<PackedReservoir *>(ptr);
+		}
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	return RESTIR_OK;
+}
+
+int restir_get_reservoir_bytes(const restir_context *ctx, size_t *bytes) {
+	if (ctx == nullptr || bytes == nullptr) {
+		return RESTIR_E_INVALID;
+	}
+	*bytes = ctx->reservoirBytes();
+	return RESTIR_OK;
+}
+
 int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count) {
 	ENTER(ctx);
 	if (count < 1 || count > 16) {
@@ -1048,6 +1114,9 @@ int restir_band_local_peer(restir_context *ctx, restir_band_peer *out) {
 	if (out == nullptr || ctx->band.W == 0) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_band_local_peer: null result or restir_resize_band not called");
 	}
+	if (ctx->generic()) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_band_local_peer: the halo kernels move packed reservoirs, this context holds a reservoir variant");
+	}
 	for (int b = 0; b < 3; ++b) out->reservoirs[b] = ctx->reservoirs[b];
 	out->flags = ctx->bandFlags;
 	out->alloc_begin = (uint32_t)ctx->band.allocBegin;
@@ -1061,6 +1130,9 @@ int restir_band_export_ipc(restir_context *ctx, restir_band_ipc *out) {
 	ENTER(ctx);
 	if (out == nullptr || ctx->band.W == 0) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_band_export_ipc: null result or restir_resize_band not called");
+	}
+	if (ctx->generic()) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_band_export_ipc: the halo kernels move packed reservoirs, this context holds a reservoir variant");
 	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
 	std::memset(out, 0, sizeof(*out));
@@ -1109,6 +1181,10 @@ int restir_band_connect(restir_context *ctx, int side, const restir_band_peer *p
 	p = restir_context::PeerSide{};
 	if (peer == nullptr) {
 		return RESTIR_OK;
+	}
+	if (ctx->generic()) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_band_connect: the halo kernels move packed reservoirs; a context with a reservoir variant "
+		                                       "(restir_set_reservoir_variant) exchanges its halo rows through restir_reservoir_device_ptr");
 	}
 	if (!peer->reservoirs[0] || !peer->reservoirs[1] || !peer->reservoirs[2] || !peer->flags) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_band_connect: incomplete peer");
@@ -1205,6 +1281,15 @@ int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int pre
 	if (out_buffer == prev_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "restir pass: out and prev buffers must differ");
 	}
+	if (ctx->generic()) { // one kernel, rays traced inline (restir_generic.cu)
+		if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+		if ((p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0 && (rc = waitUpload(ctx, gbuffer ^ 1)) != RESTIR_OK) return rc;
+		beforeLaunch(ctx, "generic_restir_kernel");
+		launch_generic_restir(ctx->variantN, ctx->variantMis, p, ctx->genericReservoirs[out_buffer], ctx->genericReservoirs[prev_buffer], ctx->stream);
+		if ((rc = afterLaunch(ctx, "generic_restir_kernel")) != RESTIR_OK) return rc;
+		if ((rc = markReadIfOwned(ctx, gbuffer)) != RESTIR_OK) return rc;
+		return markReadIfOwned(ctx, gbuffer ^ 1);
+	}
 	// restirOmni.glsl cut at its testVisibility call (:148-160): candidates | shadow rays | visibility + temporal
 	const PassGrid g = pass_grid(ctx->band);
 	const bool vis = (p.u.flags & RESTIR_VISIBILITY_REUSE_FLAG) != 0, temporal = (p.u.flags & RESTIR_TEMPORAL_REUSE_FLAG) != 0;
@@ -1282,8 +1367,15 @@ int passSpatial(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer,
 		return fail(ctx, RESTIR_E_INVALID, "spatial pass: in and out buffers must differ");
 	}
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
-	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
 	if (lit_out && (rc = checkLightingTarget(ctx, lit_out, lit_format)) != RESTIR_OK) return rc;
+	if (ctx->generic()) {
+		beforeLaunch(ctx, "generic_spatial_kernel");
+		launch_generic_spatial(ctx->variantN, ctx->variantMis, p, ctx->genericReservoirs[in_buffer], ctx->genericReservoirs[out_buffer], iter, ctx->stream);
+		if ((rc = afterLaunch(ctx, "generic_spatial_kernel")) != RESTIR_OK) return rc;
+		if (lit_out && (rc = restir_pass_lighting(ctx, gbuffer, out_buffer, lit_out, lit_format)) != RESTIR_OK) return rc;
+		return markReadIfOwned(ctx, gbuffer);
+	}
+	if ((rc = haloWait(ctx, in_buffer)) != RESTIR_OK) return rc;
 	const char *name = lit_out ? "spatial_reuse_kernel+lighting" : "spatial_reuse_kernel";
 	beforeLaunch(ctx, name);
 	launch_spatial_reuse(p, ctx->reservoirs[in_buffer], ctx->reservoirs[out_buffer], iter, lit_out ? &ctx->lighting : nullptr, lit_out, lit_format,
@@ -1301,6 +1393,16 @@ int passUnbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer
 	if ((rc = checkBuffer(ctx, out_buffer)) != RESTIR_OK) return rc;
 	if (in_buffer == out_buffer) {
 		return fail(ctx, RESTIR_E_INVALID, "unbiased pass: in and out buffers must differ");
+	}
+	if (ctx->generic()) { // one kernel, rays traced inline (restir_generic.cu)
+		if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+		if (lit_out && (rc = checkLightingTarget(ctx, lit_out, lit_format)) != RESTIR_OK) return rc;
+		beforeLaunch(ctx, "generic_unbiased_kernel");
+		launch_generic_unbiased(ctx->variantN, ctx->variantMis, p, ctx->genericReservoirs[in_buffer], ctx->genericReservoirs[out_buffer],
+		                        (int)ctx->unbiasedNeighbors, ctx->stream);
+		if ((rc = afterLaunch(ctx, "generic_unbiased_kernel")) != RESTIR_OK) return rc;
+		if (lit_out && (rc = restir_pass_lighting(ctx, gbuffer, out_buffer, lit_out, lit_format)) != RESTIR_OK) return rc;
+		return markReadIfOwned(ctx, gbuffer);
 	}
 	// unbiasedReuse.glsl cut at its testVisibility calls (:139-166): merge | shadow rays | normalisation
 	const PassGrid g = pass_grid(ctx->band);
@@ -1359,6 +1461,12 @@ int restir_pass_lighting(restir_context *ctx, int gbuffer, int buffer, void *out
 	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
 	if ((rc = checkLightingTarget(ctx, out_device, out_format)) != RESTIR_OK) return rc;
 	if ((rc = waitUpload(ctx, gbuffer)) != RESTIR_OK) return rc;
+	if (ctx->generic()) {
+		beforeLaunch(ctx, "generic_lighting_kernel");
+		launch_generic_lighting(ctx->variantN, ctx->variantMis, p, ctx->lighting, ctx->genericReservoirs[buffer], out_device, out_format, ctx->stream);
+		if ((rc = afterLaunch(ctx, "generic_lighting_kernel")) != RESTIR_OK) return rc;
+		return markReadIfOwned(ctx, gbuffer);
+	}
 	beforeLaunch(ctx, "lighting_kernel");
 	launch_lighting(p, ctx->lighting, ctx->reservoirs[buffer], out_device, out_format, ctx->stream);
 	if ((rc = afterLaunch(ctx, "lighting_kernel")) != RESTIR_OK) return rc;
@@ -1423,6 +1531,11 @@ int restir_download_reservoirs(restir_context *ctx, int buffer, restir_reservoir
 	if (dst_host == nullptr) {
 		return fail(ctx, RESTIR_E_INVALID, "null destination");
 	}
+	if (ctx->generic()) { // already the reference's records
+		CU(ctx, cudaMemcpyAsync(dst_host, ctx->genericReservoirs[buffer], ctx->allocPixels() * ctx->reservoirBytes(), cudaMemcpyDeviceToHost, ctx->stream));
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		return RESTIR_OK;
+	}
 	if ((rc = ensureStaging(ctx)) != RESTIR_OK) return rc;
 	size_t px = ctx->allocPixels();
 	launch_unpack_reservoirs(sceneView(ctx), ctx->reservoirs[buffer], ctx->staging, px, ctx->stream);
@@ -1439,6 +1552,11 @@ int restir_upload_reservoirs(restir_context *ctx, int buffer, const restir_reser
 	if (src_host == nullptr) {
 		return fail(ctx, RESTIR_E_INVALID, "null source");
 	}
+	if (ctx->generic()) {
+		CU(ctx, cudaMemcpyAsync(ctx->genericReservoirs[buffer], src_host, ctx->allocPixels() * ctx->reservoirBytes(), cudaMemcpyHostToDevice, ctx->stream));
+		CU(ctx, cudaStreamSynchronize(ctx->stream));
+		return RESTIR_OK;
+	}
 	if ((rc = ensureStaging(ctx)) != RESTIR_OK) return rc;
 	size_t px = ctx->allocPixels();
 	CU(ctx, cudaMemcpyAsync(ctx->staging, src_host, px * sizeof(restir_reservoir), cudaMemcpyHostToDevice, ctx->stream));
@@ -1452,8 +1570,8 @@ int restir_reservoir_device_ptr(restir_context *ctx, int buffer, void **ptr, siz
 	ENTER(ctx);
 	int rc;
 	if ((rc = checkBuffer(ctx, buffer)) != RESTIR_OK) return rc;
-	if (ptr) *ptr = ctx->reservoirs[buffer];
-	if (row_pitch_bytes) *row_pitch_bytes = (size_t)ctx->band.W * sizeof(PackedReservoir);
+	if (ptr) *ptr = ctx->generic() ? static_cast<void *>(ctx->genericReservoirs[buffer]) : static_cast<void *>(ctx->reservoirs[buffer]);
+	if (row_pitch_bytes) *row_pitch_bytes = (size_t)ctx->band.W * (ctx->generic() ? ctx->reservoirBytes() : sizeof(PackedReservoir));
 	return RESTIR_OK;
 }
 

@@ -25,6 +25,7 @@ struct SceneView {
 	const float4 *nodes;       // reference layout, 5 x float4 per node (80 B)
 	const float4 *tris;        // reference layout, 3 x float4 per triangle (48 B)
 	const float4 *image;       // derived at upload (traversal_image.h): the same nodes re-strided to 4 x float4 (64 B); null => literal 80-byte walk
+	const float4 *triEdges;    // derived at upload: 64-byte (p1, e1, e2) records of `tris` for the walk over `image` (restir_trace.cuh)
 	const restir_point_light *pointLights;
 	const restir_tri_light *triLights;
 	const restir_alias_column *alias;

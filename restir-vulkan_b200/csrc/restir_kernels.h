@@ -86,6 +86,17 @@ void launch_gbuffer(const SceneView &sc, const GBufferScene &g, const Band &band
                     void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
 cudaError_t preload_gbuffer_kernels();
 
+// ---- the reference's compile-time variants: RESERVOIR_SIZE > 1, UNBIASED_MIS, one kernel per shader (restir_generic.cu) ----------
+// Reservoir buffers of these kernels hold the reference's std430 records (generic_reservoir_bytes each).  false: (n, mis) is not instantiated.
+bool generic_variant_supported(int n, bool mis);
+size_t generic_reservoir_bytes(int n, bool mis);
+bool launch_generic_restir(int n, bool mis, const PassParams &p, void *out, const void *prev, cudaStream_t s);
+bool launch_generic_spatial(int n, bool mis, const PassParams &p, const void *in, void *out, int iter, cudaStream_t s);
+bool launch_generic_unbiased(int n, bool mis, const PassParams &p, const void *in, void *out, int numNeighbors, cudaStream_t s);
+bool launch_generic_lighting(int n, bool mis, const PassParams &p, const restir_lighting_uniforms &lu, const void *res, void *outPixels, int fmt,
+                             cudaStream_t s);
+cudaError_t preload_generic_kernels();
+
 // ---- AabbTree::build on the device (restir_bvh_build.cu) ---------------------------------------------------------------
 struct BvhLeaves { // aabbTreeBuilder.cpp:28-32 as arrays; `bin` is shared by both copies
 	float *lo[3], *hi[3], *cen[3];

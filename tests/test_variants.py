@@ -70,3 +70,87 @@ def test_variant_ray_counts():
         frames = ph.run_oracle(case, passes=po.Variant(n, mis))
         for f in frames:
             assert n * px * 2 <= f["rays"] <= n * px * (1 + 5 + 1)
+
+
+# ---- GPU: the generic kernels (csrc/restir_generic.cu) against the oracle's variants ---------------------------------------
+
+def _run_cuda(case, n, mis, fused):
+    import torch
+
+    ctx = ph.make_context(case.scene)
+    ctx.set_reservoir_variant(n, mis, fused)
+    ctx.resize(case.w, case.h)
+    ctx.set_unbiased_neighbors(case.unbiased_neighbors)
+    gb = case.gbuffers()
+    img = torch.zeros((case.h, case.w, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    out = []
+    ctx.counters(reset=True)
+    for f in range(len(case.cameras)):
+        i = f & 1
+        u, lu = case.uniforms(f)
+        ctx.upload_gbuffer(i, *gb[f].planes())
+        ctx.set_uniforms(u)
+        ctx.set_lighting_uniforms(lu)
+        if case.unbiased:
+            ctx.pass_restir(i, capi.RESTIR_BUF_TEMP, i ^ 1)
+            initial = ctx.download_reservoirs(capi.RESTIR_BUF_TEMP)
+            ctx.pass_unbiased(i, capi.RESTIR_BUF_TEMP, i)
+        else:
+            ctx.pass_restir(i, i, i ^ 1)
+            initial = ctx.download_reservoirs(i)
+            for j in range(case.iterations):
+                ctx.pass_spatial(i, i, i ^ 1, 2 * j)
+                ctx.pass_spatial(i, i ^ 1, i, 2 * j + 1)
+        ctx.pass_lighting(i, i, img, capi.RESTIR_OUT_RGBA32F)
+        ctx.synchronize()
+        c = ctx.counters(reset=True)
+        out.append(dict(reservoirs=ctx.download_reservoirs(i), initial=initial, rgba=img.cpu().numpy().copy(), rays=c["shadow_rays"]))
+    ctx.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,mis", VARIANTS)
+@pytest.mark.parametrize("name", list(CASES))
+def test_generic_kernels_match_oracle_variants(name, n, mis):
+    case = _case(name)
+    want = ph.run_oracle(case, passes=po.Variant(n, mis))
+    got = _run_cuda(case, n, mis, fused=True)
+    for f, (fw, fg) in enumerate(zip(want, got)):
+        for key in ("initial", "reservoirs"):
+            assert _same(fw[key], fg[key]), f"{name} RESERVOIR_SIZE={n} MIS={mis} frame {f}: {key} differs"
+        ph.compare_rgb(fg["rgba"], fw["rgba"])
+        assert fg["rays"] == fw["rays"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_passes_equal_the_tuned_path(name):
+    """(1, off) through the single-kernel passes == the tuned path (cut shaders, packed reservoirs, sorted lockstep rays): every
+    byte of every reservoir and of the image, and the same number of testVisibility calls."""
+    case = _case(name)
+    a, b = ph.run_cuda(case), _run_cuda(case, 1, False, fused=True)
+    for fa, fb in zip(a, b):
+        assert _same(fa["reservoirs"], fb["reservoirs"]) and _same(fa["initial"], fb["initial"]) and _same(fa["rgba"], fb["rgba"])
+        assert fa["rays"] == fb["rays"]
+
+
+@pytest.mark.gpu
+def test_variant_switch_reallocates_and_rejects_what_is_not_built():
+    scene = fixtures.make_procedural(seed=4, grid=8, boxes=10, lights="point", n_point_lights=9)
+    ctx = ph.make_context(scene)
+    ctx.resize(64, 32)
+    assert ctx.reservoir_bytes() == 64
+    ctx.set_reservoir_variant(2, True)
+    assert ctx.reservoir_bytes() == 144 and ctx.download_reservoirs(0).dtype.itemsize == 144 and not ctx.download_reservoirs(0).view(np.uint8).any()
+    ctx.set_reservoir_variant(4, False)
+    assert ctx.reservoir_bytes() == 208
+    with pytest.raises(capi.RestirError, match="not built"):
+        ctx.set_reservoir_variant(3, False)
+    with pytest.raises(capi.RestirError):
+        ctx.band_local_peer()
+    ctx.set_reservoir_variant(1, False)
+    assert ctx.reservoir_bytes() == 64
+    ctx.band_local_peer()
+    ctx.close()
