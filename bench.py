@@ -364,6 +364,9 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
     cams = [capi.make_camera(position=pos, look_at=look, aspect=w / h),
             capi.make_camera(position=(pos[0] + 0.05, pos[1], pos[2]), look_at=look, aspect=w / h)]
     k = cfg["neighbors"]
+    variant = (args.reservoir_size, args.unbiased_mis, args.fused_passes)
+    if variant != (1, False, False) and world > 1:
+        raise SystemExit("bench.py: reservoir variants run on one GPU (the halo kernels move packed reservoirs)")
 
     def new_context():
         c = capi.RestirContext(local_rank, stream.cuda_stream)
@@ -373,6 +376,8 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         c.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
         c.set_spatial_staging(args.spatial_staging == "on")
+        if variant != (1, False, False):
+            c.set_reservoir_variant(*variant)
         return c
 
     ctx = new_context()
@@ -596,6 +601,12 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         "unbiased_finalize_kernel+lighting": own_pixels * (finalize + 16 + 32 + 4) + light_bytes,
         "lighting_kernel": own_pixels * 68 + light_bytes,
     }
+    if variant != (1, False, False):
+        rb = args.reservoir_size * (64 if args.unbiased_mis else 48) + 16          # the reference's std430 record, as resident in HBM on this path
+        alg.update({"generic_restir_kernel": own_pixels * (32 + 28 + 2 * rb) + light_bytes + bvh_bytes,
+                    "generic_spatial_kernel": own_pixels * (36 + 2 * rb) + light_bytes,
+                    "generic_unbiased_kernel": own_pixels * (36 + 2 * rb) + light_bytes + bvh_bytes,
+                    "generic_lighting_kernel": own_pixels * (32 + rb + 4) + light_bytes})
     # one ray = neighbour/own position 16 B + sample position 16 B [+ neighbour index 4 B] + visibility byte; + the tree once per launch
     if "trace_kernel<pixel>" in kernel_ms:
         alg["trace_kernel<pixel>"] = own_pixels * 33 + bvh_bytes
@@ -748,7 +759,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
 
     # ---- N = 1: full-size parity of >= 64 rows against the CPU oracle (+ the timed CPU baseline for the headline) -----
     cpu_baseline, parity = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and variant[:2] == (1, False):
         po = graft.load_oracle()
         # inputs of frame index 1 exactly as the GPU sees them: frame 0's final reservoirs as history
         ctx.resize(w, h)
@@ -858,6 +869,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
                    "l2": "L2 flushed (256 MiB memset) between timed steps, outside the event brackets",
                    "reservoir_layout": "32-byte packed", "gbuffer_bytes_per_pixel": 36,
                    "frame": "restir_frame_lit (lighting fused into the last reuse kernel)" if fused else "restir passes + lighting pass",
+                   "variant": {"reservoir_size": variant[0], "unbiased_mis": variant[1], "fused_passes": variant[2]},
                    "parallelism": f"row-bands x{world} ({balance_note}), halo exchange: {'own kernels over NVLink peer memory' if args.halo == 'peer' else 'NCCL send/recv'}, "
                                   f"halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
         "rays_per_frame": rays_total / steps, "rays_walked_per_frame": walked_total / steps,
@@ -892,6 +904,11 @@ def main():
                          "between the passes (bands.exchange_halo)")
     ap.add_argument("--spatial-staging", default="off", choices=["off", "on"],
                     help="biased spatial pass: gate data staged in shared memory (restir_set_spatial_staging) or read directly (A/B)")
+    ap.add_argument("--reservoir-size", type=int, default=1, choices=[1, 2, 4], help="RESERVOIR_SIZE (restir_set_reservoir_variant); N = 1 only")
+    ap.add_argument("--unbiased-mis", action="store_true", help="UNBIASED_MIS (restir_set_reservoir_variant); N = 1 only")
+    ap.add_argument("--fused-passes", action="store_true",
+                    help="one kernel per reference shader, rays traced inline (restir_set_reservoir_variant(..., fused = 1)): the A/B of the tuned "
+                         "path's cut passes; N = 1 only")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep bands of equal height instead of equal measured cost")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skips the CPU baseline and the oracle parity samples")
     ap.add_argument("--no-e2e", action="store_true")

@@ -98,7 +98,13 @@ int restir_get_band(const restir_context *ctx, uint32_t *row_begin, uint32_t *ro
 /* Replaces: the G-buffer image bindings of initializeFrameDescriptorSetFor (restirPass.h:152-219),
  * SpatialReusePass::initializeDescriptorSetFor (spatialReusePass.h:28-89), UnbiasedReusePass
  * (unbiasedReusePass.h:111-161) and LightingPass (lightingPass.h:48-96).  slot is the G-buffer index
- * (0/1, src/app.h numGBuffers).  Planes are DEVICE pointers that must stay valid while bound. */
+ * (0/1, src/app.h numGBuffers).  Planes are DEVICE pointers that must stay valid while bound.
+ * Formats and pitches: exactly one tuple is accepted, RESTIR_GBUFFER_NVIDIA_DEFAULT with tightly packed rows (pitch = width x texel
+ * size) — what GBuffer::Formats::initialize picks on NVIDIA hardware.  The other candidates of gBufferPass.cpp:75-108 (RGB16_SNORM /
+ * RGB16F / RGBA16F / RGB32F normals, D32S8 / D24S8 depth, RGB32F positions) and padded pitches are refused on purpose
+ * (RESTIR_E_UNSUPPORTED): every kernel decodes the texels inline, a second format is a second set of kernels, and an importer that
+ * holds such images converts or copies them once per frame at the interop boundary (linear, tightly packed images are what a
+ * CUDA external-memory import of a Vulkan image needs anyway). */
 int restir_bind_gbuffer(restir_context *ctx, int slot, restir_gbuffer_format format, const restir_gbuffer_planes *device_planes);
 /* Same, from HOST memory (pinned or pageable): copies the planes into context-owned device memory and binds
  * them.  The copy runs on a copy stream the context owns (asynchronous when the host memory is pinned, which

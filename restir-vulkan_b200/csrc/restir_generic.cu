@@ -38,7 +38,7 @@ template <> struct GSample<true> {
 	float sumPHat;
 	float pad_[3];
 };
-template <int N, bool MIS> struct GReservoir {
+template <int N, bool MIS> struct alignas(16) GReservoir { // moved as float4: local copies must be 16-byte aligned too
 	GSample<MIS> s[N];
 	uint32_t M;
 	uint32_t pad_[3];
