@@ -1187,28 +1187,30 @@ void oracle_gbuffer_pass(const oracle_scene *s, const float *attrs, const int32_
 			V3 inv = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
 			float best = INFINITY, bu = 0, bv = 0;
 			int bestTri = -1;
+			// nearer child first (slab entry parameter; ties: left first), like the kernel: the pruning by `best` makes the
+			// result depend on the order in the last bit of near-ties, so both sides walk the same way
 			int stack[64], top = 1;
 			stack[0] = 0;
 			while (top > 0) {
 				const restir_aabb_node &node = nodes[stack[--top]];
+				const int child[2] = {node.leftChild, node.rightChild};
+				float rminOf[2];
+				bool hitBox[2];
 				for (int side = 0; side < 2; ++side) {
 					const float *bmin = side ? node.rightAabbMin : node.leftAabbMin;
 					const float *bmax = side ? node.rightAabbMax : node.leftAabbMax;
-					int child = side ? node.rightChild : node.leftChild;
 					V3 t1 = v3((bmin[0] - pos.x) * inv.x, (bmin[1] - pos.y) * inv.y, (bmin[2] - pos.z) * inv.z);
 					V3 t2 = v3((bmax[0] - pos.x) * inv.x, (bmax[1] - pos.y) * inv.y, (bmax[2] - pos.z) * inv.z);
 					float rmin = fmaxf(fminf(t1.x, t2.x), fmaxf(fminf(t1.y, t2.y), fminf(t1.z, t2.z)));
 					float rmax = fminf(fmaxf(t1.x, t2.x), fminf(fmaxf(t1.y, t2.y), fmaxf(t1.z, t2.z)));
-					if (!(rmin <= best && rmax >= rmin && rmax > 0.0f)) {
+					rminOf[side] = rmin;
+					hitBox[side] = rmin <= best && rmax >= rmin && rmax > 0.0f;
+				}
+				for (int side = 0; side < 2; ++side) {
+					if (!hitBox[side] || child[side] >= 0) {
 						continue;
 					}
-					if (child >= 0) {
-						if (top < 64) {
-							stack[top++] = child;
-						}
-						continue;
-					}
-					int ti = ~child;
+					int ti = ~child[side];
 					const restir_triangle &tri = tris[ti];
 					V3 p1 = v3(tri.p1[0], tri.p1[1], tri.p1[2]);
 					V3 e1 = v3(tri.p2[0], tri.p2[1], tri.p2[2]) - p1;
@@ -1246,6 +1248,18 @@ void oracle_gbuffer_pass(const oracle_scene *s, const float *attrs, const int32_
 					bestTri = ti;
 					bu = u_;
 					bv = v_;
+				}
+				const bool il = hitBox[0] && child[0] >= 0, ir = hitBox[1] && child[1] >= 0;
+				if (il && ir) {
+					const bool leftNear = rminOf[0] <= rminOf[1];
+					if (top < 63) {
+						stack[top++] = leftNear ? child[1] : child[0];
+						stack[top++] = leftNear ? child[0] : child[1];
+					}
+				} else if (il || ir) {
+					if (top < 64) {
+						stack[top++] = il ? child[0] : child[1];
+					}
 				}
 			}
 			uint8_t *a = albedoOut + pix * 4;

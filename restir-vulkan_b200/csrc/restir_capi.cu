@@ -101,6 +101,7 @@ struct restir_context {
 	int rayElision = 1; // restir_set_ray_elision
 	bool spatialStaging = false; // restir_set_spatial_staging
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
+	unsigned *traceCursors = nullptr;       // device, kTraceMaxRegions + kTraceMaxSms words (restir_trace.cu, RESTIR_TRACE_AFFINE)
 	uint64_t launches = 0;
 
 	// optional per-kernel CUDA-event timing (restir_profile_begin / _end)
@@ -374,9 +375,12 @@ TraceParams traceParams(const restir_context *ctx) {
 	tp.tris = ctx->tris;
 	tp.image = ctx->image;
 	tp.triEdges = ctx->triEdges;
+	tp.nNodes = ctx->nNodes;
 	tp.band = ctx->band;
 	tp.shadowed = ctx->shadowed;
 	tp.counters = ctx->counters;
+	tp.regionCursors = ctx->traceCursors;
+	tp.smSlots = ctx->traceCursors ? ctx->traceCursors + kTraceMaxRegions : nullptr;
 	return tp;
 }
 
@@ -454,6 +458,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		}
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->counters, sizeof(unsigned long long) * kCounterCount), "cudaMalloc counters")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * kCounterCount, ctx->stream), "memset")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->traceCursors, sizeof(unsigned) * (kTraceMaxRegions + kTraceMaxSms)), "cudaMalloc trace cursors")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_pixel_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_trace_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
@@ -526,6 +531,7 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->gbSrgbThresholds);
 	freeDev(ctx->staging);
 	freeDev(ctx->counters);
+	freeDev(ctx->traceCursors);
 	for (auto &r : ctx->reservoirs) {
 		freeDev(r);
 	}

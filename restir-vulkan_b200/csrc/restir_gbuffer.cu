@@ -158,30 +158,35 @@ __global__ void __launch_bounds__(kThreads) gbuffer_kernel(SceneView sc, GBuffer
 	f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
 	float best = __int_as_float(0x7f800000), bu = 0.0f, bv = 0.0f;
 	int bestTri = -1;
+	// Closest hit = the depth test LESS over all fragments of the pixel.  The walk visits the nearer child first (slab entry
+	// parameter; ties: left first) so that `best` shrinks early and the farther subtrees are pruned by `rmin <= best`; the oracle
+	// twin walks in the same order (the pruning makes the result order-dependent in the last bit of near-ties).
 	int stack[64];
 	int top = 1;
 	stack[0] = 0;
 	while (top > 0) {
 		const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
 		float4 ch = __ldg(n + 4);
+		int child[2] = {__float_as_int(ch.x), __float_as_int(ch.y)};
+		float rminOf[2];
+		bool hitBox[2];
 #pragma unroll
 		for (int side = 0; side < 2; ++side) {
 			float4 bmin = __ldg(n + side * 2), bmax = __ldg(n + side * 2 + 1);
-			int child = __float_as_int(side ? ch.y : ch.x);
 			float t1x = (bmin.x - pos.x) * inv.x, t1y = (bmin.y - pos.y) * inv.y, t1z = (bmin.z - pos.z) * inv.z;
 			float t2x = (bmax.x - pos.x) * inv.x, t2y = (bmax.y - pos.y) * inv.y, t2z = (bmax.z - pos.z) * inv.z;
 			float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
 			float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
-			if (!(rmin <= best && rmax >= rmin && rmax > 0.0f)) {
+			rminOf[side] = rmin;
+			hitBox[side] = rmin <= best && rmax >= rmin && rmax > 0.0f;
+		}
+		// leaves first (left, then right), then the inner children: the farther one is pushed first, so the nearer one is popped first
+#pragma unroll
+		for (int side = 0; side < 2; ++side) {
+			if (!hitBox[side] || child[side] >= 0) {
 				continue;
 			}
-			if (child >= 0) {
-				if (top < 64) {
-					stack[top++] = child;
-				}
-				continue;
-			}
-			int ti = ~child;
+			int ti = ~child[side];
 			const float4 *t = sc.tris + (size_t)ti * 3;
 			float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
 			f3 p1 = mk3(a.x, a.y, a.z);
@@ -222,6 +227,18 @@ __global__ void __launch_bounds__(kThreads) gbuffer_kernel(SceneView sc, GBuffer
 			bestTri = ti;
 			bu = u_;
 			bv = v_;
+		}
+		const bool il = hitBox[0] && child[0] >= 0, ir = hitBox[1] && child[1] >= 0;
+		if (il && ir) {
+			const bool leftNear = rminOf[0] <= rminOf[1];
+			if (top < 63) {
+				stack[top++] = leftNear ? child[1] : child[0];
+				stack[top++] = leftNear ? child[0] : child[1];
+			}
+		} else if (il || ir) {
+			if (top < 64) {
+				stack[top++] = il ? child[0] : child[1];
+			}
 		}
 	}
 	if (bestTri < 0) { // clears, gBufferPass.cpp:117-123

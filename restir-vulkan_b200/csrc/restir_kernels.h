@@ -21,6 +21,7 @@ enum TraceMode {
 struct TraceParams {
 	const float4 *nodes, *tris, *image; // image == null: literal walk of the 80-byte nodes (restir_trace.cuh)
 	const float4 *triEdges;             // with image: 64-byte (p1, e1, e2) records derived from tris at upload (restir_trace.cuh)
+	unsigned nNodes;
 	Band band;
 	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)
 	unsigned slots;
@@ -34,7 +35,10 @@ struct TraceParams {
 	unsigned outStride, outOffset;
 	int elide;                         // kTraceUnbiased: answer neighbour rays without a walk where that is exact (restir_trace.cu item_resolve)
 	unsigned long long *counters;
+	unsigned *regionCursors, *smSlots; // RESTIR_TRACE_AFFINE: one chunk cursor per region of the work list, one arrival counter per SM
+	unsigned blocksPerSm;
 };
+constexpr unsigned kTraceMaxRegions = 4096, kTraceMaxSms = 1024; // regionCursors holds kTraceMaxRegions + kTraceMaxSms words, smSlots = regionCursors + kTraceMaxRegions
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);
 
 // ---- per-pixel kernels (restir_kernels.cu) ---------------------------------------------------------------

@@ -210,6 +210,14 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 #ifndef RESTIR_TRACE_MIN_BLOCKS
 #define RESTIR_TRACE_MIN_BLOCKS 5
 #endif
+// RESTIR_TRACE_AFFINE 1 (experiment): chunks are not handed out from one global cursor but from one cursor per REGION of the work
+// list — a contiguous run of chunks, i.e. a compact part of the screen — and the CTAs resident on one SM own neighbouring regions
+// (region = %smid x CTAs per SM + arrival order on that SM), so the rays an SM walks one after the other cross the same part of
+// the scene and find its deep nodes in that SM's L1 (70 % sector hits with the global cursor).  A CTA whose region is exhausted
+// moves on to the following regions (work stealing), so every chunk is processed whatever the mapping.  0: one global cursor.
+#ifndef RESTIR_TRACE_AFFINE
+#define RESTIR_TRACE_AFFINE 0
+#endif
 // RESTIR_TRACE_REFILL = T > 0 (experiment, off): a warp does not wait for its last rays.  When T or fewer lanes are still
 // walking, the idle lanes take the next rays of the sorted chunk (which start at the root together and are aimed at the
 // same light) while the survivors keep their lanes and their stacks.  T = 0 (default): lockstep batches of 32.
@@ -223,14 +231,58 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
 	constexpr int CHUNK = ChunkOf<MODE>::value;
 	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
+#if RESTIR_TRACE_TOP_SMEM > 0
+	__shared__ float4 topNodes[RESTIR_TRACE_TOP_SMEM * 4];
+	if (IMAGE) { // the first nodes of the image = the top of the tree (breadth-first numbering), once per CTA of the persistent grid
+		const unsigned count = min((unsigned)RESTIR_TRACE_TOP_SMEM, tp.nNodes) * 4u;
+		for (unsigned t = threadIdx.x; t < count; t += kTraceThreads) {
+			topNodes[t] = __ldg(tp.image + t);
+		}
+		__syncthreads();
+	}
+	const float4 *const topOfTree = IMAGE ? topNodes : nullptr;
+#else
+	const float4 *const topOfTree = nullptr;
+#endif
 	const unsigned lane = threadIdx.x & 31u;
 	unsigned *keys = allKeys[threadIdx.x >> 5];
 	const unsigned full = 0xffffffffu;
 	unsigned rays = 0, answered = 0, overflow = 0;
 	const float4 *const walkTris = RESTIR_TRACE_TRI_EDGES ? tp.triEdges : tp.tris;
 
+#if RESTIR_TRACE_AFFINE
+	__shared__ unsigned homeRegion;
+	const unsigned nRegions = gridDim.x;
+	const unsigned nChunks = (unsigned)((tp.nItems + CHUNK - 1) / CHUNK);
+	if (threadIdx.x == 0) {
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		unsigned slot = atomicAdd(tp.smSlots + smid, 1u);
+		homeRegion = (smid * tp.blocksPerSm + slot) % nRegions;
+	}
+	__syncthreads();
+	unsigned region = homeRegion, visited = 0;
+#endif
 	for (;;) {
 		unsigned base = 0;
+#if RESTIR_TRACE_AFFINE
+		// chunks [regionBegin, regionEnd) of region r; its cursor counts the chunks handed out
+		const unsigned regionBegin = (unsigned)((unsigned long long)nChunks * region / nRegions);
+		const unsigned regionEnd = (unsigned)((unsigned long long)nChunks * (region + 1) / nRegions);
+		unsigned taken = 0;
+		if (lane == 0) {
+			taken = atomicAdd(tp.regionCursors + region, 1u);
+		}
+		taken = __shfl_sync(full, taken, 0);
+		if (taken >= regionEnd - regionBegin) { // exhausted: help the next region
+			if (++visited >= nRegions) {
+				break;
+			}
+			region = region + 1 == nRegions ? 0 : region + 1;
+			continue;
+		}
+		base = (regionBegin + taken) * (unsigned)CHUNK;
+#else
 		if (lane == 0) {
 			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)CHUNK), 0xffffffffull);
 		}
@@ -238,6 +290,7 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 		if (base >= tp.nItems) {
 			break;
 		}
+#endif
 		unsigned valid = 0;
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
@@ -289,7 +342,7 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 					continue;
 				}
 				if (walking) {
-					int st = walk_step(tp.image, walkTris, ray, cur, top, stack);
+					int st = walk_step(tp.image, walkTris, ray, cur, top, stack, topOfTree);
 					if (st != kWalkOn) {
 						tp.shadowed[out] = st == kWalkHit ? 1 : 0;
 						walking = false;
@@ -309,7 +362,7 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 					f3 p1, p2, o, d;
 					size_t out = item_segment<MODE>(tp, item, p1, p2);
 					segment_setup(p1, p2, o, d);
-					bool clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
+					bool clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d, topOfTree) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
 					tp.shadowed[out] = clear ? 0 : 1;
 					rays++;
 				}
@@ -344,7 +397,18 @@ template <int MODE, bool IMAGE> static cudaError_t launch_mode(const TraceParams
 	unsigned long long chunks = (tp.nItems + CHUNK - 1) / CHUNK;
 	unsigned long long wanted = (chunks + kTraceWarps - 1) / kTraceWarps;
 	unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)smCount * blocksPerSm, std::max<unsigned long long>(wanted, 1));
-	trace_kernel<MODE, IMAGE><<<grid, kTraceThreads, 0, s>>>(tp);
+	TraceParams launch = tp;
+	launch.blocksPerSm = (unsigned)blocksPerSm;
+#if RESTIR_TRACE_AFFINE
+	if (launch.regionCursors == nullptr || launch.smSlots == nullptr || chunks >= 0xffffffffull) {
+		return cudaErrorInvalidValue;
+	}
+	cudaError_t ez = cudaMemsetAsync(launch.regionCursors, 0, sizeof(unsigned) * (kTraceMaxRegions + kTraceMaxSms), s); // cursors, then the per-SM arrival counters
+	if (ez != cudaSuccess) {
+		return ez;
+	}
+#endif
+	trace_kernel<MODE, IMAGE><<<grid, kTraceThreads, 0, s>>>(launch);
 	return cudaGetLastError();
 }
 

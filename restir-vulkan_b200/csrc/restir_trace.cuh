@@ -139,6 +139,12 @@ __device__ __forceinline__ bool test_visibility_reference(const SceneView &sc, f
 #ifndef RESTIR_TRACE_TRI_EDGES
 #define RESTIR_TRACE_TRI_EDGES 1
 #endif
+//   RESTIR_TRACE_TOP_SMEM 0 (default): every node is read from global memory (L1 / L2).  N > 0 (experiment): the trace kernel's
+//     CTAs keep the first N nodes of the image — the top levels of the tree: AabbTree::build numbers nodes breadth-first — in
+//     shared memory and visits to them read it (four 16-byte LDS) instead of two 32-byte LDG.  Measured: profiles/r2_i_summary.md.
+#ifndef RESTIR_TRACE_TOP_SMEM
+#define RESTIR_TRACE_TOP_SMEM 0
+#endif
 
 // softwareRaytracing.glsl:15-37 on a derived (p1, e1, e2) record
 __device__ __forceinline__ bool ray_triangle_edges(const float4 *__restrict__ triEdges, int id, f3 o, f3 d) {
@@ -183,9 +189,19 @@ __device__ __forceinline__ WalkRay walk_ray(f3 o, f3 d) {
 enum WalkStatus { kWalkOn = 0, kWalkClear = 1, kWalkHit = 2 };
 
 // One node visit: both boxes, hit leaves, then the next node (or the end of the walk).
-__device__ __forceinline__ int walk_step(const float4 *__restrict__ image, const float4 *__restrict__ tris, const WalkRay &r, int &cur, int &top, int *stack) {
+__device__ __forceinline__ int walk_step(const float4 *__restrict__ image, const float4 *__restrict__ tris, const WalkRay &r, int &cur, int &top, int *stack,
+                                         const float4 *topNodes = nullptr) {
 	const float4 *n = image + (unsigned)cur * 4u;
-	F8 lo = ldg256(n), hi = ldg256(n + 2);
+	F8 lo, hi;
+	if (RESTIR_TRACE_TOP_SMEM > 0 && topNodes != nullptr && cur < RESTIR_TRACE_TOP_SMEM) {
+		const float4 *s = topNodes + (unsigned)cur * 4u;
+		float4 a = s[0], b = s[1], c = s[2], d = s[3];
+		lo = F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+		hi = F8{{c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w}};
+	} else {
+		lo = ldg256(n);
+		hi = ldg256(n + 2);
+	}
 	float4 qx = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]), qy = make_float4(lo.v[4], lo.v[5], lo.v[6], lo.v[7]);
 	float4 qz = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
 	int2 ch = make_int2(__float_as_int(hi.v[4]), __float_as_int(hi.v[5]));
@@ -233,12 +249,13 @@ __device__ __forceinline__ int walk_step(const float4 *__restrict__ image, const
 }
 
 // Returns true when nothing is hit.
-__device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image, const float4 *__restrict__ tris, f3 o, f3 d) {
+__device__ __forceinline__ bool trace_any_image(const float4 *__restrict__ image, const float4 *__restrict__ tris, f3 o, f3 d,
+                                                const float4 *topNodes = nullptr) {
 	int stack[32];
 	int top = 0, cur = 0;
 	const WalkRay r = walk_ray(o, d);
 	for (;;) {
-		int st = walk_step(image, tris, r, cur, top, stack);
+		int st = walk_step(image, tris, r, cur, top, stack, topNodes);
 		if (st != kWalkOn) {
 			return st == kWalkClear;
 		}
