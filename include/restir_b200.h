@@ -146,6 +146,18 @@ int restir_pass_gbuffer(restir_context *ctx, int slot, const restir_camera *came
 /* The device planes of a slot the context owns (restir_pass_gbuffer / restir_upload_gbuffer), rows [alloc_begin, alloc_end). */
 int restir_gbuffer_device_planes(restir_context *ctx, int slot, restir_gbuffer_planes *out);
 
+/* ---- Vulkan interop -------------------------------------------------------- */
+
+/* The CUDA half of sharing the reference's G-buffer images with this library instead of copying them: `fd` is the POSIX file
+ * descriptor vkGetMemoryFdKHR returns for a VkDeviceMemory allocated with VkExportMemoryAllocateInfo{ handleTypes =
+ * VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT } (src/vma.h allocations of gBufferPass.cpp:34-58 would need that pNext and LINEAR
+ * tiling); `size` the allocation size.  Returns a device pointer to the whole allocation, valid until restir_release_external_memory
+ * or restir_destroy; pass pointer + image offset to restir_bind_gbuffer.  CUDA takes ownership of the descriptor.  Ordering
+ * between the Vulkan queue and this context's stream stays the caller's (vkQueueWaitIdle / restir_synchronize, or exported
+ * semaphores).  Not exercised by the tests of this repository beyond its error path: the image has no Vulkan. */
+int restir_import_external_memory(restir_context *ctx, int fd, uint64_t size, void **device_ptr);
+int restir_release_external_memory(restir_context *ctx, void *device_ptr);
+
 /* ---- uniforms ------------------------------------------------------------------------------------ */
 
 /* Replaces: the mapped write of the RestirUniforms UBO each frame (src/app.cpp:775-826, initial values

@@ -62,7 +62,7 @@ EXPORTS = [
     "restir_create", "restir_destroy", "restir_last_error", "restir_synchronize", "restir_upload_bvh", "restir_build_bvh_device",
     "restir_upload_lights", "restir_resize", "restir_resize_band", "restir_get_band", "restir_bind_gbuffer",
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
-    "restir_gbuffer_device_planes", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
+    "restir_gbuffer_device_planes", "restir_import_external_memory", "restir_release_external_memory", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
     "restir_get_reservoir_bytes",
     "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
@@ -385,6 +385,15 @@ class RestirContext:
         pl = GBufferPlanes()
         self._check(self.lib.restir_gbuffer_device_planes(self._ctx, C.c_int(slot), C.byref(pl)))
         return [pl.albedo, pl.normal, pl.material, pl.worldPos, pl.depth]
+
+    def import_external_memory(self, fd, size):
+        """Device pointer (int) of an allocation another API exported as an opaque POSIX fd (restir_import_external_memory)."""
+        ptr = C.c_void_p()
+        self._check(self.lib.restir_import_external_memory(self._ctx, C.c_int(fd), C.c_uint64(size), C.byref(ptr)))
+        return ptr.value
+
+    def release_external_memory(self, ptr):
+        self._check(self.lib.restir_release_external_memory(self._ctx, C.c_void_p(ptr)))
 
     def set_uniforms(self, uniforms):
         u = np.ascontiguousarray(uniforms)

@@ -91,6 +91,7 @@ struct restir_context {
 	unsigned *haloTicket = nullptr;
 	uint64_t produced[3] = {0, 0, 0};        // times each buffer has been produced since the neighbours were connected
 	std::vector<void *> ipcOpened;
+	std::vector<std::pair<void *, cudaExternalMemory_t>> imported; // restir_import_external_memory
 
 	restir_uniforms uniforms{};
 	bool haveUniforms = false;
@@ -505,6 +506,10 @@ void restir_destroy(restir_context *ctx) {
 		cudaStreamDestroy(ctx->copyStream);
 	}
 	dropPeers(ctx);
+	for (auto &im : ctx->imported) {
+		cudaDestroyExternalMemory(im.second);
+	}
+	ctx->imported.clear();
 	freeDev(ctx->bandFlags);
 	freeDev(ctx->haloTicket);
 	dropGBuffers(ctx);
@@ -1029,6 +1034,51 @@ int restir_gbuffer_device_planes(restir_context *ctx, int slot, restir_gbuffer_p
 	*out = restir_gbuffer_planes{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],
 	                             ctx->ownedPlanes[slot][4]};
 	return RESTIR_OK;
+}
+
+int restir_import_external_memory(restir_context *ctx, int fd, uint64_t size, void **device_ptr) {
+	ENTER(ctx);
+	if (device_ptr == nullptr || fd < 0 || size == 0) {
+		return fail(ctx, RESTIR_E_INVALID, "restir_import_external_memory: bad descriptor, size or result pointer");
+	}
+	*device_ptr = nullptr;
+	cudaExternalMemoryHandleDesc hd{};
+	hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+	hd.handle.fd = fd;
+	hd.size = size;
+	cudaExternalMemory_t mem = nullptr;
+	cudaError_t e = cudaImportExternalMemory(&mem, &hd);
+	if (e != cudaSuccess) { // not sticky: a descriptor that is not an exported allocation says nothing about the device
+		cudaGetLastError();
+		return fail(ctx, RESTIR_E_INVALID, "cudaImportExternalMemory: %s", cudaGetErrorString(e));
+	}
+	cudaExternalMemoryBufferDesc bd{};
+	bd.offset = 0;
+	bd.size = size;
+	void *ptr = nullptr;
+	e = cudaExternalMemoryGetMappedBuffer(&ptr, mem, &bd);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		cudaDestroyExternalMemory(mem);
+		return fail(ctx, RESTIR_E_INVALID, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e));
+	}
+	ctx->imported.emplace_back(ptr, mem);
+	*device_ptr = ptr;
+	return RESTIR_OK;
+}
+
+int restir_release_external_memory(restir_context *ctx, void *device_ptr) {
+	ENTER(ctx);
+	for (size_t k = 0; k < ctx->imported.size(); ++k) {
+		if (ctx->imported[k].first == device_ptr) {
+			CU(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(device_ptr); // the mapping; then the import itself
+			cudaDestroyExternalMemory(ctx->imported[k].second);
+			ctx->imported.erase(ctx->imported.begin() + (long)k);
+			return RESTIR_OK;
+		}
+	}
+	return fail(ctx, RESTIR_E_INVALID, "restir_release_external_memory: not a pointer restir_import_external_memory returned");
 }
 
 int restir_set_uniforms(restir_context *ctx, const restir_uniforms *u) {

@@ -318,3 +318,27 @@ def test_errors_are_returned_not_aborted():
     with pytest.raises(capi.RestirError, match="alias table"):
         ctx.upload_lights(scene.point_blob, scene.tri_blob, bad_alias[: 16 + 48])
     ctx.close()
+
+
+def test_external_memory_import_error_path():
+    """restir_import_external_memory with descriptors that are not exported allocations: an error code and a message, no abort, and
+    the context stays usable (the import of a real Vulkan allocation cannot be exercised in this image: no Vulkan)."""
+    import os
+
+    _torch()
+    scene = _scene("procedural:point")
+    ctx = ph.make_context(scene)
+    with pytest.raises(capi.RestirError):
+        ctx.import_external_memory(-1, 4096)
+    r, w = os.pipe()
+    try:
+        with pytest.raises(capi.RestirError, match="cudaImportExternalMemory|cudaExternalMemoryGetMappedBuffer"):
+            ctx.import_external_memory(os.dup(r), 1 << 20)
+    finally:
+        os.close(r)
+        os.close(w)
+    with pytest.raises(capi.RestirError):
+        ctx.release_external_memory(12345)
+    ctx.resize(32, 16)                      # not sticky: the context still works
+    assert ctx.reservoir_bytes() == 64
+    ctx.close()
