@@ -113,23 +113,45 @@ __global__ void bvh_make_leaves_kernel(const float4 *__restrict__ tris, unsigned
 }
 
 // ---- per level ---------------------------------------------------------------------------------------------------------
-// flags for the two prefix sums over the jobs: makes a node (span >= 2), splits (span > 2)
-__global__ void bvh_job_flags_kernel(const BvhJob *__restrict__ jobs, unsigned nJobs, unsigned *__restrict__ makesNode, unsigned *__restrict__ splits) {
+// The size of a level and the first node id it hands out live on the device: the host launches every level's kernels with grids
+// sized by an upper bound (min(2^level, n) jobs) and looks at this record only every few levels, to see whether the queue is empty.
+struct BvhLevel {
+	unsigned nJobs;      // jobs of the level about to be processed
+	int firstNode;       // id of the first node this level makes
+	unsigned levels;     // levels processed so far that had jobs
+	unsigned lastNodes;  // nodes made by the last such level (0: it only hung single leaves)
+};
+
+// flags for the two prefix sums over the jobs: makes a node (span >= 2), splits (span > 2); zero up to the launch bound
+__global__ void bvh_job_flags_kernel(const BvhJob *__restrict__ jobs, const BvhLevel *__restrict__ lv, unsigned bound, unsigned *__restrict__ makesNode,
+                                     unsigned *__restrict__ splits) {
 	unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= nJobs) {
+	if (j >= bound) {
 		return;
 	}
-	unsigned span = (unsigned)(jobs[j].end - jobs[j].beg);
+	unsigned span = j < lv->nJobs ? (unsigned)(jobs[j].end - jobs[j].beg) : 0u;
 	makesNode[j] = span >= 2u ? 1u : 0u;
 	splits[j] = span > 2u ? 1u : 0u;
 }
 
-__global__ void bvh_job_begin_kernel(BvhJob *__restrict__ jobs, unsigned nJobs, const unsigned *__restrict__ nodeScan, const unsigned *__restrict__ splitScan,
-                                     int firstNode, BvhLeaves leaves, restir_aabb_node *__restrict__ nodes, BvhJobState *__restrict__ state) {
+// after job_begin: the next level's size and first node id (queue order = id order)
+__global__ void bvh_level_advance_kernel(BvhLevel *lv, const unsigned *__restrict__ nodeTotal, const unsigned *__restrict__ splitTotal) {
+	if (lv->nJobs > 0u) {
+		lv->levels += 1u;
+		lv->lastNodes = *nodeTotal;
+	}
+	lv->firstNode += (int)*nodeTotal;
+	lv->nJobs = 2u * *splitTotal;
+}
+
+__global__ void bvh_job_begin_kernel(BvhJob *__restrict__ jobs, const BvhLevel *__restrict__ lv, const unsigned *__restrict__ nodeScan,
+                                     const unsigned *__restrict__ splitScan, BvhLeaves leaves, restir_aabb_node *__restrict__ nodes,
+                                     BvhJobState *__restrict__ state) {
 	unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= nJobs) {
+	if (j >= lv->nJobs) {
 		return;
 	}
+	const int firstNode = lv->firstNode;
 	BvhJob job = jobs[j];
 	const unsigned span = (unsigned)(job.end - job.beg);
 	if (span == 1u) { // :88-90
@@ -220,9 +242,9 @@ __global__ void bvh_leaf_bounds_kernel(BvhLeaves leaves, const int *__restrict__
 }
 
 // :124-131
-__global__ void bvh_job_axis_kernel(const BvhJob *__restrict__ jobs, unsigned nJobs, BvhLeaves leaves, BvhJobState *__restrict__ state) {
+__global__ void bvh_job_axis_kernel(const BvhJob *__restrict__ jobs, const BvhLevel *__restrict__ lv, BvhLeaves leaves, BvhJobState *__restrict__ state) {
 	unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= nJobs || jobs[j].split < 0) {
+	if (j >= lv->nJobs || jobs[j].split < 0) {
 		return;
 	}
 	BvhJobState &st = state[jobs[j].split];
@@ -271,10 +293,10 @@ __global__ void bvh_leaf_bin_kernel(BvhLeaves leaves, const int *__restrict__ jo
 }
 
 // :143-171 and :198-207.  One thread per job, the host builder's loop.
-__global__ void bvh_job_split_kernel(const BvhJob *__restrict__ jobs, unsigned nJobs, BvhLeaves leaves, BvhJobState *__restrict__ state,
+__global__ void bvh_job_split_kernel(const BvhJob *__restrict__ jobs, const BvhLevel *__restrict__ lv, BvhLeaves leaves, BvhJobState *__restrict__ state,
                                      restir_aabb_node *__restrict__ nodes) {
 	unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= nJobs || jobs[j].split < 0) {
+	if (j >= lv->nJobs || jobs[j].split < 0) {
 		return;
 	}
 	BvhJobState &st = state[jobs[j].split];
@@ -363,10 +385,10 @@ __global__ void bvh_leaf_flags_kernel(BvhLeaves leaves, const int *__restrict__ 
 }
 
 // pivot, median fallback (:179-196), child jobs (:208-209)
-__global__ void bvh_job_children_kernel(BvhJob *__restrict__ jobs, unsigned nJobs, const unsigned *__restrict__ leftScan, BvhLeaves leaves,
+__global__ void bvh_job_children_kernel(BvhJob *__restrict__ jobs, const BvhLevel *__restrict__ lv, const unsigned *__restrict__ leftScan, BvhLeaves leaves,
                                         restir_aabb_node *__restrict__ nodes, BvhJob *__restrict__ next) {
 	unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= nJobs || jobs[j].split < 0) {
+	if (j >= lv->nJobs || jobs[j].split < 0) {
 		return;
 	}
 	BvhJob job = jobs[j];
@@ -587,6 +609,7 @@ cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_n
 	BvhJobState *state = (BvhJobState *)take(((size_t)n / 3 + 2) * sizeof(BvhJobState));
 	unsigned *tmp = (unsigned *)take((2 * ((size_t)n / kScanBlock + 4) + 2 * ((size_t)n / kScanBlock / kScanBlock + 4) + 8) * 4);
 	unsigned *bad = (unsigned *)take(256);
+	BvhLevel *lv = (BvhLevel *)take(256);
 
 	const unsigned tb = 256;
 	auto grid = [&](unsigned count) { return (count + tb - 1) / tb; };
@@ -602,39 +625,41 @@ cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_n
 	if ((e = cudaMemcpyAsync(jobs[0], &root, sizeof(root), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
 	if ((e = cudaMemcpyAsync(nonFinite, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
 
-	unsigned nJobs = 1;
-	int firstNode = 0, cur = 0, levels = 0;
-	while (nJobs > 0) {
-		++levels;
+	// the queue's first generation: the root range
+	BvhLevel first{1u, 0, 0u, 0u};
+	if ((e = cudaMemcpyAsync(lv, &first, sizeof(first), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+	int cur = 0, levels = 0;
+	for (unsigned level = 0;; ++level) {
+		// a level has at most min(2^level, n) jobs: the grids and the scans are sized by that bound, the kernels read the level's
+		// real size from `lv` — no host round trip per level (the build is launch-bound: 30 levels x ~18 launches for Sponza)
+		const unsigned bound = level >= 31u ? n : std::min(n, 1u << level);
 		BvhJob *J = jobs[cur & 1], *N = jobs[(cur & 1) ^ 1];
 		BvhLeaves &in = L[cur & 1], &out = L[(cur & 1) ^ 1];
-		bvh_job_flags_kernel<<<grid(nJobs), tb, 0, s>>>(J, nJobs, makesNode, splits);
-		if ((e = exclusive_scan_u32(makesNode, nodeScan, nJobs, tmp, s)) != cudaSuccess) return e;
-		if ((e = exclusive_scan_u32(splits, splitScan, nJobs, tmp, s)) != cudaSuccess) return e;
-		bvh_job_begin_kernel<<<grid(nJobs), tb, 0, s>>>(J, nJobs, nodeScan, splitScan, firstNode, in, nodes, state);
-		// queue order fixes the ids of this level and the size of the next: two words back to the host per level
-		unsigned totals[2];
-		if ((e = cudaMemcpyAsync(&totals[0], nodeScan + nJobs, sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-		if ((e = cudaMemcpyAsync(&totals[1], splitScan + nJobs, sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-		if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-		firstNode += (int)totals[0];
-		if (totals[1] == 0) {
-			if (totals[0] == 0) {
-				--levels; // a generation of single leaves only: they hang one level higher than a generation that still makes nodes
-			}
-			break;
-		}
+		bvh_job_flags_kernel<<<grid(bound), tb, 0, s>>>(J, lv, bound, makesNode, splits);
+		if ((e = exclusive_scan_u32(makesNode, nodeScan, bound, tmp, s)) != cudaSuccess) return e;
+		if ((e = exclusive_scan_u32(splits, splitScan, bound, tmp, s)) != cudaSuccess) return e;
+		bvh_job_begin_kernel<<<grid(bound), tb, 0, s>>>(J, lv, nodeScan, splitScan, in, nodes, state);
 		bvh_leaf_bounds_kernel<<<grid(n), tb, 0, s>>>(in, jobOf[cur & 1], J, n, state);
-		bvh_job_axis_kernel<<<grid(nJobs), tb, 0, s>>>(J, nJobs, in, state);
+		bvh_job_axis_kernel<<<grid(bound), tb, 0, s>>>(J, lv, in, state);
 		bvh_leaf_bin_kernel<<<grid(n), tb, 0, s>>>(in, jobOf[cur & 1], J, n, state);
-		bvh_job_split_kernel<<<grid(nJobs), tb, 0, s>>>(J, nJobs, in, state, nodes);
+		bvh_job_split_kernel<<<grid(bound), tb, 0, s>>>(J, lv, in, state, nodes);
 		bvh_leaf_flags_kernel<<<grid(n), tb, 0, s>>>(in, jobOf[cur & 1], J, n, state, goesLeft);
 		if ((e = exclusive_scan_u32(goesLeft, leftScan, n, tmp, s)) != cudaSuccess) return e;
-		bvh_job_children_kernel<<<grid(nJobs), tb, 0, s>>>(J, nJobs, leftScan, in, nodes, N);
+		bvh_job_children_kernel<<<grid(bound), tb, 0, s>>>(J, lv, leftScan, in, nodes, N);
 		bvh_leaf_partition_kernel<<<grid(n), tb, 0, s>>>(in, out, jobOf[cur & 1], J, n, leftScan, jobOf[(cur & 1) ^ 1]);
+		bvh_level_advance_kernel<<<1, 1, 0, s>>>(lv, nodeScan + bound, splitScan + bound);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
-		nJobs = totals[1] * 2;
 		++cur;
+		if ((level & 7u) == 7u || level >= 64u) { // is the queue empty?  (levels processed after it emptied are no-ops)
+			BvhLevel now;
+			if ((e = cudaMemcpyAsync(&now, lv, sizeof(now), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+			if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+			if (now.nJobs == 0u) {
+				// a last generation of single leaves only hangs them one level higher than one that still made nodes
+				levels = (int)now.levels - (now.lastNodes == 0u ? 1 : 0);
+				break;
+			}
+		}
 	}
 	*levelsOut = levels;
 	return cudaGetLastError();
@@ -651,7 +676,8 @@ cudaError_t preload_bvh_build_kernels() {
 	                         (const void *)bvh_leaf_bounds_kernel,  (const void *)bvh_job_axis_kernel,     (const void *)bvh_leaf_bin_kernel,
 	                         (const void *)bvh_job_split_kernel,    (const void *)bvh_leaf_flags_kernel,   (const void *)bvh_job_children_kernel,
 	                         (const void *)bvh_leaf_partition_kernel, (const void *)scan_block_kernel,      (const void *)scan_add_kernel,
-	                         (const void *)bvh_image_kernel,        (const void *)bvh_check_finite_kernel};
+	                         (const void *)bvh_image_kernel,        (const void *)bvh_check_finite_kernel,
+	                         (const void *)bvh_level_advance_kernel};
 	for (const void *k : kernels) {
 		if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k);
 	}
