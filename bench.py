@@ -370,8 +370,8 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
 
     def new_context():
         c = capi.RestirContext(local_rank, stream.cuda_stream)
-        if args.traversal == "reference-order":
-            c.set_traversal(capi.RESTIR_TRAVERSAL_REFERENCE_ORDER)
+        if args.traversal != "auto":
+            c.set_traversal({"reference-order": capi.RESTIR_TRAVERSAL_REFERENCE_ORDER, "image": capi.RESTIR_TRAVERSAL_IMAGE}[args.traversal])
         c.upload_bvh(scene.nodes, scene.triangles)
         c.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
@@ -587,7 +587,12 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
     rays_prof, traced_prof = c_prof["shadow_rays"] / reps, c_prof["shadow_rays_traced"] / reps
     peak, peak_src = peaks()
     info = ctx.bvh_info()
-    bvh_bytes = (info["nodes"] * 64 + info["triangles"] * 64) if info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE else scene.nodes.size + scene.triangles.size
+    if info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE:        # 64-byte 4-wide nodes + 64-byte triangle records (csrc/wide_image.h)
+        bvh_bytes = info["wide_nodes"] * 64 + info["triangles"] * 64
+    elif info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE:
+        bvh_bytes = info["nodes"] * 64 + info["triangles"] * 64
+    else:
+        bvh_bytes = scene.nodes.size + scene.triangles.size
     light_bytes = scene.point_blob.size + scene.tri_blob.size + scene.alias_blob.size
     # algorithmic bytes per launch of each kernel: every input read once, every output written once
     finalize = 16 + 16 + 4 * k + 4 * (k + 1) + (k + 1)
@@ -895,7 +900,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=HEADLINE, choices=sorted(CONFIGS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--traversal", default="auto", choices=["auto", "reference-order"],
+    ap.add_argument("--traversal", default="auto", choices=["auto", "image", "reference-order"],
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")

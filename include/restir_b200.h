@@ -187,26 +187,43 @@ int restir_get_reservoir_bytes(const restir_context *ctx, size_t *bytes);
  * ignores uniforms.spatialNeighbors; this overrides it (1..16) for the north-star's 5-neighbour runs. */
 int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
 
-/* Shadow-ray traversal.  The uploaded tree is always the reference's (aabbTreeBuilder node / triangle
- * layout) and is always walked in softwareRaytracing.glsl:39-85's own order.  AUTO (default):
- * restir_upload_bvh keeps a device image of the same nodes at 64 bytes each (two 32-byte loads from one
- * line instead of five 16-byte loads that straddle lines) and, having checked that the reference's 32-entry stack cannot
- * overflow on this tree, drops the per-push bound check.  REFERENCE_ORDER: walk the 80-byte nodes literally,
- * dropped pushes counted — also what AUTO falls back to when the stack could overflow
- * (restir_get_bvh_info tells).  Takes effect at the next restir_upload_bvh.  Uploads whose child indices are
- * out of range or that are not trees are rejected with RESTIR_E_INVALID. */
+/* Shadow-ray traversal.  The uploaded tree is always the reference's (aabbTreeBuilder node / triangle layout) and the
+ * visibility bits are always those of softwareRaytracing.glsl:39-85 on that tree; what differs is what the trace kernel reads.
+ * AUTO (default): restir_upload_bvh derives, on the host,
+ *   - the binary image: the same nodes at 64 bytes each (two 32-byte loads from one line instead of five 16-byte loads that
+ *     straddle lines), walked without per-push bound checks once the reference's 32-entry stack is known not to overflow; and
+ *   - the WIDE image (csrc/wide_image.h): the tree collapsed to 4 children per node with boxes quantised outwards to a 15-bit
+ *     grid, 64 bytes per node.  For rays whose origin, direction and reciprocal direction are finite the reference's slab test
+ *     is monotone in the box, its boxes are nested (checked), so the reference tests a triangle iff the triangle's own leaf box
+ *     passes; the wide walk is a conservative search for those leaves and evaluates the leaf box and the triangle with the
+ *     reference's arithmetic.  Used when the uploaded boxes are finite and nested and every triangle hangs under one leaf;
+ *     rays outside the finite range walk the binary image.
+ * IMAGE: the binary image only.  WIDE: same as AUTO.  REFERENCE_ORDER: walk the 80-byte nodes literally, dropped pushes
+ * counted — also what AUTO falls back to when the stack could overflow.  restir_get_bvh_info tells which one is in use.
+ * Takes effect at the next restir_upload_bvh.  Uploads whose child indices are out of range or that are not trees are rejected
+ * with RESTIR_E_INVALID.  A tree built by restir_build_bvh_device is walked through its binary image. */
 #define RESTIR_TRAVERSAL_AUTO 0
 #define RESTIR_TRAVERSAL_REFERENCE_ORDER 1
-#define RESTIR_TRAVERSAL_IMAGE 2 /* reported by restir_get_bvh_info only */
+#define RESTIR_TRAVERSAL_IMAGE 2
+#define RESTIR_TRAVERSAL_WIDE 3
 int restir_set_traversal(restir_context *ctx, int mode);
 
 typedef struct restir_bvh_info {
 	uint32_t nodes, triangles;
 	uint32_t reachable_nodes, depth;
 	uint32_t reference_stack_bound; /* worst-case occupancy of the reference's 32-entry stack on this tree */
-	int32_t traversal;              /* RESTIR_TRAVERSAL_IMAGE or RESTIR_TRAVERSAL_REFERENCE_ORDER */
+	int32_t traversal;              /* what the trace kernel walks: RESTIR_TRAVERSAL_WIDE, _IMAGE or _REFERENCE_ORDER */
+	uint32_t wide_nodes, wide_depth, wide_stack_bound; /* the 4-wide image (0 when not in use) */
 } restir_bvh_info;
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
+/* Host-only self-check of the WIDE traversal (no reference equivalent, no GPU, called by no pass): builds the wide image of
+ * the tree exactly as restir_upload_bvh does and walks it on the CPU with the operations the kernel uses (the box arithmetic is
+ * one header shared by host and device, csrc/wide_image.h) for n segments p1 -> p2 (3 floats each).  shadowed[i] = 1 when the
+ * segment is occluded; walked_wide[i] = 0 marks the segments the wide walk hands to the binary image (non-finite or
+ * out-of-range origin / direction: shadowed[i] is then 0); *visits (may be NULL) = wide nodes visited.  RESTIR_E_UNSUPPORTED
+ * when the tree is not walked wide (message says why). */
+int restir_check_wide_walk(const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles, const float *p1, const float *p2,
+                           uint64_t n, unsigned char *shadowed, unsigned char *walked_wide, uint64_t *visits, char *message, size_t message_bytes);
 /* No reference equivalent (the reference traces every ray it asks for).  The unbiased pass answers a neighbour ray
  * of unbiasedReuse.glsl:139-156 without walking the tree when the answer is already determined, exactly: the pixel's
  * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every

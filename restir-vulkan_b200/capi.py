@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RESTIR_B200_LIB") or os.path.join(_HERE, "librestir_b
 RESTIR_BUF_FRAME0, RESTIR_BUF_FRAME1, RESTIR_BUF_TEMP = 0, 1, 2
 RESTIR_OUT_RGBA32F, RESTIR_OUT_RGBA8_SRGB = 0, 1
 RESTIR_VISIBILITY_REUSE_FLAG, RESTIR_TEMPORAL_REUSE_FLAG = 1, 2
-RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_IMAGE = 0, 1, 2
+RESTIR_TRAVERSAL_AUTO, RESTIR_TRAVERSAL_REFERENCE_ORDER, RESTIR_TRAVERSAL_IMAGE, RESTIR_TRAVERSAL_WIDE = 0, 1, 2, 3
 RESTIR_E_INVALID, RESTIR_E_CUDA, RESTIR_E_NOMEM, RESTIR_E_UNSUPPORTED, RESTIR_E_HALO = -1, -2, -3, -4, -5
 
 RESERVOIR_DTYPE = np.dtype(
@@ -64,7 +64,7 @@ EXPORTS = [
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
     "restir_gbuffer_device_planes", "restir_import_external_memory", "restir_release_external_memory", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
     "restir_get_reservoir_bytes",
-    "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_profile_begin", "restir_profile_end",
+    "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_check_wide_walk", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
@@ -100,7 +100,8 @@ class Counters(C.Structure):
 
 
 class BvhInfo(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("nodes", "triangles", "reachable_nodes", "depth", "reference_stack_bound")] + [("traversal", C.c_int32)]
+    _fields_ = [(n, C.c_uint32) for n in ("nodes", "triangles", "reachable_nodes", "depth", "reference_stack_bound")] + [("traversal", C.c_int32)] + [
+        (n, C.c_uint32) for n in ("wide_nodes", "wide_depth", "wide_stack_bound")]
 
 
 class KernelTime(C.Structure):
@@ -209,6 +210,20 @@ def check_aabb_tree(nodes, n_triangles):
     info, msg = BvhInfo(), C.create_string_buffer(256)
     rc = load_library().restir_check_aabb_tree(_hp(nodes), C.c_uint32(nodes.shape[0]), C.c_uint32(n_triangles), C.byref(info), msg, C.c_size_t(256))
     return rc, {n: getattr(info, n) for n, _ in BvhInfo._fields_}, msg.value.decode()
+
+
+def check_wide_walk(nodes, triangles, p1, p2):
+    """restir_check_wide_walk: (rc, shadowed, walked_wide, visits, message).  Host only."""
+    nodes = np.ascontiguousarray(nodes).view(np.uint8).reshape(-1, 80)
+    tris = np.ascontiguousarray(triangles).view(np.uint8).reshape(-1, 48)
+    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 3)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 3)
+    n = p1.shape[0]
+    shadowed, walked = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    visits, msg = C.c_uint64(0), C.create_string_buffer(256)
+    rc = load_library().restir_check_wide_walk(_hp(nodes), C.c_uint32(nodes.shape[0]), _hp(tris), C.c_uint32(tris.shape[0]), _hp(p1), _hp(p2), C.c_uint64(n),
+                                               _hp(shadowed), _hp(walked), C.byref(visits), msg, C.c_size_t(256))
+    return rc, shadowed, walked, int(visits.value), msg.value.decode()
 
 
 def collect_triangle_lights(triangles, tri_material, material_emissive):

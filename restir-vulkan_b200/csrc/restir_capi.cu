@@ -16,6 +16,7 @@
 #include "../../include/restir_b200.h"
 #include "restir_kernels.h"
 #include "traversal_image.h"
+#include "wide_image.h"
 
 using namespace restir;
 
@@ -30,7 +31,10 @@ struct restir_context {
 	float4 *nodes = nullptr, *tris = nullptr;
 	float4 *image = nullptr; // 64-byte image of `nodes` (traversal_image.h); null => literal 80-byte walk
 	float4 *triEdges = nullptr; // 64-byte (p1, e1, e2) records of `tris` (restir_trace.cuh)
-	unsigned char *treeBlock = nullptr; // one allocation holding `image` then `triEdges`: what the trace kernel walks
+	uint4 *wide = nullptr;      // 4-wide quantised image of the same tree (wide_image.h); null => the binary image is walked
+	WideGrid wideGrid{};
+	WideImageInfo wideInfo;
+	unsigned char *treeBlock = nullptr; // one allocation holding `image`, `triEdges`, then `wide`: what the trace kernel walks
 	size_t treeBlockBytes = 0;
 	TraversalImageInfo imageInfo;
 	uint32_t nNodes = 0, nTris = 0;
@@ -376,6 +380,8 @@ TraceParams traceParams(const restir_context *ctx) {
 	tp.tris = ctx->tris;
 	tp.image = ctx->image;
 	tp.triEdges = ctx->triEdges;
+	tp.wide = ctx->wide;
+	tp.grid = ctx->wideGrid;
 	tp.nNodes = ctx->nNodes;
 	tp.band = ctx->band;
 	tp.shadowed = ctx->shadowed;
@@ -580,37 +586,80 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	if (!build_traversal_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, image, info, why)) {
 		return fail(ctx, RESTIR_E_INVALID, "restir_upload_bvh: %s", why.c_str());
 	}
+	const bool useImage = info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	// the 4-wide quantised image (wide_image.h): walked instead of the binary one wherever its exactness argument applies
+	std::vector<WideNode> wide;
+	std::vector<uint32_t> triOrder;
+	std::vector<float> leafBoxes;
+	WideGrid wideGrid{};
+	WideImageInfo wideInfo;
+	if (useImage && ctx->traversal != RESTIR_TRAVERSAL_IMAGE) {
+		build_wide_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, wide, triOrder, leafBoxes, wideGrid, wideInfo);
+	} else {
+		wideInfo.why = "not requested";
+	}
+	if (wideInfo.usable) {
+		// the triangle records are laid out in the order the wide leaves name them; the binary image (walked by the rays the
+		// wide walk does not take, and by the single-kernel variants) names the same records
+		std::vector<uint32_t> recordOf(n_triangles);
+		for (uint32_t r = 0; r < n_triangles; ++r) {
+			recordOf[triOrder[r]] = r;
+		}
+		for (Node64 &n : image) {
+			if (n.left < 0) n.left = ~(int32_t)recordOf[(uint32_t)~n.left];
+			if (n.right < 0) n.right = ~(int32_t)recordOf[(uint32_t)~n.right];
+		}
+	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	freeDev(ctx->nodes);
 	freeDev(ctx->tris);
 	freeDev(ctx->treeBlock);
 	ctx->image = ctx->triEdges = nullptr;
+	ctx->wide = nullptr;
+	ctx->wideInfo = WideImageInfo{};
 	ctx->nNodes = ctx->nTris = 0;
 	freeDev(ctx->gbAttrs); // per-triangle attributes belong to the previous triangle list
 	freeDev(ctx->gbTriMaterial);
 	ctx->gbTris = 0;
-	const bool useImage = info.usable && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
 	const size_t triBytes = (size_t)n_triangles * sizeof(restir_triangle);
 	CU(ctx, cudaMalloc(&ctx->nodes, (size_t)n_nodes * sizeof(restir_aabb_node)));
 	CU(ctx, cudaMalloc(&ctx->tris, triBytes));
 	CU(ctx, cudaMemcpyAsync(ctx->nodes, nodes, (size_t)n_nodes * sizeof(restir_aabb_node), cudaMemcpyHostToDevice, ctx->stream));
 	CU(ctx, cudaMemcpyAsync(ctx->tris, triangles, triBytes, cudaMemcpyHostToDevice, ctx->stream));
 	if (useImage) {
-		// what the trace kernel walks, in one allocation: the 64-byte nodes, then the 64-byte (p1, e1, e2) triangle records
+		// what the trace kernel walks, in one allocation: the 64-byte binary nodes, the 64-byte (p1, e1, e2 | leaf box) triangle
+		// records, the 64-byte 4-wide nodes (the leaf boxes pass through the tail of the block on their way into the records)
 		const size_t imageBytes = (image.size() * sizeof(Node64) + 255) & ~(size_t)255;
 		const size_t edgeBytes = (size_t)n_triangles * 64;
-		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes));
-		ctx->treeBlockBytes = imageBytes + edgeBytes;
+		const size_t wideBytes = (wide.size() * sizeof(WideNode) + 255) & ~(size_t)255;
+		const size_t boxBytes = wideInfo.usable ? leafBoxes.size() * sizeof(float) : 0;
+		const size_t orderBytes = wideInfo.usable ? triOrder.size() * sizeof(uint32_t) : 0;
+		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes + wideBytes + boxBytes + orderBytes));
+		ctx->treeBlockBytes = imageBytes + edgeBytes + wideBytes + boxBytes + orderBytes;
 		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
 		ctx->triEdges = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
 		CU(ctx, cudaMemcpyAsync(ctx->image, image.data(), image.size() * sizeof(Node64), cudaMemcpyHostToDevice, ctx->stream));
-		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, ctx->stream);
+		const float *boxes = nullptr;
+		const uint32_t *order = nullptr;
+		if (wideInfo.usable) {
+			ctx->wide = reinterpret_cast<uint4 *>(ctx->treeBlock + imageBytes + edgeBytes);
+			float *dstBoxes = reinterpret_cast<float *>(ctx->treeBlock + imageBytes + edgeBytes + wideBytes);
+			uint32_t *dstOrder = reinterpret_cast<uint32_t *>(ctx->treeBlock + imageBytes + edgeBytes + wideBytes + boxBytes);
+			CU(ctx, cudaMemcpyAsync(ctx->wide, wide.data(), wide.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
+			CU(ctx, cudaMemcpyAsync(dstBoxes, leafBoxes.data(), boxBytes, cudaMemcpyHostToDevice, ctx->stream));
+			CU(ctx, cudaMemcpyAsync(dstOrder, triOrder.data(), orderBytes, cudaMemcpyHostToDevice, ctx->stream));
+			boxes = dstBoxes;
+			order = dstOrder;
+		}
+		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, order, boxes, ctx->stream);
 		CU(ctx, cudaGetLastError());
 	}
 	CU(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->nNodes = n_nodes;
 	ctx->nTris = n_triangles;
 	ctx->imageInfo = info;
+	ctx->wideGrid = wideGrid;
+	ctx->wideInfo = wideInfo;
 	return RESTIR_OK;
 }
 
@@ -627,6 +676,9 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	freeDev(ctx->tris);
 	freeDev(ctx->treeBlock);
 	ctx->image = ctx->triEdges = nullptr;
+	ctx->wide = nullptr;
+	ctx->wideInfo = WideImageInfo{};
+	ctx->wideInfo.why = "tree built on the device: the binary image is walked (the wide image is derived on the host by restir_upload_bvh)";
 	ctx->nNodes = ctx->nTris = 0;
 	freeDev(ctx->gbAttrs);
 	freeDev(ctx->gbTriMaterial);
@@ -673,7 +725,7 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
 		ctx->triEdges = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
 		launch_bvh_image(reinterpret_cast<const restir_aabb_node *>(ctx->nodes), nNodes, ctx->image, ctx->stream);
-		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, ctx->stream);
+		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, nullptr, nullptr, ctx->stream);
 		CU(ctx, cudaGetLastError());
 	} else {
 		info.why = "deeper than the 32-entry stack";
@@ -1158,7 +1210,7 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count) {
 
 int restir_set_traversal(restir_context *ctx, int mode) {
 	ENTER(ctx);
-	if (mode != RESTIR_TRAVERSAL_AUTO && mode != RESTIR_TRAVERSAL_REFERENCE_ORDER) {
+	if (mode != RESTIR_TRAVERSAL_AUTO && mode != RESTIR_TRAVERSAL_REFERENCE_ORDER && mode != RESTIR_TRAVERSAL_IMAGE && mode != RESTIR_TRAVERSAL_WIDE) {
 		return fail(ctx, RESTIR_E_INVALID, "unknown traversal mode %d", mode);
 	}
 	ctx->traversal = mode;
@@ -1297,7 +1349,10 @@ int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out) {
 	out->reachable_nodes = ctx->imageInfo.reachableNodes;
 	out->depth = (uint32_t)ctx->imageInfo.depth;
 	out->reference_stack_bound = (uint32_t)ctx->imageInfo.referenceStackBound;
-	out->traversal = ctx->image ? RESTIR_TRAVERSAL_IMAGE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	out->traversal = ctx->wide ? RESTIR_TRAVERSAL_WIDE : ctx->image ? RESTIR_TRAVERSAL_IMAGE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	out->wide_nodes = ctx->wideInfo.nodes;
+	out->wide_depth = (uint32_t)ctx->wideInfo.depth;
+	out->wide_stack_bound = (uint32_t)ctx->wideInfo.stackBound;
 	return RESTIR_OK;
 }
 
@@ -1323,8 +1378,52 @@ int restir_check_aabb_tree(const void *nodes, uint32_t n_nodes, uint32_t n_trian
 		out->depth = (uint32_t)info.depth;
 		out->reference_stack_bound = (uint32_t)info.referenceStackBound;
 		out->traversal = info.usable ? RESTIR_TRAVERSAL_IMAGE : RESTIR_TRAVERSAL_REFERENCE_ORDER;
+		if (ok && info.usable) { // would restir_upload_bvh walk the 4-wide image?  (wide_image.h: nested finite boxes, one leaf per triangle)
+			std::vector<WideNode> wide;
+			std::vector<uint32_t> triOrder;
+			std::vector<float> leafBoxes;
+			WideGrid grid{};
+			WideImageInfo wi;
+			build_wide_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, wide, triOrder, leafBoxes, grid, wi);
+			if (wi.usable) {
+				out->traversal = RESTIR_TRAVERSAL_WIDE;
+				out->wide_nodes = wi.nodes;
+				out->wide_depth = (uint32_t)wi.depth;
+				out->wide_stack_bound = (uint32_t)wi.stackBound;
+			} else if (message && message_bytes && text.empty()) {
+				std::strncpy(message, wi.why.c_str(), message_bytes - 1);
+				message[message_bytes - 1] = 0;
+			}
+		}
 	}
 	return ok ? RESTIR_OK : RESTIR_E_INVALID;
+}
+
+int restir_check_wide_walk(const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles, const float *p1, const float *p2,
+                           uint64_t n, unsigned char *shadowed, unsigned char *walked_wide, uint64_t *visits, char *message, size_t message_bytes) {
+	if (message && message_bytes) message[0] = 0;
+	if (nodes == nullptr || triangles == nullptr || n_nodes == 0 || n_triangles == 0 || (n != 0 && (p1 == nullptr || p2 == nullptr || shadowed == nullptr || walked_wide == nullptr))) {
+		return RESTIR_E_INVALID;
+	}
+	std::vector<Node64> image;
+	TraversalImageInfo info;
+	std::string why;
+	if (!build_traversal_image(static_cast<const restir_aabb_node *>(nodes), n_nodes, n_triangles, image, info, why)) {
+		if (message && message_bytes) {
+			std::strncpy(message, why.c_str(), message_bytes - 1);
+			message[message_bytes - 1] = 0;
+		}
+		return RESTIR_E_INVALID;
+	}
+	if (!wide_walk_host(static_cast<const restir_aabb_node *>(nodes), n_nodes, static_cast<const restir_triangle *>(triangles), n_triangles, p1, p2, n, shadowed,
+	                    walked_wide, visits, why)) {
+		if (message && message_bytes) {
+			std::strncpy(message, why.c_str(), message_bytes - 1);
+			message[message_bytes - 1] = 0;
+		}
+		return RESTIR_E_UNSUPPORTED;
+	}
+	return RESTIR_OK;
 }
 
 int restir_pass_restir(restir_context *ctx, int gbuffer, int out_buffer, int prev_buffer) {

@@ -840,18 +840,24 @@ __global__ void derive_tri_table_kernel(const restir_tri_light *__restrict__ lig
 
 // (p1, e1 = p2 - p1, e2 = p3 - p1) records for the trace kernel (restir_trace.cuh ray_triangle_edges): the subtractions of
 // softwareRaytracing.glsl:16-17, made once per upload instead of once per test
-__global__ void derive_triangle_edges_kernel(const float4 *__restrict__ tris, uint32_t n, float4 *__restrict__ out) {
+// order (may be null: identity): record i holds triangle order[i] — the wide image names its leaves' records consecutively
+// (wide_image.h).  leafBoxes (may be null): per record the fp32 box of its leaf (min.xyz, max.xyz), kept in the spare floats
+// of the record for the wide walk's exact leaf test (restir_wide.cuh wide_leaf_hit).
+__global__ void derive_triangle_edges_kernel(const float4 *__restrict__ tris, uint32_t n, float4 *__restrict__ out, const uint32_t *__restrict__ order,
+                                             const float *__restrict__ leafBoxes) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) {
-		float4 a = tris[(size_t)i * 3], b = tris[(size_t)i * 3 + 1], c = tris[(size_t)i * 3 + 2];
+		const size_t t = order ? order[i] : i;
+		float4 a = tris[t * 3], b = tris[t * 3 + 1], c = tris[t * 3 + 2];
 		f3 p1 = mk3(a.x, a.y, a.z);
 		f3 e1 = mk3(b.x, b.y, b.z) - p1;
 		f3 e2 = mk3(c.x, c.y, c.z) - p1;
 		float4 *o = out + (size_t)i * 4;
 		o[0] = make_float4(p1.x, p1.y, p1.z, e1.x);
 		o[1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-		o[2] = make_float4(e2.z, 0.0f, 0.0f, 0.0f);
-		o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		const float *lb = leafBoxes ? leafBoxes + (size_t)i * 6 : nullptr;
+		o[2] = lb ? make_float4(e2.z, lb[0], lb[1], lb[2]) : make_float4(e2.z, 0.0f, 0.0f, 0.0f);
+		o[3] = lb ? make_float4(lb[3], lb[4], lb[5], 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 }
 
@@ -927,8 +933,8 @@ void launch_unpack_reservoirs(const SceneView &sc, const PackedReservoir *in, re
 void launch_pack_reservoirs(const restir_reservoir *in, PackedReservoir *out, size_t n, cudaStream_t s) {
 	if (n) pack_reservoirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
 }
-void launch_derive_triangle_edges(const float4 *tris, uint32_t n, float4 *out, cudaStream_t s) {
-	if (n) derive_triangle_edges_kernel<<<(n + 255) / 256, 256, 0, s>>>(tris, n, out);
+void launch_derive_triangle_edges(const float4 *tris, uint32_t n, float4 *out, const uint32_t *order, const float *leafBoxes, cudaStream_t s) {
+	if (n) derive_triangle_edges_kernel<<<(n + 255) / 256, 256, 0, s>>>(tris, n, out, order, leafBoxes);
 }
 void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
                                 cudaStream_t s) {

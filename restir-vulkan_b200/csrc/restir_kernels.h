@@ -2,6 +2,7 @@
 #pragma once
 
 #include "restir_device.cuh"
+#include "wide_image.h"
 
 namespace restir {
 
@@ -21,6 +22,8 @@ enum TraceMode {
 struct TraceParams {
 	const float4 *nodes, *tris, *image; // image == null: literal walk of the 80-byte nodes (restir_trace.cuh)
 	const float4 *triEdges;             // with image: 64-byte (p1, e1, e2) records derived from tris at upload (restir_trace.cuh)
+	const uint4 *wide;                  // 4-wide quantised image of the same tree (wide_image.h, restir_wide.cuh); null: the binary image is walked
+	WideGrid grid;
 	unsigned nNodes;
 	Band band;
 	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)
@@ -69,7 +72,7 @@ void launch_raycast_gbuffer(const SceneView &sc, const Band &band, const Raycast
                             void *albedo, void *normal, void *material, void *worldPos, void *depth, cudaStream_t s);
 void launch_unpack_reservoirs(const SceneView &sc, const PackedReservoir *in, restir_reservoir *out, size_t n, cudaStream_t s);
 void launch_pack_reservoirs(const restir_reservoir *in, PackedReservoir *out, size_t n, cudaStream_t s);
-void launch_derive_triangle_edges(const float4 *tris, uint32_t n, float4 *out, cudaStream_t s);
+void launch_derive_triangle_edges(const float4 *tris, uint32_t n, float4 *out, const uint32_t *order, const float *leafBoxes, cudaStream_t s);
 void launch_derive_light_tables(const restir_point_light *pl, int np, float4 *pointOut, const restir_tri_light *tl, int nt, float4 *triOut,
                                 cudaStream_t s);
 

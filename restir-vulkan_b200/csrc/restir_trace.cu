@@ -27,6 +27,7 @@
 
 #include "restir_kernels.h"
 #include "restir_trace.cuh"
+#include "restir_wide.cuh"
 
 namespace restir {
 
@@ -228,7 +229,22 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 #ifndef RESTIR_TRACE_REFILL
 #define RESTIR_TRACE_REFILL 0
 #endif
-template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
+// What a trace kernel walks: the uploaded 80-byte nodes in the reference's order, their 64-byte binary image, or the 4-wide
+// quantised image (restir_wide.cuh) with the binary image for the rays outside its range.
+enum TraceWalk { kWalkReference = 0, kWalkImage = 1, kWalkWide = 2 };
+
+// the binary walk for the rays the wide walk does not take (non-finite or out-of-range origin / direction: wide_image.h).
+// Inlined: as a __noinline__ call it crashes ptxas 12.9 (segmentation fault at every -O level).
+static __device__ __forceinline__ bool trace_any_image_call(const float4 *__restrict__ image, const float4 *__restrict__ tris, f3 o, f3 d) {
+	return trace_any_image(image, tris, o, d, nullptr);
+}
+
+#ifndef RESTIR_TRACE_MIN_BLOCKS_WIDE
+#define RESTIR_TRACE_MIN_BLOCKS_WIDE 4
+#endif
+template <int MODE, int WALK>
+__global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRACE_MIN_BLOCKS_WIDE : RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
+	constexpr bool IMAGE = WALK == kWalkImage;
 	constexpr int CHUNK = ChunkOf<MODE>::value;
 	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
 #if RESTIR_TRACE_TOP_SMEM > 0
@@ -362,7 +378,13 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 					f3 p1, p2, o, d;
 					size_t out = item_segment<MODE>(tp, item, p1, p2);
 					segment_setup(p1, p2, o, d);
-					bool clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d, topOfTree) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
+					bool clear;
+					if (WALK == kWalkWide) {
+						WideLaneRay wr;
+						clear = wide_lane_setup(tp.grid, o, d, wr) ? trace_any_wide(tp.wide, tp.triEdges, wr) : trace_any_image_call(tp.image, tp.triEdges, o, d);
+					} else {
+						clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d, topOfTree) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
+					}
 					tp.shadowed[out] = clear ? 0 : 1;
 					rays++;
 				}
@@ -383,10 +405,10 @@ template <int MODE, bool IMAGE> __global__ void __launch_bounds__(kTraceThreads,
 
 // ---- launcher ----------------------------------------------------------------------------------------------
 
-template <int MODE, bool IMAGE> static cudaError_t launch_mode(const TraceParams &tp, int smCount, cudaStream_t s) {
+template <int MODE, int WALK> static cudaError_t launch_mode(const TraceParams &tp, int smCount, cudaStream_t s) {
 	static int blocksPerSm = 0; // same for every device of one box
 	if (blocksPerSm == 0) {
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, trace_kernel<MODE, IMAGE>, kTraceThreads, 0);
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, trace_kernel<MODE, WALK>, kTraceThreads, 0);
 		if (e != cudaSuccess) {
 			return e;
 		}
@@ -408,7 +430,7 @@ template <int MODE, bool IMAGE> static cudaError_t launch_mode(const TraceParams
 		return ez;
 	}
 #endif
-	trace_kernel<MODE, IMAGE><<<grid, kTraceThreads, 0, s>>>(launch);
+	trace_kernel<MODE, WALK><<<grid, kTraceThreads, 0, s>>>(launch);
 	return cudaGetLastError();
 }
 
@@ -420,22 +442,31 @@ cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStrea
 	if (e != cudaSuccess) {
 		return e;
 	}
-	const bool image = tp.image != nullptr;
-	switch (mode) {
-	case kTracePixel: return image ? launch_mode<kTracePixel, true>(tp, smCount, s) : launch_mode<kTracePixel, false>(tp, smCount, s);
-	case kTraceUnbiased: return image ? launch_mode<kTraceUnbiased, true>(tp, smCount, s) : launch_mode<kTraceUnbiased, false>(tp, smCount, s);
-	default: return image ? launch_mode<kTraceSegments, true>(tp, smCount, s) : launch_mode<kTraceSegments, false>(tp, smCount, s);
+	const int walk = tp.image == nullptr ? kWalkReference : (tp.wide != nullptr && RESTIR_TRACE_TRI_EDGES && !RESTIR_TRACE_REFILL) ? kWalkWide : kWalkImage;
+	switch (mode * 3 + walk) {
+	case kTracePixel * 3 + kWalkReference: return launch_mode<kTracePixel, kWalkReference>(tp, smCount, s);
+	case kTracePixel * 3 + kWalkImage: return launch_mode<kTracePixel, kWalkImage>(tp, smCount, s);
+	case kTracePixel * 3 + kWalkWide: return launch_mode<kTracePixel, kWalkWide>(tp, smCount, s);
+	case kTraceUnbiased * 3 + kWalkReference: return launch_mode<kTraceUnbiased, kWalkReference>(tp, smCount, s);
+	case kTraceUnbiased * 3 + kWalkImage: return launch_mode<kTraceUnbiased, kWalkImage>(tp, smCount, s);
+	case kTraceUnbiased * 3 + kWalkWide: return launch_mode<kTraceUnbiased, kWalkWide>(tp, smCount, s);
+	case kTraceSegments * 3 + kWalkReference: return launch_mode<kTraceSegments, kWalkReference>(tp, smCount, s);
+	case kTraceSegments * 3 + kWalkImage: return launch_mode<kTraceSegments, kWalkImage>(tp, smCount, s);
+	default: return launch_mode<kTraceSegments, kWalkWide>(tp, smCount, s);
 	}
 }
 
 cudaError_t preload_trace_kernels() {
 	cudaFuncAttributes a;
-	cudaError_t e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, true>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, false>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, true>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, false>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, true>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, false>);
+	cudaError_t e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkImage>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkReference>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkWide>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkImage>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkReference>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkWide>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkImage>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkReference>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkWide>);
 	return e;
 }
 

@@ -1,0 +1,163 @@
+// restir_wide.cuh — the shadow-ray walk over the 4-wide quantised image of the uploaded tree (sm_100a).
+//
+// wide_image.h proves why the answer is the reference's: for rays in the finite range the reference tests a triangle iff its
+// own leaf box passes rayAabIntersection, so     shadowed <=> exists t: leafBox(t) passes && triangle(t) hit     and the
+// hierarchy above the leaves only has to be conservative.  Here the hierarchy is 4-wide with boxes on a 15-bit grid; the two
+// exact factors are evaluated at the leaves with the reference's arithmetic (ray_triangle_edges, ray_box_reference).
+//
+// One node visit = two 32-byte loads (four boxes + four children; the binary image: the same 64 bytes for two boxes), per
+// plane one byte permute (decode AND entry / exit selection) and half a packed fused multiply-add, per box two 3-input
+// min / max and three compares.  Measured against the binary walk in profiles/r2_j_summary.md.
+#pragma once
+
+#include "restir_trace.cuh"
+#include "wide_image.h"
+
+namespace restir {
+
+struct U8 {
+	unsigned v[8];
+};
+__device__ __forceinline__ U8 ldg256u(const void *p) {
+	U8 r;
+#ifdef WIDE_NO_LDG256
+	uint4 x = __ldg(reinterpret_cast<const uint4 *>(p)), y = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+	r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = x.w; r.v[4] = y.x; r.v[5] = y.y; r.v[6] = y.z; r.v[7] = y.w;
+	return r;
+#endif
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+	    : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+#ifdef WIDE_NO_MNMX3
+	return fmaxf(a, fmaxf(b, c));
+#else
+	float r;
+	asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); // FMNMX3
+	return r;
+#endif
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+#ifdef WIDE_NO_MNMX3
+	return fminf(a, fminf(b, c));
+#else
+	float r;
+	asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+	return r;
+#endif
+}
+
+// Per-ray constants of the conservative box test (wide_image.h wide_ray_setup, same operations), duplicated into both halves
+// of a register pair where a packed FFMA2 reads them.
+struct WideLaneRay {
+	f3 o, d;
+	float2 sx, sy, sz, cLoX, cLoY, cLoZ, cHiX, cHiY, cHiZ;
+	unsigned selNx, selNy, selNz; // the exit selector is the entry selector ^ 0x0220
+};
+
+__device__ __forceinline__ bool wide_lane_setup(const WideGrid &g, f3 o, f3 d, WideLaneRay &r) {
+	const float of[3] = {o.x, o.y, o.z}, df[3] = {d.x, d.y, d.z};
+	const float iv[3] = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+	WideRay w;
+	bool ok = wide_ray_setup(g, of, df, iv, w);
+	r.o = o;
+	r.d = d;
+	r.sx = make_float2(w.s[0], w.s[0]); r.sy = make_float2(w.s[1], w.s[1]); r.sz = make_float2(w.s[2], w.s[2]);
+	r.cLoX = make_float2(w.cLo[0], w.cLo[0]); r.cLoY = make_float2(w.cLo[1], w.cLo[1]); r.cLoZ = make_float2(w.cLo[2], w.cLo[2]);
+	r.cHiX = make_float2(w.cHi[0], w.cHi[0]); r.cHiY = make_float2(w.cHi[1], w.cHi[1]); r.cHiZ = make_float2(w.cHi[2], w.cHi[2]);
+	r.selNx = w.selNear[0]; r.selNy = w.selNear[1]; r.selNz = w.selNear[2];
+	return ok;
+}
+
+// entry / exit parameters of two children at once on one axis
+__device__ __forceinline__ void wide_axis_pair(unsigned w0, unsigned w1, unsigned selN, float2 s, float2 cLo, float2 cHi, float2 &tn, float2 &tf) {
+	const unsigned selF = selN ^ 0x0220u;
+	float2 vn = make_float2(__uint_as_float(__byte_perm(w0, 0x3F000000u, selN)), __uint_as_float(__byte_perm(w1, 0x3F000000u, selN)));
+	float2 vf = make_float2(__uint_as_float(__byte_perm(w0, 0x3F000000u, selF)), __uint_as_float(__byte_perm(w1, 0x3F000000u, selF)));
+#ifdef WIDE_NO_FFMA2
+	tn = make_float2(fmaf(vn.x, s.x, cLo.x), fmaf(vn.y, s.y, cLo.y));
+	tf = make_float2(fmaf(vf.x, s.x, cHi.x), fmaf(vf.y, s.y, cHi.y));
+#else
+	tn = __ffma2_rn(vn, s, cLo);
+	tf = __ffma2_rn(vf, s, cHi);
+#endif
+}
+
+// (*) of wide_image.h at a leaf: the reference's triangle test, then the reference's slab test on the leaf's own fp32 box
+// (kept in the spare floats of the 64-byte triangle record: e2.z, min.xyz | max.xyz, -)
+__device__ __forceinline__ bool wide_leaf_hit(const float4 *__restrict__ triRec, unsigned id, const WideLaneRay &r) {
+	if (!ray_triangle_edges(triRec, (int)id, r.o, r.d)) {
+		return false;
+	}
+	const float4 *t = triRec + (size_t)id * 4;
+	float4 a = __ldg(t + 2), b = __ldg(t + 3);
+	f3 inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+	return ray_box_reference(r.o, inv, make_float4(a.y, a.z, a.w, 0.0f), make_float4(b.x, b.y, b.z, 0.0f));
+}
+
+// Returns true when nothing is hit.  The caller has checked wide_lane_setup.
+//
+// The walk's unit is a GROUP: (first child node << 4) | 4-bit mask of the children still to visit.  The inner children a visit
+// finds hit become the current group in one step — no index word per child (wide_image.h: children of a node are numbered
+// consecutively), no push per child — and the group left over from the level above goes on the stack as ONE entry, so the
+// stack holds one entry per level of the wide tree (<= kWideStack, checked at upload).
+__device__ __forceinline__ bool trace_any_wide(const uint4 *__restrict__ wide, const float4 *__restrict__ triRec, const WideLaneRay &r) {
+	unsigned stack[kWideStack];
+	int top = 0;
+	unsigned group = 1u; // node 0, one child to visit: the root
+	for (;;) {
+		if ((group & 15u) == 0u) {
+			if (top == 0) {
+				return true;
+			}
+			group = stack[--top];
+		}
+		const unsigned slot = (unsigned)__ffs((int)(group & 15u)) - 1u;
+		group &= group - 1u; // the lowest set bit lies in the mask
+		const uint4 *n = wide + ((size_t)((group >> 4) + slot)) * 4u;
+		const U8 a = ldg256u(n), b = ldg256u(n + 2); // a: x words of the four slots, y words; b: z words, (childBase, triBase, inner, count)
+		float2 nx, fx, ny, fy, nz, fz;
+		unsigned hits;
+		// slots 0 and 1
+		wide_axis_pair(a.v[0], a.v[1], r.selNx, r.sx, r.cLoX, r.cHiX, nx, fx);
+		wide_axis_pair(a.v[4], a.v[5], r.selNy, r.sy, r.cLoY, r.cHiY, ny, fy);
+		wide_axis_pair(b.v[0], b.v[1], r.selNz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
+		{
+			float n0 = fmax3(nx.x, ny.x, nz.x), f0 = fmin3(fx.x, fy.x, fz.x), n1 = fmax3(nx.y, ny.y, nz.y), f1 = fmin3(fx.y, fy.y, fz.y);
+			hits = (n0 <= f0 && n0 <= 1.0f && f0 >= 0.0f ? 1u : 0u) | (n1 <= f1 && n1 <= 1.0f && f1 >= 0.0f ? 2u : 0u);
+		}
+		// slots 2 and 3
+		wide_axis_pair(a.v[2], a.v[3], r.selNx, r.sx, r.cLoX, r.cHiX, nx, fx);
+		wide_axis_pair(a.v[6], a.v[7], r.selNy, r.sy, r.cLoY, r.cHiY, ny, fy);
+		wide_axis_pair(b.v[2], b.v[3], r.selNz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
+		{
+			float n0 = fmax3(nx.x, ny.x, nz.x), f0 = fmin3(fx.x, fy.x, fz.x), n1 = fmax3(nx.y, ny.y, nz.y), f1 = fmin3(fx.y, fy.y, fz.y);
+			hits |= (n0 <= f0 && n0 <= 1.0f && f0 >= 0.0f ? 4u : 0u) | (n1 <= f1 && n1 <= 1.0f && f1 >= 0.0f ? 8u : 0u);
+		}
+		// hit leaves: slots [inner, count), records triBase + (slot - inner); empty slots are never hit (inverted boxes)
+		unsigned leaf = hits >> b.v[6];
+		if (leaf != 0u) {
+#pragma unroll 1
+			do {
+				const unsigned j = (unsigned)__ffs((int)leaf) - 1u;
+				leaf &= leaf - 1u;
+				if (wide_leaf_hit(triRec, b.v[5] + j, r)) {
+					return false;
+				}
+			} while (leaf != 0u);
+		}
+		// hit inner children: slots [0, inner), nodes childBase + slot
+		const unsigned inner = hits & ~(0xffffffffu << b.v[6]);
+		if (inner != 0u) {
+			if ((group & 15u) != 0u) {
+				stack[top++] = group;
+			}
+			group = (b.v[4] << 4) | inner;
+		}
+	}
+}
+
+} // namespace restir

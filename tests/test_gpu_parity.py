@@ -89,7 +89,7 @@ def test_shadow_rays_bit_exact(name, n_rays):
 
 
 def test_traversal_modes_agree_and_report():
-    """The 64-byte re-stride and the literal 80-byte walk of the same uploaded tree give the same bits; a tree
+    """The 4-wide quantised image, the 64-byte re-stride and the literal 80-byte walk of the same uploaded tree give the same bits; a tree
     whose child indices are out of range is rejected at upload instead of being traversed."""
     torch = _torch()
     scene = _scene("procedural:tri")
@@ -100,14 +100,16 @@ def test_traversal_modes_agree_and_report():
     p2 = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
     d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
     outs = []
-    for mode in (capi.RESTIR_TRAVERSAL_AUTO, capi.RESTIR_TRAVERSAL_REFERENCE_ORDER):
+    for mode in (capi.RESTIR_TRAVERSAL_AUTO, capi.RESTIR_TRAVERSAL_IMAGE, capi.RESTIR_TRAVERSAL_REFERENCE_ORDER):
         ctx = capi.RestirContext(0)
         ctx.set_traversal(mode)
         ctx.upload_bvh(scene.nodes, scene.triangles)
         info = ctx.bvh_info()
         if mode == capi.RESTIR_TRAVERSAL_AUTO:
-            assert info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE and 0 < info["wide_nodes"] < scene.nodes.shape[0]
             assert info["reachable_nodes"] == scene.nodes.shape[0] and info["reference_stack_bound"] <= 32
+        elif mode == capi.RESTIR_TRAVERSAL_IMAGE:
+            assert info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE and info["wide_nodes"] == 0
         else:
             assert info["traversal"] == capi.RESTIR_TRAVERSAL_REFERENCE_ORDER
         out = torch.zeros(n, dtype=torch.uint8, device="cuda")
@@ -116,7 +118,7 @@ def test_traversal_modes_agree_and_report():
         ctx.synchronize()
         outs.append(out.cpu().numpy())
         ctx.close()
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     want = ph.oracle().trace_segments(ph.oracle_scene(scene), p1, p2)
     assert np.array_equal(outs[0], want)
     bad = scene.nodes.copy()

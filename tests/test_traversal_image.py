@@ -17,7 +17,8 @@ def test_shipped_scenes_known_answers(name, stack, depth):
     scene = fixtures.load_baked(name, rebuild=False)          # the reference builder's own nodes
     rc, info, msg = capi.check_aabb_tree(scene.nodes, scene.n_triangles)
     assert rc == 0 and msg == ""
-    assert info["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE
+    assert info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE      # the reference's trees are nested and finite: wide_image.h applies
+    assert info["wide_depth"] <= (depth + 1) // 2 + 4 and info["wide_stack_bound"] <= 32 and info["wide_nodes"] < scene.nodes.shape[0]
     assert info["reachable_nodes"] == scene.nodes.shape[0] == scene.n_triangles - 1
     assert info["reference_stack_bound"] == stack
     assert info["depth"] == depth
