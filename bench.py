@@ -376,6 +376,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         c.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
         c.set_spatial_staging(args.spatial_staging == "on")
+        c.set_occluder_cache(args.occluder_cache == "on")
         if variant != (1, False, False):
             c.set_reservoir_variant(*variant)
         return c
@@ -520,7 +521,8 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
     counters = ctx.counters(reset=True, check=False)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, float(counters["shadow_rays"]), float(counters["kernel_launches"]), float(counters["halo_misses"]),
-                      float(counters["stack_overflows"]), float(counters["halo_wait_timeouts"]), float(counters["shadow_rays_traced"])],
+                      float(counters["stack_overflows"]), float(counters["halo_wait_timeouts"]), float(counters["shadow_rays_traced"]),
+                      float(counters["shadow_rays_cached"])],
                      dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -529,7 +531,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms = float(tmax[0])
         t = tsum
-    rays_total, launches, halo_misses, overflows, halo_timeouts, walked_total = (float(t[j]) for j in range(1, 7))
+    rays_total, launches, halo_misses, overflows, halo_timeouts, walked_total, cached_total = (float(t[j]) for j in range(1, 8))
     ms_per_frame = dev_ms / steps
     mrays = rays_total / (dev_ms * 1e-3) / 1e6
     mrays_walked = walked_total / (dev_ms * 1e-3) / 1e6
@@ -878,6 +880,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
                    "parallelism": f"row-bands x{world} ({balance_note}), halo exchange: {'own kernels over NVLink peer memory' if args.halo == 'peer' else 'NCCL send/recv'}, "
                                   f"halo {halo} rows (spatial reach {HALO}, temporal reprojection reach measured on the host)"},
         "rays_per_frame": rays_total / steps, "rays_walked_per_frame": walked_total / steps,
+        "rays_answered_by_cached_occluder_per_frame": cached_total / steps,
         "kernel_ms": kernel_ms, "kernel_launches_per_frame": kernel_launches, "kernel_hbm_frac": kernel_hbm_frac,
         "trace_kernel_mrays_walked_per_s": trace_mrays_walked,
         "hbm_frame_frac": hbm_frame_frac, "frame_algorithmic_bytes": frame_bytes_all,
@@ -902,6 +905,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--traversal", default="auto", choices=["auto", "image", "reference-order"],
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
+    ap.add_argument("--occluder-cache", default="on", choices=["on", "off"],
+                    help="trace kernel: test the cached occluder of (screen region, light) before queueing a ray for a walk (exact; A/B)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],

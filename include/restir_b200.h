@@ -208,6 +208,14 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
 #define RESTIR_TRAVERSAL_WIDE 3
 int restir_set_traversal(restir_context *ctx, int mode);
 
+/* No reference equivalent.  With the WIDE traversal the trace kernel keeps, per 64 x 32-pixel screen region and light, the last
+ * triangle that occluded a ray, and tests it (the reference's triangle test and the reference's slab test on its leaf box)
+ * before queueing a ray for a walk: "shadowed" needs one witness, and most shadowed rays of a region at a light share theirs.
+ * The table only proposes witnesses — its contents cannot change a visibility bit — but shadow_rays_traced then depends on
+ * what earlier frames left in it.  enable = 0 walks every ray that is not elided (A/B, deterministic counters); both settings
+ * clear the table.  Default: 1. */
+int restir_set_occluder_cache(restir_context *ctx, int enable);
+
 typedef struct restir_bvh_info {
 	uint32_t nodes, triangles;
 	uint32_t reachable_nodes, depth;
@@ -341,6 +349,8 @@ typedef struct restir_counters {
 	uint64_t shadow_rays_traced; /* of shadow_rays, the ones that needed a walk of the tree: the rest were answered exactly
 	                              * without one (neighbour rays of a pixel whose own ray is shadowed, unbiasedReuse.glsl:157-166;
 	                              * neighbour rays bit-identical to the neighbour's own ray) */
+	uint64_t shadow_rays_cached; /* of shadow_rays, the ones answered "shadowed" by the occluder cache: one exact triangle + leaf-box test
+	                              * of a triangle that occluded an earlier ray of the same screen region at the same light, no walk */
 } restir_counters;
 /* Synchronises the stream.  `out` is always filled; the return value is RESTIR_E_HALO when halo_wait_timeouts != 0. */
 int restir_get_counters(restir_context *ctx, restir_counters *out, int reset);

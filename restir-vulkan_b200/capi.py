@@ -64,7 +64,7 @@ EXPORTS = [
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
     "restir_gbuffer_device_planes", "restir_import_external_memory", "restir_release_external_memory", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
     "restir_get_reservoir_bytes",
-    "restir_set_traversal", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_check_wide_walk", "restir_profile_begin", "restir_profile_end",
+    "restir_set_traversal", "restir_set_occluder_cache", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_check_wide_walk", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
@@ -96,7 +96,7 @@ class Texture(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("shadow_rays", "stack_overflows", "halo_misses", "kernel_launches", "halo_wait_timeouts",
-                                            "shadow_rays_traced")]
+                                            "shadow_rays_traced", "shadow_rays_cached")]
 
 
 class BvhInfo(C.Structure):
@@ -451,6 +451,9 @@ class RestirContext:
     def set_spatial_staging(self, enable):
         self._check(self.lib.restir_set_spatial_staging(self._ctx, C.c_int(1 if enable else 0)))
 
+    def set_occluder_cache(self, enable):
+        self._check(self.lib.restir_set_occluder_cache(self._ctx, C.c_int(1 if enable else 0)))
+
     def set_traversal(self, mode):
         """Takes effect at the next upload_bvh."""
         self._check(self.lib.restir_set_traversal(self._ctx, C.c_int(mode)))
@@ -539,7 +542,7 @@ class RestirContext:
             self._check(rc)
         return {"shadow_rays": c.shadow_rays, "stack_overflows": c.stack_overflows, "halo_misses": c.halo_misses,
                 "kernel_launches": c.kernel_launches, "shadow_rays_traced": c.shadow_rays_traced,
-                "halo_wait_timeouts": c.halo_wait_timeouts}
+                "halo_wait_timeouts": c.halo_wait_timeouts, "shadow_rays_cached": c.shadow_rays_cached}
 
     def raycast_gbuffer(self, cam, tri_material, material_table, albedo, normal, material, world_pos, depth):
         self._check(self.lib.restir_tools_raycast_gbuffer(self._ctx, C.byref(cam), _dp(tri_material), _dp(material_table), _dp(albedo),

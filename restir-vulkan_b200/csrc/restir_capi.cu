@@ -106,6 +106,10 @@ struct restir_context {
 	int rayElision = 1; // restir_set_ray_elision
 	bool spatialStaging = false; // restir_set_spatial_staging
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
+	unsigned *occluders = nullptr;          // device, occluder cache of the trace kernel (restir_trace.cu): [region][256] entries
+	size_t occluderEntries = 0;
+	unsigned regionsX = 0;
+	int occluderCache = 1;
 	unsigned *traceCursors = nullptr;       // device, kTraceMaxRegions + kTraceMaxSms words (restir_trace.cu, RESTIR_TRACE_AFFINE)
 	uint64_t launches = 0;
 
@@ -374,6 +378,13 @@ int haloPush(restir_context *ctx, int buffer) {
 	return afterLaunch(ctx, "halo_push_kernel");
 }
 
+int clearOccluders(restir_context *ctx) {
+	if (ctx->occluders != nullptr) {
+		CU(ctx, cudaMemsetAsync(ctx->occluders, 0xff, ctx->occluderEntries * sizeof(unsigned), ctx->stream));
+	}
+	return RESTIR_OK;
+}
+
 TraceParams traceParams(const restir_context *ctx) {
 	TraceParams tp{};
 	tp.nodes = ctx->nodes;
@@ -383,6 +394,9 @@ TraceParams traceParams(const restir_context *ctx) {
 	tp.wide = ctx->wide;
 	tp.grid = ctx->wideGrid;
 	tp.nNodes = ctx->nNodes;
+	tp.nTris = ctx->nTris;
+	tp.occluders = (ctx->occluderCache && ctx->wide != nullptr && ctx->nTris < (1u << 24)) ? ctx->occluders : nullptr;
+	tp.regionsX = ctx->regionsX;
 	tp.band = ctx->band;
 	tp.shadowed = ctx->shadowed;
 	tp.counters = ctx->counters;
@@ -543,6 +557,7 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->staging);
 	freeDev(ctx->counters);
 	freeDev(ctx->traceCursors);
+	freeDev(ctx->occluders);
 	for (auto &r : ctx->reservoirs) {
 		freeDev(r);
 	}
@@ -660,7 +675,7 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	ctx->imageInfo = info;
 	ctx->wideGrid = wideGrid;
 	ctx->wideInfo = wideInfo;
-	return RESTIR_OK;
+	return clearOccluders(ctx); // its entries name triangle records of the previous tree
 }
 
 int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t n_triangles, void *nodes_out) {
@@ -780,6 +795,10 @@ int restir_upload_lights(restir_context *ctx, const void *point_blob, size_t poi
 	for (auto &r : ctx->genericReservoirs) {
 		if (r) CU(ctx, cudaMemsetAsync(r, 0, ctx->allocPixels() * ctx->reservoirBytes(), ctx->stream));
 	}
+	{
+		int rc = clearOccluders(ctx); // keyed by light index
+		if (rc != RESTIR_OK) return rc;
+	}
 	freeDev(ctx->pointPosLum);
 	freeDev(ctx->triAux);
 	if (ctx->pointCount) CU(ctx, cudaMalloc(&ctx->pointPosLum, sizeof(float4) * (size_t)ctx->pointCount));
@@ -821,6 +840,12 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 	b.allocBegin = (int)(row_begin > halo ? row_begin - halo : 0);
 	b.allocEnd = (int)((uint64_t)row_end + halo < height ? row_end + halo : height);
 	ctx->band = b;
+	// occluder cache: 256 entries per 64 x 32-pixel region of the rows this context holds, all empty
+	freeDev(ctx->occluders);
+	ctx->regionsX = (width + 63) / 64;
+	ctx->occluderEntries = (size_t)ctx->regionsX * (((size_t)(b.allocEnd - b.allocBegin) + 31) / 32) * 256;
+	CU(ctx, cudaMalloc(&ctx->occluders, ctx->occluderEntries * sizeof(unsigned)));
+	CU(ctx, cudaMemsetAsync(ctx->occluders, 0xff, ctx->occluderEntries * sizeof(unsigned), ctx->stream));
 	if (ctx->generic()) {
 		size_t bytes = ctx->allocPixels() * ctx->reservoirBytes();
 		for (auto &r : ctx->genericReservoirs) { // app.h:264-284: three buffers, zero-filled
@@ -1339,6 +1364,12 @@ int restir_set_ray_elision(restir_context *ctx, int enable) {
 	return RESTIR_OK;
 }
 
+int restir_set_occluder_cache(restir_context *ctx, int enable) {
+	ENTER(ctx);
+	ctx->occluderCache = enable ? 1 : 0;
+	return clearOccluders(ctx);
+}
+
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out) {
 	if (ctx == nullptr || out == nullptr) {
 		return RESTIR_E_INVALID;
@@ -1765,6 +1796,7 @@ int restir_get_counters(restir_context *ctx, restir_counters *out, int reset) {
 	if (out) {
 		out->shadow_rays = h[kCounterRays];
 		out->shadow_rays_traced = h[kCounterTraced];
+		out->shadow_rays_cached = h[kCounterCached];
 		out->halo_wait_timeouts = h[kCounterHaloTimeout];
 		out->stack_overflows = h[kCounterOverflow];
 		out->halo_misses = h[kCounterHaloMiss];

@@ -52,8 +52,9 @@ struct Band {
 	int allocBegin, allocEnd;
 };
 
-enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterWork = 3, kCounterTraced = 4, kCounterHaloTimeout = 5, kCounterCount = 6 };
+enum CounterSlot { kCounterRays = 0, kCounterOverflow = 1, kCounterHaloMiss = 2, kCounterWork = 3, kCounterTraced = 4, kCounterHaloTimeout = 5, kCounterCached = 6, kCounterCount = 7 };
 // kCounterRays counts the reference's testVisibility calls that were answered, kCounterTraced the ones that needed a walk of the tree.
+// kCounterCached (part of kCounterRays): answered by the occluder cache — one triangle test instead of a walk (restir_trace.cu).
 // kCounterWork is the persistent trace kernel's work cursor (zeroed before every trace launch).
 
 struct PassParams {

@@ -24,6 +24,9 @@ struct TraceParams {
 	const float4 *triEdges;             // with image: 64-byte (p1, e1, e2) records derived from tris at upload (restir_trace.cuh)
 	const uint4 *wide;                  // 4-wide quantised image of the same tree (wide_image.h, restir_wide.cuh); null: the binary image is walked
 	WideGrid grid;
+	unsigned *occluders;                // occluder cache (restir_trace.cu): [screen region][256] -> tag << 24 | triangle record; null: off
+	unsigned regionsX;                  // regions (64 x 32 pixels) per region row
+	unsigned nTris;
 	unsigned nNodes;
 	Band band;
 	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)

@@ -56,6 +56,10 @@ template <int MODE> struct ChunkOf {
 #endif
 constexpr unsigned kInvalidKey = 0xffffffffu;
 
+// What a trace kernel walks: the uploaded 80-byte nodes in the reference's order, their 64-byte binary image, or the 4-wide
+// quantised image (restir_wide.cuh) with the binary image for the rays outside its range.
+enum TraceWalk { kWalkReference = 0, kWalkImage = 1, kWalkWide = 2 };
+
 // ---- item -> pixel, key, segment ---------------------------------------------------------------------------
 
 __device__ __forceinline__ bool item_pixel(const TraceParams &tp, unsigned p, size_t &pix) {
@@ -143,8 +147,25 @@ template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParam
 	return kItemRay;
 }
 
+// ---- occluder cache -------------------------------------------------------------------------------------------------------
+// 86 % of restirOmni's selected candidates are shadowed (Sponza, 200 lights), and the triangle that shadows one pixel from a
+// light shadows most of its neighbourhood from that light: measured on the CPU over three frames, the last occluder found for
+// (64 x 32-pixel screen region, light) answers 3 of 4 shadowed rays of the next frame (profiles/r2_j_summary.md).  A shadowed
+// answer needs ONE witness — (*) of wide_image.h: the triangle hit with the reference's arithmetic and its leaf box passed with
+// the reference's arithmetic — so before a ray is queued for a walk the cached triangle of its (region, light) is tested,
+// exactly; a hit answers the ray (and frees its lane: the sort moves answered items behind the rays), a miss costs one
+// triangle test.  Walks that find an occluder record it.  The table only ever proposes witnesses, so its contents (racy
+// plain stores, stale entries of earlier frames) cannot change a bit of the result.
+// Entry = tag (bits 8..15 of the light index) << 24 | triangle record; 0xffffffff = empty (records stay below 2^24).
+constexpr unsigned kOccluderSlots = 256;
+__device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t opix, unsigned light) {
+	const unsigned W = (unsigned)tp.band.W, n = (unsigned)opix;
+	const unsigned yl = n / W, x = n - yl * W;
+	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (light & (kOccluderSlots - 1u));
+}
+
 // Sort key of an item: (light the ray is aimed at, position in the chunk); kInvalidKey = nothing to trace.
-template <int MODE> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local, unsigned &answered) {
+template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local, unsigned &answered, unsigned &cached) {
 	if (item >= tp.nItems) {
 		return kInvalidKey;
 	}
@@ -157,19 +178,35 @@ template <int MODE> __device__ __forceinline__ unsigned item_key(const TracePara
 		answered += state == kItemAnswered ? 1u : 0u;
 		return kInvalidKey;
 	}
-	unsigned light = RESTIR_TRACE_SORT ? (unsigned)__ldg(reinterpret_cast<const int *>(tp.reservoirs + pix) + 3) : 0u; // PackedReservoir::lightIndex
-	return ((light & 0x7fffffu) << 8) | local;
+	const unsigned light = (unsigned)__ldg(reinterpret_cast<const int *>(tp.reservoirs + pix) + 3); // PackedReservoir::lightIndex
+	if (WALK == kWalkWide && tp.occluders != nullptr) {
+		const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, light));
+		const unsigned rec = e & 0xffffffu;
+		if ((e >> 24) == ((light >> 8) & 255u) && rec < tp.nTris) {
+			float4 w = __ldg(tp.worldPos + opix);
+			float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+			f3 o, d;
+			segment_setup(mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z), o, d);
+			if (wide_ray_in_range(tp.grid, o, d) && wide_leaf_hit(tp.triEdges, rec, o, d)) {
+				tp.shadowed[out] = 1;
+				cached++;
+				return kInvalidKey;
+			}
+		}
+	}
+	return (((RESTIR_TRACE_SORT ? light : 0u) & 0x7fffffu) << 8) | local;
 }
 
 // Segment of an item item_key found to be a ray; returns the index of its visibility byte.
-template <int MODE> __device__ __forceinline__ size_t item_segment(const TraceParams &tp, unsigned item, f3 &p1, f3 &p2) {
+template <int MODE> __device__ __forceinline__ size_t item_segment(const TraceParams &tp, unsigned item, f3 &p1, f3 &p2, size_t &opix) {
 	if (MODE == kTraceSegments) {
 		const float *a = tp.segP1 + (size_t)item * 3, *b = tp.segP2 + (size_t)item * 3;
 		p1 = mk3(a[0], a[1], a[2]);
 		p2 = mk3(b[0], b[1], b[2]);
+		opix = 0;
 		return item;
 	}
-	size_t pix, opix, out;
+	size_t pix, out;
 	if (MODE == kTracePixel) {
 		item_resolve<MODE>(tp, item, pix, opix, out, false);
 	} else {
@@ -229,9 +266,6 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 #ifndef RESTIR_TRACE_REFILL
 #define RESTIR_TRACE_REFILL 0
 #endif
-// What a trace kernel walks: the uploaded 80-byte nodes in the reference's order, their 64-byte binary image, or the 4-wide
-// quantised image (restir_wide.cuh) with the binary image for the rays outside its range.
-enum TraceWalk { kWalkReference = 0, kWalkImage = 1, kWalkWide = 2 };
 
 // the binary walk for the rays the wide walk does not take (non-finite or out-of-range origin / direction: wide_image.h).
 // Inlined: as a __noinline__ call it crashes ptxas 12.9 (segmentation fault at every -O level).
@@ -242,8 +276,8 @@ static __device__ __forceinline__ bool trace_any_image_call(const float4 *__rest
 #ifndef RESTIR_TRACE_MIN_BLOCKS_WIDE
 #define RESTIR_TRACE_MIN_BLOCKS_WIDE 4
 #endif
-template <int MODE, int WALK>
-__global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRACE_MIN_BLOCKS_WIDE : RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
+template <int MODE, int WALK> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
+	static_assert(WALK != kWalkWide, "the wide image is walked by trace_wide_kernel");
 	constexpr bool IMAGE = WALK == kWalkImage;
 	constexpr int CHUNK = ChunkOf<MODE>::value;
 	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
@@ -263,7 +297,7 @@ __global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRAC
 	const unsigned lane = threadIdx.x & 31u;
 	unsigned *keys = allKeys[threadIdx.x >> 5];
 	const unsigned full = 0xffffffffu;
-	unsigned rays = 0, answered = 0, overflow = 0;
+	unsigned rays = 0, answered = 0, overflow = 0, cached = 0;
 	const float4 *const walkTris = RESTIR_TRACE_TRI_EDGES ? tp.triEdges : tp.tris;
 
 #if RESTIR_TRACE_AFFINE
@@ -311,7 +345,7 @@ __global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRAC
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned local = r * 32u + lane;
-			unsigned key = item_key<MODE>(tp, base + local, local, answered);
+			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached);
 			keys[local] = key;
 			valid += __popc(__ballot_sync(full, key != kInvalidKey));
 		}
@@ -341,7 +375,8 @@ __global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRAC
 						unsigned key = keys[mine];
 						if (key != kInvalidKey) {
 							f3 p1, p2, o, d;
-							out = item_segment<MODE>(tp, base + (key & 255u), p1, p2);
+							size_t opix;
+							out = item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
 							segment_setup(p1, p2, o, d);
 							ray = walk_ray(o, d);
 							top = 0;
@@ -376,15 +411,10 @@ __global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRAC
 				if (key != kInvalidKey) {
 					unsigned item = base + (key & 255u);
 					f3 p1, p2, o, d;
-					size_t out = item_segment<MODE>(tp, item, p1, p2);
+					size_t opix;
+					size_t out = item_segment<MODE>(tp, item, p1, p2, opix);
 					segment_setup(p1, p2, o, d);
-					bool clear;
-					if (WALK == kWalkWide) {
-						WideLaneRay wr;
-						clear = wide_lane_setup(tp.grid, o, d, wr) ? trace_any_wide(tp.wide, tp.triEdges, wr) : trace_any_image_call(tp.image, tp.triEdges, o, d);
-					} else {
-						clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d, topOfTree) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
-					}
+					bool clear = IMAGE ? trace_any_image(tp.image, walkTris, o, d, topOfTree) : trace_any_reference(tp.nodes, tp.tris, o, d, overflow);
 					tp.shadowed[out] = clear ? 0 : 1;
 					rays++;
 				}
@@ -394,21 +424,135 @@ __global__ void __launch_bounds__(kTraceThreads, WALK == kWalkWide ? RESTIR_TRAC
 	}
 	// one atomic per warp
 	rays = __reduce_add_sync(full, rays);
-	answered = __reduce_add_sync(full, answered);
+	answered = __reduce_add_sync(full, answered + cached);
+	cached = __reduce_add_sync(full, cached);
 	overflow = __reduce_add_sync(full, overflow);
 	if (lane == 0) {
 		if (rays + answered) atomicAdd(tp.counters + kCounterRays, (unsigned long long)(rays + answered));
 		if (rays) atomicAdd(tp.counters + kCounterTraced, (unsigned long long)rays);
 		if (overflow) atomicAdd(tp.counters + kCounterOverflow, (unsigned long long)overflow);
+		if (cached) atomicAdd(tp.counters + kCounterCached, (unsigned long long)cached);
+	}
+}
+
+// ---- the kernel that walks the wide image ---------------------------------------------------------------------------------------
+// Same persistent structure (chunks from a global cursor, items resolved and keyed, sorted by light, lockstep batches), built
+// around the walk's register budget: at 64 registers (4 CTAs per SM) everything that lives across a walk competes with the
+// walk's own operands, so the segment's origin and direction wait in shared memory for the leaf tests, the counters are per-warp
+// words in shared memory fed by votes, and what a finished ray needs (its visibility byte, its cache entry) is derived again
+// from its key.  Rays outside the wide walk's range (wide_image.h) walk the binary image after the batch.
+template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS_WIDE) trace_wide_kernel(const __grid_constant__ TraceParams tp) {
+	constexpr int CHUNK = ChunkOf<MODE>::value;
+	constexpr int WALK = kWalkWide;
+	__shared__ unsigned allKeys[kTraceWarps][CHUNK];
+	__shared__ float rayOD[6][kTraceThreads];
+	__shared__ unsigned stats[kTraceWarps][4]; // rays walked, answered without a walk (cached included), cached, unused
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	unsigned *keys = allKeys[warp];
+	const unsigned full = 0xffffffffu;
+	if (lane < 4) {
+		stats[warp][lane] = 0;
+	}
+	__syncwarp();
+	for (;;) {
+		unsigned base = 0;
+		if (lane == 0) {
+			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)CHUNK), 0xffffffffull);
+		}
+		base = __shfl_sync(full, base, 0);
+		if (base >= tp.nItems) {
+			break;
+		}
+		unsigned valid = 0;
+#pragma unroll 1
+		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
+			unsigned local = r * 32u + lane;
+			unsigned answered = 0, cached = 0;
+			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached);
+			keys[local] = key;
+			const unsigned nValid = __popc(__ballot_sync(full, key != kInvalidKey));
+			const unsigned nAnswered = __popc(__ballot_sync(full, answered + cached != 0u)), nCached = __popc(__ballot_sync(full, cached != 0u));
+			valid += nValid;
+			if (lane == 0) {
+				stats[warp][0] += nValid;
+				stats[warp][1] += nAnswered;
+				stats[warp][2] += nCached;
+			}
+		}
+		__syncwarp();
+		if (valid == 0) {
+			continue;
+		}
+		constexpr bool kSorted = MODE != kTraceSegments && RESTIR_TRACE_SORT;
+		if (kSorted) {
+			warp_sort<CHUNK>(keys, lane); // holes (kInvalidKey) end up behind the `valid` rays
+		}
+#pragma unroll 1
+		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
+			const unsigned key = keys[r * 32u + lane];
+			if (__ballot_sync(full, key != kInvalidKey) == 0u) {
+				if (kSorted) break; // sorted: only holes follow
+				continue;
+			}
+			int rec = -1;       // >= 0: the record of the occluding triangle
+			bool unsafe = false; // the wide walk does not take this ray
+			if (key != kInvalidKey) {
+				f3 p1, p2, o, d;
+				size_t opix;
+				item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
+				segment_setup(p1, p2, o, d);
+				float *od = &rayOD[0][threadIdx.x];
+				od[0] = o.x; od[kTraceThreads] = o.y; od[2 * kTraceThreads] = o.z;
+				od[3 * kTraceThreads] = d.x; od[4 * kTraceThreads] = d.y; od[5 * kTraceThreads] = d.z;
+				WideLaneRay wr;
+				if (wide_lane_setup(tp.grid, o, d, wr)) {
+					rec = trace_any_wide(tp.wide, tp.triEdges, wr, od, kTraceThreads);
+				} else {
+					unsafe = true;
+				}
+			}
+			if (__any_sync(full, unsafe)) { // rare: non-finite or out-of-range origin / direction
+				if (unsafe) {
+					const float *od = &rayOD[0][threadIdx.x];
+					const f3 o = mk3(od[0], od[kTraceThreads], od[2 * kTraceThreads]), d = mk3(od[3 * kTraceThreads], od[4 * kTraceThreads], od[5 * kTraceThreads]);
+					rec = trace_any_image_call(tp.image, tp.triEdges, o, d) ? -1 : -2;
+				}
+			}
+			if (key != kInvalidKey) {
+				f3 p1, p2;
+				size_t opix;
+				const size_t out = item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
+				tp.shadowed[out] = rec != -1 ? 1 : 0;
+				if (MODE != kTraceSegments && rec >= 0 && tp.occluders != nullptr) { // the witness for the next ray of this region at this light
+					const unsigned light = key >> 8;
+					tp.occluders[occluder_entry(tp, opix, light)] = (((light >> 8) & 255u) << 24) | (unsigned)rec;
+				}
+			}
+		}
+		__syncwarp();
+	}
+	__syncwarp();
+	if (lane == 0) { // one atomic per warp and counter
+		const unsigned rays = stats[warp][0], answered = stats[warp][1], cached = stats[warp][2];
+		if (rays + answered) atomicAdd(tp.counters + kCounterRays, (unsigned long long)(rays + answered));
+		if (rays) atomicAdd(tp.counters + kCounterTraced, (unsigned long long)rays);
+		if (cached) atomicAdd(tp.counters + kCounterCached, (unsigned long long)cached);
 	}
 }
 
 // ---- launcher ----------------------------------------------------------------------------------------------
 
+template <int MODE, int WALK> struct KernelOf {
+	static constexpr auto value = trace_kernel<MODE, WALK>;
+};
+template <int MODE> struct KernelOf<MODE, kWalkWide> {
+	static constexpr auto value = trace_wide_kernel<MODE>;
+};
+
 template <int MODE, int WALK> static cudaError_t launch_mode(const TraceParams &tp, int smCount, cudaStream_t s) {
 	static int blocksPerSm = 0; // same for every device of one box
 	if (blocksPerSm == 0) {
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, trace_kernel<MODE, WALK>, kTraceThreads, 0);
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, KernelOf<MODE, WALK>::value, kTraceThreads, 0);
 		if (e != cudaSuccess) {
 			return e;
 		}
@@ -430,7 +574,7 @@ template <int MODE, int WALK> static cudaError_t launch_mode(const TraceParams &
 		return ez;
 	}
 #endif
-	trace_kernel<MODE, WALK><<<grid, kTraceThreads, 0, s>>>(launch);
+	KernelOf<MODE, WALK>::value<<<grid, kTraceThreads, 0, s>>>(launch);
 	return cudaGetLastError();
 }
 
@@ -460,13 +604,13 @@ cudaError_t preload_trace_kernels() {
 	cudaFuncAttributes a;
 	cudaError_t e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkImage>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkReference>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTracePixel, kWalkWide>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_wide_kernel<kTracePixel>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkImage>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkReference>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceUnbiased, kWalkWide>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_wide_kernel<kTraceUnbiased>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkImage>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkReference>);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkWide>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_wide_kernel<kTraceSegments>);
 	return e;
 }
 

@@ -53,28 +53,38 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // Per-ray constants of the conservative box test (wide_image.h wide_ray_setup, same operations), duplicated into both halves
 // of a register pair where a packed FFMA2 reads them.
 struct WideLaneRay {
-	f3 o, d;
 	float2 sx, sy, sz, cLoX, cLoY, cLoZ, cHiX, cHiY, cHiZ;
-	unsigned selNx, selNy, selNz; // the exit selector is the entry selector ^ 0x0220
+	unsigned selNx, selNy, selNz, selFx, selFy, selFz;
 };
+
+// The walk keeps its loop-invariant operands in registers.  Without this ptxas, held to 64 registers, prefers to RECOMPUTE them
+// from the origin and the direction on every node visit (K * inv, (h - o) * inv, the margins, the selectors: twenty-odd
+// instructions per visit, profiles/r2_j_summary.md); an empty asm makes the values opaque, so they are kept.
+__device__ __forceinline__ void keep(float &x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void keep(unsigned &x) { asm volatile("" : "+r"(x)); }
 
 __device__ __forceinline__ bool wide_lane_setup(const WideGrid &g, f3 o, f3 d, WideLaneRay &r) {
 	const float of[3] = {o.x, o.y, o.z}, df[3] = {d.x, d.y, d.z};
 	const float iv[3] = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
 	WideRay w;
 	bool ok = wide_ray_setup(g, of, df, iv, w);
-	r.o = o;
-	r.d = d;
+	for (int a = 0; a < 3; ++a) {
+		keep(w.s[a]);
+		keep(w.cLo[a]);
+		keep(w.cHi[a]);
+		keep(w.selNear[a]);
+		keep(w.selFar[a]);
+	}
 	r.sx = make_float2(w.s[0], w.s[0]); r.sy = make_float2(w.s[1], w.s[1]); r.sz = make_float2(w.s[2], w.s[2]);
 	r.cLoX = make_float2(w.cLo[0], w.cLo[0]); r.cLoY = make_float2(w.cLo[1], w.cLo[1]); r.cLoZ = make_float2(w.cLo[2], w.cLo[2]);
 	r.cHiX = make_float2(w.cHi[0], w.cHi[0]); r.cHiY = make_float2(w.cHi[1], w.cHi[1]); r.cHiZ = make_float2(w.cHi[2], w.cHi[2]);
 	r.selNx = w.selNear[0]; r.selNy = w.selNear[1]; r.selNz = w.selNear[2];
+	r.selFx = w.selFar[0]; r.selFy = w.selFar[1]; r.selFz = w.selFar[2];
 	return ok;
 }
 
 // entry / exit parameters of two children at once on one axis
-__device__ __forceinline__ void wide_axis_pair(unsigned w0, unsigned w1, unsigned selN, float2 s, float2 cLo, float2 cHi, float2 &tn, float2 &tf) {
-	const unsigned selF = selN ^ 0x0220u;
+__device__ __forceinline__ void wide_axis_pair(unsigned w0, unsigned w1, unsigned selN, unsigned selF, float2 s, float2 cLo, float2 cHi, float2 &tn, float2 &tf) {
 	float2 vn = make_float2(__uint_as_float(__byte_perm(w0, 0x3F000000u, selN)), __uint_as_float(__byte_perm(w1, 0x3F000000u, selN)));
 	float2 vf = make_float2(__uint_as_float(__byte_perm(w0, 0x3F000000u, selF)), __uint_as_float(__byte_perm(w1, 0x3F000000u, selF)));
 #ifdef WIDE_NO_FFMA2
@@ -88,30 +98,42 @@ __device__ __forceinline__ void wide_axis_pair(unsigned w0, unsigned w1, unsigne
 
 // (*) of wide_image.h at a leaf: the reference's triangle test, then the reference's slab test on the leaf's own fp32 box
 // (kept in the spare floats of the 64-byte triangle record: e2.z, min.xyz | max.xyz, -)
-__device__ __forceinline__ bool wide_leaf_hit(const float4 *__restrict__ triRec, unsigned id, const WideLaneRay &r) {
-	if (!ray_triangle_edges(triRec, (int)id, r.o, r.d)) {
+__device__ __forceinline__ bool wide_leaf_hit(const float4 *__restrict__ triRec, unsigned id, f3 o, f3 d) {
+	if (!ray_triangle_edges(triRec, (int)id, o, d)) {
 		return false;
 	}
 	const float4 *t = triRec + (size_t)id * 4;
 	float4 a = __ldg(t + 2), b = __ldg(t + 3);
-	f3 inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-	return ray_box_reference(r.o, inv, make_float4(a.y, a.z, a.w, 0.0f), make_float4(b.x, b.y, b.z, 0.0f));
+	keep(d.x), keep(d.y), keep(d.z); // the three divisions belong to the (rare) hit, not in front of the loop over the leaves where the compiler hoists them
+	f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	return ray_box_reference(o, inv, make_float4(a.y, a.z, a.w, 0.0f), make_float4(b.x, b.y, b.z, 0.0f));
 }
 
-// Returns true when nothing is hit.  The caller has checked wide_lane_setup.
+// (*) of wide_image.h holds for this ray whatever finds the leaf: origin and direction finite, 1 / direction finite (|d| in
+// [2^-39, 2^39] puts |1 / d| inside wide_ray_setup's [2^-40, 2^40] without a division), origin within the grid's range.
+__device__ __forceinline__ bool wide_ray_in_range(const WideGrid &g, f3 o, f3 d) {
+	const float lo = 1.8189894035458565e-12f, hi = 549755813888.0f;
+	return fabsf(d.x) >= lo && fabsf(d.x) <= hi && fabsf(d.y) >= lo && fabsf(d.y) <= hi && fabsf(d.z) >= lo && fabsf(d.z) <= hi &&
+	       fabsf(o.x) <= g.maxOrigin[0] && fabsf(o.y) <= g.maxOrigin[1] && fabsf(o.z) <= g.maxOrigin[2];
+}
+
+// Returns the record of the triangle that occludes the segment, -1 when nothing is hit.  The caller has checked wide_lane_setup.
 //
 // The walk's unit is a GROUP: (first child node << 4) | 4-bit mask of the children still to visit.  The inner children a visit
 // finds hit become the current group in one step — no index word per child (wide_image.h: children of a node are numbered
 // consecutively), no push per child — and the group left over from the level above goes on the stack as ONE entry, so the
 // stack holds one entry per level of the wide tree (<= kWideStack, checked at upload).
-__device__ __forceinline__ bool trace_any_wide(const uint4 *__restrict__ wide, const float4 *__restrict__ triRec, const WideLaneRay &r) {
+// od: this thread's segment origin and direction in shared memory (od[c * stride], c = 0..5), read back only where a leaf is
+// tested (1.7 times per ray): six registers less across the walk.
+__device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, const float4 *__restrict__ triRec, const WideLaneRay &r, const float *od,
+                                              int stride) {
 	unsigned stack[kWideStack];
 	int top = 0;
 	unsigned group = 1u; // node 0, one child to visit: the root
 	for (;;) {
 		if ((group & 15u) == 0u) {
 			if (top == 0) {
-				return true;
+				return -1;
 			}
 			group = stack[--top];
 		}
@@ -122,30 +144,42 @@ __device__ __forceinline__ bool trace_any_wide(const uint4 *__restrict__ wide, c
 		float2 nx, fx, ny, fy, nz, fz;
 		unsigned hits;
 		// slots 0 and 1
-		wide_axis_pair(a.v[0], a.v[1], r.selNx, r.sx, r.cLoX, r.cHiX, nx, fx);
-		wide_axis_pair(a.v[4], a.v[5], r.selNy, r.sy, r.cLoY, r.cHiY, ny, fy);
-		wide_axis_pair(b.v[0], b.v[1], r.selNz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
+		wide_axis_pair(a.v[0], a.v[1], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+		wide_axis_pair(a.v[4], a.v[5], r.selNy, r.selFy, r.sy, r.cLoY, r.cHiY, ny, fy);
+		wide_axis_pair(b.v[0], b.v[1], r.selNz, r.selFz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
+		// a slot is hit when max(entry, 0) <= min(exit, 1): the sign bit of the difference says "missed" (an exact 0 is +0: hit)
+		float2 gap01;
 		{
-			float n0 = fmax3(nx.x, ny.x, nz.x), f0 = fmin3(fx.x, fy.x, fz.x), n1 = fmax3(nx.y, ny.y, nz.y), f1 = fmin3(fx.y, fy.y, fz.y);
-			hits = (n0 <= f0 && n0 <= 1.0f && f0 >= 0.0f ? 1u : 0u) | (n1 <= f1 && n1 <= 1.0f && f1 >= 0.0f ? 2u : 0u);
+			float n0 = fmaxf(fmax3(nx.x, ny.x, nz.x), 0.0f), f0 = fminf(fmin3(fx.x, fy.x, fz.x), 1.0f);
+			float n1 = fmaxf(fmax3(nx.y, ny.y, nz.y), 0.0f), f1 = fminf(fmin3(fx.y, fy.y, fz.y), 1.0f);
+			gap01 = __fadd2_rn(make_float2(f0, f1), make_float2(-n0, -n1));
 		}
 		// slots 2 and 3
-		wide_axis_pair(a.v[2], a.v[3], r.selNx, r.sx, r.cLoX, r.cHiX, nx, fx);
-		wide_axis_pair(a.v[6], a.v[7], r.selNy, r.sy, r.cLoY, r.cHiY, ny, fy);
-		wide_axis_pair(b.v[2], b.v[3], r.selNz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
+		wide_axis_pair(a.v[2], a.v[3], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+		wide_axis_pair(a.v[6], a.v[7], r.selNy, r.selFy, r.sy, r.cLoY, r.cHiY, ny, fy);
+		wide_axis_pair(b.v[2], b.v[3], r.selNz, r.selFz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
 		{
-			float n0 = fmax3(nx.x, ny.x, nz.x), f0 = fmin3(fx.x, fy.x, fz.x), n1 = fmax3(nx.y, ny.y, nz.y), f1 = fmin3(fx.y, fy.y, fz.y);
-			hits |= (n0 <= f0 && n0 <= 1.0f && f0 >= 0.0f ? 4u : 0u) | (n1 <= f1 && n1 <= 1.0f && f1 >= 0.0f ? 8u : 0u);
+			float n0 = fmaxf(fmax3(nx.x, ny.x, nz.x), 0.0f), f0 = fminf(fmin3(fx.x, fy.x, fz.x), 1.0f);
+			float n1 = fmaxf(fmax3(nx.y, ny.y, nz.y), 0.0f), f1 = fminf(fmin3(fx.y, fy.y, fz.y), 1.0f);
+			const float2 gap23 = __fadd2_rn(make_float2(f0, f1), make_float2(-n0, -n1));
+			// the four sign bits, slot 0 in bit 0: each funnel shift appends one
+			unsigned missed = __float_as_uint(gap23.y) >> 31;
+			missed = __funnelshift_l(__float_as_uint(gap23.x), missed, 1);
+			missed = __funnelshift_l(__float_as_uint(gap01.y), missed, 1);
+			missed = __funnelshift_l(__float_as_uint(gap01.x), missed, 1);
+			hits = ~missed & 15u;
 		}
 		// hit leaves: slots [inner, count), records triBase + (slot - inner); empty slots are never hit (inverted boxes)
 		unsigned leaf = hits >> b.v[6];
 		if (leaf != 0u) {
+			const f3 o = mk3(od[0], od[stride], od[2 * stride]), d = mk3(od[3 * stride], od[4 * stride], od[5 * stride]);
+			const unsigned triBase = b.v[5];
 #pragma unroll 1
 			do {
 				const unsigned j = (unsigned)__ffs((int)leaf) - 1u;
 				leaf &= leaf - 1u;
-				if (wide_leaf_hit(triRec, b.v[5] + j, r)) {
-					return false;
+				if (wide_leaf_hit(triRec, triBase + j, o, d)) {
+					return (int)(triBase + j);
 				}
 			} while (leaf != 0u);
 		}

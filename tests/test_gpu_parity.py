@@ -257,6 +257,7 @@ def test_ray_elision_is_exact(name):
     for enable in (1, 0):
         ctx = ph.make_context(scene)
         ctx.set_ray_elision(enable)
+        ctx.set_occluder_cache(enable)                            # the other way of answering a ray without a walk (below)
         got = ph.run_cuda(case, ctx)
         ctx.close()
         ph.assert_frames_match(got, want, f"{name} elision={enable}")
@@ -264,9 +265,37 @@ def test_ray_elision_is_exact(name):
         asked = sum(f["counters"]["shadow_rays"] for f in got)
         assert walked[enable] <= asked
         if not enable:
-            assert walked[enable] == asked
+            assert walked[enable] == asked and sum(f["counters"]["shadow_rays_cached"] for f in got) == 0
     print(f"{name}: {walked[0]} rays asked for, {walked[1]} walked with the exact shortcuts on")
     assert walked[1] < walked[0]
+
+
+@pytest.mark.parametrize("name", ["procedural:point", "procedural:tri", "sponza", "office"])
+def test_occluder_cache_is_exact(name):
+    """The trace kernel tests the last triangle that occluded a ray of the same screen region at the same light before it queues
+    a ray for a walk (restir_trace.cu).  The table only proposes witnesses: with it on, off, and on with entries left behind by a
+    DIFFERENT view of the scene (stale witnesses), every reservoir and the testVisibility count are the oracle's."""
+    _torch()
+    scene = _scene(name)
+    w, h = 224, 126
+    case = ph.Case(scene, w, h, _cams(name, 3, w, h), unbiased=True, unbiased_neighbors=5)
+    want = ph.run_oracle(case)
+    ctx = ph.make_context(scene)
+    got = ph.run_cuda(case, ctx)
+    ph.assert_frames_match(got, want, f"{name} cache on")
+    cached = sum(f["counters"]["shadow_rays_cached"] for f in got)
+    walked_on = sum(f["counters"]["shadow_rays_traced"] for f in got)
+    # the same context again: the table now holds the witnesses of the last frame of the first run (another camera position)
+    got = ph.run_cuda(case, ctx)
+    ph.assert_frames_match(got, want, f"{name} cache on, stale entries")
+    ctx.set_occluder_cache(0)
+    got = ph.run_cuda(case, ctx)
+    ph.assert_frames_match(got, want, f"{name} cache off")
+    assert sum(f["counters"]["shadow_rays_cached"] for f in got) == 0
+    walked_off = sum(f["counters"]["shadow_rays_traced"] for f in got)
+    ctx.close()
+    print(f"{name}: {walked_off} walks without the cache, {walked_on} with it ({cached} rays answered by a cached witness)")
+    assert cached > 0 and walked_on + cached == walked_off
 
 
 # ---- boundary behaviour ---------------------------------------------------------------------------------
