@@ -377,6 +377,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
         c.set_spatial_staging(args.spatial_staging == "on")
         c.set_occluder_cache(args.occluder_cache == "on")
+        c.set_ray_elision({"on": 1, "off": 0, "dedupe": 2}[args.ray_elision])
         if variant != (1, False, False):
             c.set_reservoir_variant(*variant)
         return c
@@ -905,6 +906,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--traversal", default="auto", choices=["auto", "image", "reference-order"],
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
+    ap.add_argument("--ray-elision", default="on", choices=["on", "off", "dedupe"],
+                    help="unbiased pass: answer neighbour rays without a walk where that is exact (restir_set_ray_elision; A/B)")
     ap.add_argument("--occluder-cache", default="on", choices=["on", "off"],
                     help="trace kernel: test the cached occluder of (screen region, light) before queueing a ray for a walk (exact; A/B)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

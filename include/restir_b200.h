@@ -234,8 +234,13 @@ int restir_check_wide_walk(const void *nodes, uint32_t n_nodes, const void *tria
                            uint64_t n, unsigned char *shadowed, unsigned char *walked_wide, uint64_t *visits, char *message, size_t message_bytes);
 /* No reference equivalent (the reference traces every ray it asks for).  The unbiased pass answers a neighbour ray
  * of unbiasedReuse.glsl:139-156 without walking the tree when the answer is already determined, exactly: the pixel's
- * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every
- * ray instead (A/B measurements and the tests that require both settings to give identical bits).  Default: 1. */
+ * own ray (:157-166) is shadowed, or the segment is bit-identical to the neighbour's own ray.  enable = 0 walks every ray
+ * instead (A/B measurements and the tests that require both settings to give identical bits).  Default: 1.
+ * enable = 2 (experiment, WIDE traversal only) adds one walk per DISTINCT segment: pixels of a region share samples and
+ * neighbours, so many neighbour rays ask for the same (neighbour position, sample position) pair, bit for bit — the first item
+ * to enter it into a hash table walks it, the others copy the answer afterwards.  Exact, and measured to lose: on Sponza 1080p
+ * with 200 lights it saves 22 % of the neighbour walks and still costs 0.11 ms per frame more than it saves (one atomic into a
+ * 64 MB table per ray); with 1 M lights 4 % of the rays are duplicates (profiles/r2_j_summary.md). */
 int restir_set_ray_elision(restir_context *ctx, int enable);
 /* No reference equivalent.  The biased spatial pass tests every neighbour's depth and normal before it merges the neighbour's
  * reservoir (spatialReuse.comp:62-70).  enable != 0: the CTA stages the depth and normal texels of its 32x8 tile and the

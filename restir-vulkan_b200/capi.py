@@ -446,7 +446,8 @@ class RestirContext:
         self._check(self.lib.restir_set_unbiased_neighbors(self._ctx, C.c_uint32(n)))
 
     def set_ray_elision(self, enable):
-        self._check(self.lib.restir_set_ray_elision(self._ctx, C.c_int(1 if enable else 0)))
+        """0: every ray walked; 1 (default): the exact shortcuts of restir_trace.cu item_resolve; 2: plus one walk per distinct neighbour segment (experiment)."""
+        self._check(self.lib.restir_set_ray_elision(self._ctx, C.c_int(int(enable))))
 
     def set_spatial_staging(self, enable):
         self._check(self.lib.restir_set_spatial_staging(self._ctx, C.c_int(1 if enable else 0)))

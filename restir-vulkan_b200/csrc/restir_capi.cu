@@ -106,6 +106,11 @@ struct restir_context {
 	int rayElision = 1; // restir_set_ray_elision
 	bool spatialStaging = false; // restir_set_spatial_staging
 	unsigned long long *counters = nullptr; // device, kCounterCount entries
+	unsigned *dedupe = nullptr;             // device, segment table of the neighbour rays (restir_trace.cu segment_claim), dedupeEntries words
+	size_t dedupeEntries = 0;
+	uint2 *aliases = nullptr;               // device, aliasCapacity pairs
+	size_t aliasCapacity = 0;
+	unsigned *aliasCounter = nullptr;       // device counter
 	unsigned *occluders = nullptr;          // device, occluder cache of the trace kernel (restir_trace.cu): [region][256] entries
 	size_t occluderEntries = 0;
 	unsigned regionsX = 0;
@@ -303,6 +308,25 @@ int ensureHandOver(restir_context *ctx, const PassGrid &g, unsigned raysPerPixel
 		ctx->neighborPixCount = 0;
 		CU(ctx, cudaMalloc(&ctx->neighborPix, count * sizeof(int)));
 		ctx->neighborPixCount = count;
+	}
+	if (neighbors != 0 && ctx->rayElision == 2) { // experiment: one walk per distinct neighbour segment: table of 2^n >= items words, room for items / 2 aliases
+		size_t entries = 1024;
+		while (entries < count && entries < ((size_t)1 << 28)) {
+			entries <<= 1;
+		}
+		if (ctx->dedupeEntries < entries || ctx->aliasCapacity < count / 2) {
+			CU(ctx, cudaStreamSynchronize(ctx->stream));
+			freeDev(ctx->dedupe);
+			freeDev(ctx->aliases);
+			ctx->dedupeEntries = ctx->aliasCapacity = 0;
+			CU(ctx, cudaMalloc(&ctx->dedupe, entries * sizeof(unsigned)));
+			CU(ctx, cudaMalloc(&ctx->aliases, (count / 2 + 1) * sizeof(uint2)));
+			ctx->dedupeEntries = entries;
+			ctx->aliasCapacity = count / 2;
+		}
+		if (ctx->aliasCounter == nullptr) {
+			CU(ctx, cudaMalloc(&ctx->aliasCounter, sizeof(unsigned)));
+		}
 	}
 	size_t countM = neighbors ? (size_t)g.pixelIds * (neighbors + 1) : 0;
 	if (ctx->neighborMCount < countM) {
@@ -558,6 +582,9 @@ void restir_destroy(restir_context *ctx) {
 	freeDev(ctx->counters);
 	freeDev(ctx->traceCursors);
 	freeDev(ctx->occluders);
+	freeDev(ctx->dedupe);
+	freeDev(ctx->aliases);
+	freeDev(ctx->aliasCounter);
 	for (auto &r : ctx->reservoirs) {
 		freeDev(r);
 	}
@@ -1360,7 +1387,7 @@ int restir_set_spatial_staging(restir_context *ctx, int enable) {
 
 int restir_set_ray_elision(restir_context *ctx, int enable) {
 	ENTER(ctx);
-	ctx->rayElision = enable ? 1 : 0;
+	ctx->rayElision = enable == 2 ? 2 : enable ? 1 : 0;
 	return RESTIR_OK;
 }
 
@@ -1621,7 +1648,14 @@ int passUnbiased(restir_context *ctx, int gbuffer, int in_buffer, int out_buffer
 		CU(ctx, launch_trace(tp, kTracePixel, ctx->smCount, ctx->stream));
 		if ((rc = afterLaunch(ctx, "trace_kernel<own>")) != RESTIR_OK) return rc;
 		tp.slots = k;
-		tp.elide = ctx->rayElision;
+		tp.elide = ctx->rayElision != 0;
+		if (ctx->rayElision == 2 && ctx->dedupe != nullptr) { // experiment: one walk per distinct segment (restir_trace.cu segment_claim)
+			tp.dedupe = ctx->dedupe;
+			tp.dedupeMask = (unsigned)(ctx->dedupeEntries - 1);
+			tp.aliases = ctx->aliases;
+			tp.aliasCapacity = (unsigned)std::min<size_t>(ctx->aliasCapacity, 0xffffffffu);
+			tp.aliasCount = ctx->aliasCounter;
+		}
 		tp.nItems = g.pixelIds * k;
 		tp.neighborPix = ctx->neighborPix;
 		beforeLaunch(ctx, "trace_kernel<neighbours>");

@@ -24,6 +24,11 @@ struct TraceParams {
 	const float4 *triEdges;             // with image: 64-byte (p1, e1, e2) records derived from tris at upload (restir_trace.cuh)
 	const uint4 *wide;                  // 4-wide quantised image of the same tree (wide_image.h, restir_wide.cuh); null: the binary image is walked
 	WideGrid grid;
+	unsigned *dedupe;                   // kTraceUnbiased: open-addressing table (segment -> first item that asked for it), restir_trace.cu; null: off
+	unsigned dedupeMask;                // entries - 1 (a power of two)
+	uint2 *aliases;                     // (visibility byte of a duplicate, visibility byte of the item that walks the segment)
+	unsigned aliasCapacity;
+	unsigned *aliasCount;               // device counter of `aliases`
 	unsigned *occluders;                // occluder cache (restir_trace.cu): [screen region][256] -> tag << 24 | triangle record; null: off
 	unsigned regionsX;                  // regions (64 x 32 pixels) per region row
 	unsigned nTris;

