@@ -19,6 +19,19 @@ enum TraceMode {
 	kTraceUnbiased = 1, // `slots` neighbour rays per pixel: neighbour position -> the pixel's sample (unbiasedReuse.glsl:139-156)
 	kTraceSegments = 2, // explicit segments (restir_trace_segments)
 };
+// n / d for any n < 2^32 as the high half of one 64-bit product: M = ceil(2^64 / d) (host, fast_div_make); d = 1 is M = 0.
+// Exact: n M / 2^64 = n / d + n e / (d 2^64) with e = M d - 2^64 < d, and the excess stays below 2^-32 < 1 / d.
+struct FastDiv {
+	unsigned long long M;
+	unsigned d;
+};
+inline FastDiv fast_div_make(unsigned d) {
+	FastDiv f;
+	f.d = d;
+	f.M = d <= 1 ? 0ull : ~0ull / d + 1ull; // floor((2^64 - 1) / d) + 1 = ceil(2^64 / d) when d is not a power of two, and 2^64 / d when it is
+	return f;
+}
+
 struct TraceParams {
 	const float4 *nodes, *tris, *image; // image == null: literal walk of the 80-byte nodes (restir_trace.cuh)
 	const float4 *triEdges;             // with image: 64-byte (p1, e1, e2) records derived from tris at upload (restir_trace.cuh)
@@ -33,6 +46,7 @@ struct TraceParams {
 	unsigned regionsX;                  // regions (64 x 32 pixels) per region row
 	unsigned nTris;
 	unsigned nNodes;
+	FastDiv divW, divTilesX, divSlots;  // set by launch_trace
 	Band band;
 	unsigned tilesX;                   // 8x4 tiles per tile row of the pass grid (item numbering, see tile_pixel_id)
 	unsigned slots;

@@ -60,13 +60,15 @@ constexpr unsigned kInvalidKey = 0xffffffffu;
 // quantised image (restir_wide.cuh) with the binary image for the rays outside its range.
 enum TraceWalk { kWalkReference = 0, kWalkImage = 1, kWalkWide = 2 };
 
+__device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv &f) { return f.M == 0ull ? n : (unsigned)__umul64hi((unsigned long long)n, f.M); }
+
 // ---- item -> pixel, key, segment ---------------------------------------------------------------------------
 
 __device__ __forceinline__ bool item_pixel(const TraceParams &tp, unsigned p, size_t &pix) {
 	// p is a tile-ordered pixel id: (tile, lane) with 8x4 tiles, tilesX tiles per tile row (restir_kernels.cu
 	// tile_pixel_id produces the same numbering)
 	unsigned tile = p >> 5, l = p & 31u;
-	unsigned ty = tile / tp.tilesX, tx = tile - ty * tp.tilesX;
+	unsigned ty = fast_div(tile, tp.divTilesX), tx = tile - ty * tp.tilesX;
 	int x = (int)(tx * 8u + (l & 7u));
 	int y = tp.band.rowBegin + (int)(ty * 4u + (l >> 3));
 	if (x >= tp.band.W || y >= tp.band.rowEnd) {
@@ -79,7 +81,7 @@ __device__ __forceinline__ bool item_pixel(const TraceParams &tp, unsigned p, si
 // Tile-ordered pixel id of local pixel index n (the inverse of item_pixel); false outside the band's own rows.
 __device__ __forceinline__ bool pixel_id_of_local(const TraceParams &tp, unsigned n, unsigned &id) {
 	unsigned W = (unsigned)tp.band.W;
-	unsigned yl = n / W, x = n - yl * W;
+	unsigned yl = fast_div(n, tp.divW), x = n - yl * W;
 	int y = (int)yl + tp.band.allocBegin;
 	if (y < tp.band.rowBegin || y >= tp.band.rowEnd) {
 		return false;
@@ -116,7 +118,7 @@ template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParam
 		out = (size_t)item * tp.outStride + tp.outOffset;
 		return kItemRay;
 	}
-	unsigned p = item / tp.slots, slot = item - p * tp.slots;
+	unsigned p = fast_div(item, tp.divSlots), slot = item - p * tp.slots;
 	if (!item_pixel(tp, p, pix)) {
 		return kItemNone;
 	}
@@ -160,7 +162,7 @@ template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParam
 constexpr unsigned kOccluderSlots = 256;
 __device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t opix, unsigned light) {
 	const unsigned W = (unsigned)tp.band.W, n = (unsigned)opix;
-	const unsigned yl = n / W, x = n - yl * W;
+	const unsigned yl = fast_div(n, tp.divW), x = n - yl * W;
 	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (light & (kOccluderSlots - 1u));
 }
 
@@ -194,7 +196,7 @@ __device__ __forceinline__ bool segment_claim(const TraceParams &tp, unsigned it
 		if (e == 0xffffffffu) {
 			settled = true; // first: this item walks the segment
 		} else {
-			const unsigned pe = e / tp.slots;
+			const unsigned pe = fast_div(e, tp.divSlots);
 			size_t pixe = 0;
 			const bool inside = item_pixel(tp, pe, pixe);
 			const float4 te = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pixe));
@@ -263,7 +265,7 @@ template <int MODE> __device__ __forceinline__ size_t item_segment(const TracePa
 	if (MODE == kTracePixel) {
 		item_resolve<MODE>(tp, item, pix, opix, out, false);
 	} else {
-		unsigned p = item / tp.slots, slot = item - p * tp.slots;
+		unsigned p = fast_div(item, tp.divSlots), slot = item - p * tp.slots;
 		item_pixel(tp, p, pix);
 		opix = (size_t)tp.neighborPix[(size_t)p * tp.slots + slot];
 		out = (size_t)p * (tp.slots + 1) + slot;
@@ -283,6 +285,27 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 		for (unsigned j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
 			for (unsigned t = lane; t < (unsigned)CHUNK / 2; t += 32) {
+				unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+				unsigned a = keys[i], b = keys[i + j];
+				bool ascending = (i & k) == 0u;
+				if ((a > b) == ascending) {
+					keys[i] = b;
+					keys[i + j] = a;
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// the same network over the first n keys (n a power of two <= CHUNK, warp-uniform)
+__device__ __forceinline__ void warp_sort_n(unsigned *keys, unsigned n, unsigned lane) {
+#pragma unroll 1
+	for (unsigned k = 2; k <= n; k <<= 1) {
+#pragma unroll 1
+		for (unsigned j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+			for (unsigned t = lane; t < n / 2; t += 32) {
 				unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
 				unsigned a = keys[i], b = keys[i + j];
 				bool ascending = (i & k) == 0u;
@@ -532,15 +555,20 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 					}
 					first = __shfl_sync(full, first, 0) + (unsigned)__popc(isAlias & ((1u << lane) - 1u));
 					if (aliasOf != 0xffffffffu && first < tp.aliasCapacity) {
-						const unsigned item = base + local, p = item / tp.slots, pe = aliasOf / tp.slots;
+						const unsigned item = base + local, p = fast_div(item, tp.divSlots), pe = fast_div(aliasOf, tp.divSlots);
 						tp.aliases[first] = make_uint2(p * (tp.slots + 1u) + (item - p * tp.slots), pe * (tp.slots + 1u) + (aliasOf - pe * tp.slots));
 						key = kInvalidKey;
 						answered = 1;
 					}
 				}
 			}
-			keys[local] = key;
-			const unsigned nValid = __popc(__ballot_sync(full, key != kInvalidKey));
+			// the rays of the chunk are packed at the front of the key array: what is sorted is the rays, not the chunk (half of a
+			// neighbour chunk and three quarters of a restirOmni chunk are answered without a walk)
+			const unsigned isValid = __ballot_sync(full, key != kInvalidKey);
+			if (key != kInvalidKey) {
+				keys[valid + (unsigned)__popc(isValid & ((1u << lane) - 1u))] = key;
+			}
+			const unsigned nValid = __popc(isValid);
 			const unsigned nAnswered = __popc(__ballot_sync(full, answered + cached != 0u)), nCached = __popc(__ballot_sync(full, cached != 0u));
 			valid += nValid;
 			if (lane == 0) {
@@ -554,16 +582,20 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 			continue;
 		}
 		constexpr bool kSorted = MODE != kTraceSegments && RESTIR_TRACE_SORT;
-		if (kSorted) {
-			warp_sort<CHUNK>(keys, lane); // holes (kInvalidKey) end up behind the `valid` rays
+		if (kSorted && valid > 1) {
+			unsigned n = 32;
+			while (n < valid) {
+				n <<= 1;
+			}
+			for (unsigned t = valid + lane; t < n; t += 32) {
+				keys[t] = kInvalidKey; // padding sorts behind every ray
+			}
+			__syncwarp();
+			warp_sort_n(keys, n, lane);
 		}
 #pragma unroll 1
-		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
-			const unsigned key = keys[r * 32u + lane];
-			if (__ballot_sync(full, key != kInvalidKey) == 0u) {
-				if (kSorted) break; // sorted: only holes follow
-				continue;
-			}
+		for (unsigned r = 0; r * 32u < valid; ++r) {
+			const unsigned key = r * 32u + lane < valid ? keys[r * 32u + lane] : kInvalidKey;
 			int rec = -1;       // >= 0: the record of the occluding triangle
 			bool unsafe = false; // the wide walk does not take this ray
 			if (key != kInvalidKey) {
@@ -676,7 +708,11 @@ cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStrea
 			return e;
 		}
 	}
-	e = launch_walk(tp, mode, smCount, s);
+	TraceParams launch = tp;
+	launch.divW = fast_div_make((unsigned)std::max(tp.band.W, 1));
+	launch.divTilesX = fast_div_make(std::max(tp.tilesX, 1u));
+	launch.divSlots = fast_div_make(std::max(tp.slots, 1u));
+	e = launch_walk(launch, mode, smCount, s);
 	if (e == cudaSuccess && dedupe) {
 		alias_resolve_kernel<<<smCount * 4, 256, 0, s>>>(tp.aliases, tp.aliasCount, tp.aliasCapacity, tp.shadowed);
 		e = cudaGetLastError();
