@@ -201,7 +201,7 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
  * IMAGE: the binary image only.  WIDE: same as AUTO.  REFERENCE_ORDER: walk the 80-byte nodes literally, dropped pushes
  * counted — also what AUTO falls back to when the stack could overflow.  restir_get_bvh_info tells which one is in use.
  * Takes effect at the next restir_upload_bvh.  Uploads whose child indices are out of range or that are not trees are rejected
- * with RESTIR_E_INVALID.  A tree built by restir_build_bvh_device is walked through its binary image. */
+ * with RESTIR_E_INVALID.  restir_build_bvh_device derives both images on the device (csrc/restir_wide_build.cu). */
 #define RESTIR_TRAVERSAL_AUTO 0
 #define RESTIR_TRAVERSAL_REFERENCE_ORDER 1
 #define RESTIR_TRAVERSAL_IMAGE 2
@@ -224,6 +224,11 @@ typedef struct restir_bvh_info {
 	uint32_t wide_nodes, wide_depth, wide_stack_bound; /* the 4-wide image (0 when not in use) */
 } restir_bvh_info;
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
+/* Inspection (tests, tools): the 4-wide image the context walks — n_wide nodes of 64 bytes (csrc/wide_image.h WideNode: 12 words
+ * of quantised planes, first child, first triangle record, inner count, slot count) and, per triangle record, the index of the
+ * uploaded triangle it holds.  Either pointer may be NULL.  RESTIR_E_UNSUPPORTED when the tree is not walked wide.  The image of
+ * a tree built by restir_build_bvh_device equals, byte for byte, the image restir_upload_bvh derives from the same nodes. */
+int restir_get_wide_image(restir_context *ctx, void *wide_nodes, uint32_t capacity, uint32_t *n_wide, uint32_t *tri_order);
 /* Host-only self-check of the WIDE traversal (no reference equivalent, no GPU, called by no pass): builds the wide image of
  * the tree exactly as restir_upload_bvh does and walks it on the CPU with the operations the kernel uses (the box arithmetic is
  * one header shared by host and device, csrc/wide_image.h) for n segments p1 -> p2 (3 floats each).  shadowed[i] = 1 when the

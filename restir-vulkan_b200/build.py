@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_trace.cu", "csrc/restir_halo.cu", "csrc/restir_gbuffer.cu", "csrc/restir_bvh_build.cu", "csrc/restir_generic.cu", "csrc/restir_capi.cu", "csrc/traversal_image.cpp", "csrc/wide_image.cpp", "host/scene_build.cpp"]
+SOURCES = ["csrc/restir_kernels.cu", "csrc/restir_trace.cu", "csrc/restir_halo.cu", "csrc/restir_gbuffer.cu", "csrc/restir_bvh_build.cu", "csrc/restir_wide_build.cu", "csrc/restir_generic.cu", "csrc/restir_capi.cu", "csrc/traversal_image.cpp", "csrc/wide_image.cpp", "host/scene_build.cpp"]
 DRIVER_SOURCES = ["host/restir_driver.cpp", "host/passes.hpp", "host/capture.hpp", "../include/restir_capture.h"]
 HEADERS = ["csrc/restir_math.cuh", "csrc/restir_pixel.cuh", "csrc/restir_device.cuh", "csrc/restir_kernels.h", "csrc/restir_trace.cuh", "csrc/restir_wide.cuh", "csrc/traversal_image.h", "csrc/wide_image.h", "../include/restir_b200.h",
            "../include/restir_layouts.h", "host/passes.hpp"]

@@ -64,7 +64,7 @@ EXPORTS = [
     "restir_upload_gbuffer", "restir_upload_geometry", "restir_upload_materials", "restir_pass_gbuffer",
     "restir_gbuffer_device_planes", "restir_import_external_memory", "restir_release_external_memory", "restir_set_uniforms", "restir_set_lighting_uniforms", "restir_set_unbiased_neighbors", "restir_set_reservoir_variant",
     "restir_get_reservoir_bytes",
-    "restir_set_traversal", "restir_set_occluder_cache", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_check_wide_walk", "restir_profile_begin", "restir_profile_end",
+    "restir_set_traversal", "restir_set_occluder_cache", "restir_set_ray_elision", "restir_set_spatial_staging", "restir_get_bvh_info", "restir_check_aabb_tree", "restir_check_wide_walk", "restir_get_wide_image", "restir_profile_begin", "restir_profile_end",
     "restir_pass_restir", "restir_pass_spatial", "restir_pass_unbiased", "restir_pass_lighting", "restir_frame", "restir_frame_lit",
     "restir_download_reservoirs", "restir_upload_reservoirs", "restir_reservoir_device_ptr", "restir_trace_segments",
     "restir_get_counters", "restir_build_aabb_tree", "restir_build_aabb_tree_mt", "restir_collect_triangle_lights",
@@ -451,6 +451,15 @@ class RestirContext:
 
     def set_spatial_staging(self, enable):
         self._check(self.lib.restir_set_spatial_staging(self._ctx, C.c_int(1 if enable else 0)))
+
+    def wide_image(self):
+        """(nodes (n, 16) uint32, tri_order (n_triangles,) uint32) of the 4-wide image the context walks."""
+        n = C.c_uint32(0)
+        info = self.bvh_info()
+        nodes = np.zeros((max(info["wide_nodes"], 1), 16), np.uint32)
+        order = np.zeros(info["triangles"], np.uint32)
+        self._check(self.lib.restir_get_wide_image(self._ctx, _hp(nodes), C.c_uint32(nodes.shape[0]), C.byref(n), _hp(order)))
+        return nodes[:n.value], order
 
     def set_occluder_cache(self, enable):
         self._check(self.lib.restir_set_occluder_cache(self._ctx, C.c_int(1 if enable else 0)))

@@ -31,6 +31,7 @@ struct restir_context {
 	float4 *nodes = nullptr, *tris = nullptr;
 	float4 *image = nullptr; // 64-byte image of `nodes` (traversal_image.h); null => literal 80-byte walk
 	float4 *triEdges = nullptr; // 64-byte (p1, e1, e2) records of `tris` (restir_trace.cuh)
+	const uint32_t *wideOrder = nullptr; // inside treeBlock: record r holds triangle wideOrder[r]
 	uint4 *wide = nullptr;      // 4-wide quantised image of the same tree (wide_image.h); null => the binary image is walked
 	WideGrid wideGrid{};
 	WideImageInfo wideInfo;
@@ -509,6 +510,7 @@ int restir_create(restir_context **out, int device, void *stream) {
 		if ((rc = cudaCheck(ctx, preload_halo_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_gbuffer_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_bvh_build_kernels(), "loading kernels")) != RESTIR_OK) break;
+		if ((rc = cudaCheck(ctx, preload_wide_build_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, preload_generic_kernels(), "loading kernels")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMalloc(&ctx->bandFlags, 6 * sizeof(unsigned long long)), "cudaMalloc band flags")) != RESTIR_OK) break;
 		if ((rc = cudaCheck(ctx, cudaMemsetAsync(ctx->bandFlags, 0, 6 * sizeof(unsigned long long), ctx->stream), "memset")) != RESTIR_OK) break;
@@ -658,6 +660,7 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 	freeDev(ctx->treeBlock);
 	ctx->image = ctx->triEdges = nullptr;
 	ctx->wide = nullptr;
+	ctx->wideOrder = nullptr;
 	ctx->wideInfo = WideImageInfo{};
 	ctx->nNodes = ctx->nTris = 0;
 	freeDev(ctx->gbAttrs); // per-triangle attributes belong to the previous triangle list
@@ -693,6 +696,7 @@ int restir_upload_bvh(restir_context *ctx, const void *nodes, uint32_t n_nodes, 
 			boxes = dstBoxes;
 			order = dstOrder;
 		}
+		ctx->wideOrder = order;
 		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, order, boxes, ctx->stream);
 		CU(ctx, cudaGetLastError());
 	}
@@ -719,8 +723,8 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	freeDev(ctx->treeBlock);
 	ctx->image = ctx->triEdges = nullptr;
 	ctx->wide = nullptr;
+	ctx->wideOrder = nullptr;
 	ctx->wideInfo = WideImageInfo{};
-	ctx->wideInfo.why = "tree built on the device: the binary image is walked (the wide image is derived on the host by restir_upload_bvh)";
 	ctx->nNodes = ctx->nTris = 0;
 	freeDev(ctx->gbAttrs);
 	freeDev(ctx->gbTriMaterial);
@@ -759,15 +763,74 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	info.depth = levels;
 	info.referenceStackBound = info.anyOrderStackBound = std::max(1, levels); // upper bounds (restir_check_aabb_tree computes the exact ones)
 	info.usable = levels <= 32 && ctx->traversal != RESTIR_TRAVERSAL_REFERENCE_ORDER;
+	WideGrid wideGrid{};
+	WideImageInfo wideInfo;
 	if (info.usable) {
+		// one allocation: the 64-byte binary nodes, the 64-byte triangle records, then (worst case: as many as binary nodes) the
+		// 64-byte 4-wide nodes, the leaf boxes and the record order on their way into the records
 		const size_t imageBytes = ((size_t)nNodes * 64 + 255) & ~(size_t)255;
 		const size_t edgeBytes = (size_t)n_triangles * 64;
-		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes));
-		ctx->treeBlockBytes = imageBytes + edgeBytes;
+		const bool wantWide = ctx->traversal != RESTIR_TRAVERSAL_IMAGE;
+		const size_t wideBytes = wantWide ? ((size_t)nNodes * sizeof(WideNode) + 255) & ~(size_t)255 : 0;
+		const size_t boxBytes = wantWide ? (((size_t)n_triangles * 6 * sizeof(float)) + 255) & ~(size_t)255 : 0;
+		const size_t orderBytes = wantWide ? (size_t)n_triangles * sizeof(unsigned) : 0;
+		CU(ctx, cudaMalloc(&ctx->treeBlock, imageBytes + edgeBytes + wideBytes + boxBytes + orderBytes));
+		ctx->treeBlockBytes = imageBytes + edgeBytes + wideBytes + boxBytes + orderBytes;
 		ctx->image = reinterpret_cast<float4 *>(ctx->treeBlock);
 		ctx->triEdges = reinterpret_cast<float4 *>(ctx->treeBlock + imageBytes);
 		launch_bvh_image(reinterpret_cast<const restir_aabb_node *>(ctx->nodes), nNodes, ctx->image, ctx->stream);
-		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, nullptr, nullptr, ctx->stream);
+		const unsigned *order = nullptr;
+		const float *boxes = nullptr;
+		if (wantWide) {
+			// the grid needs the scene's bounds: the two boxes of the root (the tree is nested by construction)
+			restir_aabb_node root;
+			CU(ctx, cudaMemcpyAsync(&root, ctx->nodes, sizeof(root), cudaMemcpyDeviceToHost, ctx->stream));
+			CU(ctx, cudaStreamSynchronize(ctx->stream));
+			double lo[3], hi[3];
+			for (int a = 0; a < 3; ++a) {
+				lo[a] = std::min((double)root.leftAabbMin[a], (double)root.rightAabbMin[a]);
+				hi[a] = std::max((double)root.leftAabbMax[a], (double)root.rightAabbMax[a]);
+			}
+			WideQuant quant;
+			if (!make_wide_grid(lo, hi, wideGrid, quant)) {
+				wideInfo.why = "scene coordinates out of the range the quantised grid is defined for";
+			} else {
+				const size_t need = wide_build_scratch_bytes(nNodes, n_triangles);
+				if (ctx->bvhScratchBytes < need) {
+					freeDev(ctx->bvhScratch);
+					ctx->bvhScratchBytes = 0;
+					CU(ctx, cudaMalloc(&ctx->bvhScratch, need));
+					ctx->bvhScratchBytes = need;
+				}
+				WideNode *wide = reinterpret_cast<WideNode *>(ctx->treeBlock + imageBytes + edgeBytes);
+				float *dstBoxes = reinterpret_cast<float *>(ctx->treeBlock + imageBytes + edgeBytes + wideBytes);
+				unsigned *dstOrder = reinterpret_cast<unsigned *>(ctx->treeBlock + imageBytes + edgeBytes + wideBytes + boxBytes);
+				unsigned nWide = 0;
+				int depth = 0;
+				bool usable = false;
+				beforeLaunch(ctx, "wide_build (all kernels)");
+				cudaError_t we = build_wide_image_device(reinterpret_cast<const restir_aabb_node *>(ctx->nodes), nNodes, n_triangles, quant, wide, dstOrder, dstBoxes,
+				                                         ctx->image, ctx->bvhScratch, &nWide, &depth, &usable, ctx->stream);
+				int wrc = afterLaunch(ctx, "wide_build (all kernels)");
+				if (we != cudaSuccess) return cudaCheck(ctx, we, "restir_build_bvh_device (wide image)");
+				if (wrc != RESTIR_OK) return wrc;
+				if (usable) {
+					ctx->wide = reinterpret_cast<uint4 *>(wide);
+					wideInfo.usable = true;
+					wideInfo.nodes = nWide;
+					wideInfo.depth = wideInfo.stackBound = depth;
+					order = dstOrder;
+					boxes = dstBoxes;
+				} else {
+					wideInfo.why = "the wide image could not be derived from this tree (deeper than the walk's stack, or a box off the grid)";
+					launch_bvh_image(reinterpret_cast<const restir_aabb_node *>(ctx->nodes), nNodes, ctx->image, ctx->stream); // undo a partial remap
+				}
+			}
+		} else {
+			wideInfo.why = "not requested";
+		}
+		ctx->wideOrder = order;
+		launch_derive_triangle_edges(ctx->tris, n_triangles, ctx->triEdges, order, boxes, ctx->stream);
 		CU(ctx, cudaGetLastError());
 	} else {
 		info.why = "deeper than the 32-entry stack";
@@ -779,7 +842,9 @@ int restir_build_bvh_device(restir_context *ctx, const void *triangles, uint32_t
 	ctx->nNodes = nNodes;
 	ctx->nTris = n_triangles;
 	ctx->imageInfo = info;
-	return RESTIR_OK;
+	ctx->wideGrid = wideGrid;
+	ctx->wideInfo = wideInfo;
+	return clearOccluders(ctx);
 }
 
 static int uploadBlob(restir_context *ctx, const void *blob, size_t bytes, size_t stride, unsigned char *&dst, int &count, const char *name) {
@@ -1455,6 +1520,28 @@ int restir_check_aabb_tree(const void *nodes, uint32_t n_nodes, uint32_t n_trian
 		}
 	}
 	return ok ? RESTIR_OK : RESTIR_E_INVALID;
+}
+
+int restir_get_wide_image(restir_context *ctx, void *wide_nodes, uint32_t capacity, uint32_t *n_wide, uint32_t *tri_order) {
+	ENTER(ctx);
+	if (n_wide) *n_wide = ctx->wide ? ctx->wideInfo.nodes : 0;
+	if (ctx->wide == nullptr) {
+		return fail(ctx, RESTIR_E_UNSUPPORTED, "the tree is not walked wide: %s", ctx->wideInfo.why.c_str());
+	}
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	if (wide_nodes != nullptr) {
+		if (capacity < ctx->wideInfo.nodes) {
+			return fail(ctx, RESTIR_E_INVALID, "restir_get_wide_image: room for %u nodes, the image has %u", capacity, ctx->wideInfo.nodes);
+		}
+		CU(ctx, cudaMemcpy(wide_nodes, ctx->wide, (size_t)ctx->wideInfo.nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+	}
+	if (tri_order != nullptr) { // recovered from the records: record r holds the triangle whose p1 ... simpler: kept next to the image
+		if (ctx->wideOrder == nullptr) {
+			return fail(ctx, RESTIR_E_UNSUPPORTED, "restir_get_wide_image: record order not kept");
+		}
+		CU(ctx, cudaMemcpy(tri_order, ctx->wideOrder, (size_t)ctx->nTris * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	}
+	return RESTIR_OK;
 }
 
 int restir_check_wide_walk(const void *nodes, uint32_t n_nodes, const void *triangles, uint32_t n_triangles, const float *p1, const float *p2,

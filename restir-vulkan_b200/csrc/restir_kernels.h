@@ -150,6 +150,11 @@ size_t bvh_build_scratch_bytes(unsigned n);
 cudaError_t build_aabb_tree_device(const float4 *tris, unsigned n, restir_aabb_node *nodes, void *scratch, int *levelsOut, unsigned *nonFinite,
                                    cudaStream_t s);
 void launch_bvh_image(const restir_aabb_node *nodes, unsigned n, float4 *image, cudaStream_t s);
+// the 4-wide image of a tree on the device (restir_wide_build.cu): byte for byte what build_wide_image makes on the host
+size_t wide_build_scratch_bytes(unsigned nNodes, unsigned nTris);
+cudaError_t build_wide_image_device(const restir_aabb_node *nodes, unsigned nNodes, unsigned nTris, const WideQuant &quant, WideNode *wide, unsigned *triOrder,
+                                    float *leafBoxes, float4 *image, void *scratch, unsigned *nWide, int *depth, bool *usable, cudaStream_t s);
+cudaError_t preload_wide_build_kernels();
 cudaError_t preload_bvh_build_kernels();
 
 // ---- halo exchange over peer memory (restir_halo.cu) ----------------------------------------------------------

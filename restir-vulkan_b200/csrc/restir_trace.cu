@@ -39,7 +39,7 @@ constexpr int kTraceWarps = kTraceThreads / 32;
 #ifndef RESTIR_TRACE_CHUNK
 #define RESTIR_TRACE_CHUNK 128
 #endif
-// items per warp fetch (power of two, <= 256: the local id is 8 bits of the sort key).  Neighbour rays: about half of the
+// items per warp fetch (power of two, <= 1024: the local id is the low kLocalBits of the sort key).  Neighbour rays: about half of the
 // items of a chunk are answered without a ray (item_resolve), so the chunk is twice as long to keep the batches full.
 constexpr int kChunk = RESTIR_TRACE_CHUNK;
 #ifndef RESTIR_TRACE_CHUNK_NEIGHBOURS
@@ -55,6 +55,7 @@ template <int MODE> struct ChunkOf {
 #define RESTIR_TRACE_SHARE 1 // answer a neighbour ray from the neighbour's own ray when the two segments are identical
 #endif
 constexpr unsigned kInvalidKey = 0xffffffffu;
+constexpr unsigned kLocalBits = 10, kLocalMask = (1u << kLocalBits) - 1u, kLightMask = (1u << (31 - kLocalBits)) - 1u; // sort key = light << kLocalBits | position in the chunk
 
 // What a trace kernel walks: the uploaded 80-byte nodes in the reference's order, their 64-byte binary image, or the 4-wide
 // quantised image (restir_wide.cuh) with the binary image for the rays outside its range.
@@ -245,7 +246,7 @@ template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const
 				}
 			}
 			if (!witnessed) { // (an alias keeps a valid key until the caller has recorded it)
-				key = (((RESTIR_TRACE_SORT ? light : 0u) & 0x7fffffu) << 8) | local;
+				key = (((RESTIR_TRACE_SORT ? light : 0u) & kLightMask) << kLocalBits) | local;
 			}
 		}
 	}
@@ -453,7 +454,7 @@ template <int MODE, int WALK> __global__ void __launch_bounds__(kTraceThreads, R
 						if (key != kInvalidKey) {
 							f3 p1, p2, o, d;
 							size_t opix;
-							out = item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
+							out = item_segment<MODE>(tp, base + (key & kLocalMask), p1, p2, opix);
 							segment_setup(p1, p2, o, d);
 							ray = walk_ray(o, d);
 							top = 0;
@@ -486,7 +487,7 @@ template <int MODE, int WALK> __global__ void __launch_bounds__(kTraceThreads, R
 					continue;
 				}
 				if (key != kInvalidKey) {
-					unsigned item = base + (key & 255u);
+					unsigned item = base + (key & kLocalMask);
 					f3 p1, p2, o, d;
 					size_t opix;
 					size_t out = item_segment<MODE>(tp, item, p1, p2, opix);
@@ -601,7 +602,7 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 			if (key != kInvalidKey) {
 				f3 p1, p2, o, d;
 				size_t opix;
-				item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
+				item_segment<MODE>(tp, base + (key & kLocalMask), p1, p2, opix);
 				segment_setup(p1, p2, o, d);
 				float *od = &rayOD[0][threadIdx.x];
 				od[0] = o.x; od[kTraceThreads] = o.y; od[2 * kTraceThreads] = o.z;
@@ -623,10 +624,10 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 			if (key != kInvalidKey) {
 				f3 p1, p2;
 				size_t opix;
-				const size_t out = item_segment<MODE>(tp, base + (key & 255u), p1, p2, opix);
+				const size_t out = item_segment<MODE>(tp, base + (key & kLocalMask), p1, p2, opix);
 				tp.shadowed[out] = rec != -1 ? 1 : 0;
 				if (MODE != kTraceSegments && rec >= 0 && tp.occluders != nullptr) { // the witness for the next ray of this region at this light
-					const unsigned light = key >> 8;
+					const unsigned light = key >> kLocalBits;
 					tp.occluders[occluder_entry(tp, opix, light)] = (((light >> 8) & 255u) << 24) | (unsigned)rec;
 				}
 			}

@@ -51,6 +51,40 @@ inline bool inside(const Slot &c, const Slot &p) {
 
 } // namespace
 
+bool make_wide_grid(const double lo[3], const double hi[3], WideGrid &grid, WideQuant &quant) {
+	for (int a = 0; a < 3; ++a) {
+		if (!std::isfinite(lo[a]) || !std::isfinite(hi[a]) || lo[a] > hi[a]) {
+			return false;
+		}
+		double extent = hi[a] - lo[a], H0 = std::max(std::fabs(lo[a]), std::fabs(hi[a]));
+		double want = std::max({2.001 * extent, H0 / 512.0, std::ldexp(1.0, -40)});
+		int e;
+		std::frexp(want, &e); // want = f * 2^e, 0.5 <= f < 1
+		for (;; ++e) {
+			double K = std::ldexp(1.0, e);
+			float h = (float)(lo[a] - 0.5 * K);
+			if ((double)h + 0.5 * K > lo[a]) {
+				h = std::nextafterf(h, -INFINITY);
+			}
+			double gmin = (double)h + 0.5 * K, c = K / 65536.0;
+			if (gmin <= lo[a] && gmin + 32767.0 * c >= hi[a]) {
+				grid.h[a] = h;
+				grid.K[a] = (float)K;
+				grid.H[a] = (float)std::max(std::fabs((double)h), std::fabs((double)h + K)) * 1.0000002f;
+				grid.maxOrigin[a] = (float)(K * 65536.0);
+				quant.gridMin[a] = gmin;
+				quant.cell[a] = c;
+				quant.invCell[a] = 65536.0 / K;
+				break;
+			}
+		}
+		if (!(grid.K[a] <= 1099511627776.0f) || !(grid.H[a] <= 1024.0f * grid.K[a])) {
+			return false;
+		}
+	}
+	return true;
+}
+
 bool build_wide_image(const restir_aabb_node *nodes, uint32_t nNodes, uint32_t nTris, std::vector<WideNode> &out, std::vector<uint32_t> &triOrder,
                       std::vector<float> &leafBoxes, WideGrid &grid, WideImageInfo &info) {
 	out.clear();
@@ -110,45 +144,11 @@ bool build_wide_image(const restir_aabb_node *nodes, uint32_t nNodes, uint32_t n
 		}
 	}
 
-	// ---- the grid: per axis K = 65536 cells, a power of two with 32767 cells >= the scene's extent; h = origin - K / 2 --------
-	double gridMin[3], cell[3];
-	for (int a = 0; a < 3; ++a) {
-		double extent = hi[a] - lo[a], H0 = std::max(std::fabs(lo[a]), std::fabs(hi[a]));
-		double want = std::max({2.001 * extent, H0 / 512.0, std::ldexp(1.0, -40)});
-		int e;
-		std::frexp(want, &e); // want = f * 2^e, 0.5 <= f < 1
-		for (;; ++e) {
-			double K = std::ldexp(1.0, e);
-			float h = (float)(lo[a] - 0.5 * K);
-			if ((double)h + 0.5 * K > lo[a]) {
-				h = std::nextafterf(h, -INFINITY);
-			}
-			double gmin = (double)h + 0.5 * K, c = K / 65536.0;
-			if (gmin <= lo[a] && gmin + 32767.0 * c >= hi[a]) {
-				grid.h[a] = h;
-				grid.K[a] = (float)K;
-				grid.H[a] = (float)std::max(std::fabs((double)h), std::fabs((double)h + K)) * 1.0000002f;
-				grid.maxOrigin[a] = (float)(K * 65536.0);
-				gridMin[a] = gmin;
-				cell[a] = c;
-				break;
-			}
-		}
-		if (!(grid.K[a] <= 1099511627776.0f) || !(grid.H[a] <= 1024.0f * grid.K[a])) {
-			return refuse("scene coordinates out of the range the quantised grid is defined for");
-		}
+	WideQuant quant;
+	if (!make_wide_grid(lo, hi, grid, quant)) {
+		return refuse("scene coordinates out of the range the quantised grid is defined for");
 	}
-	auto quantise = [&](const Slot &s, int a, uint32_t &word) {
-		double ql = std::floor(((double)s.mn[a] - gridMin[a]) / cell[a]), qh = std::ceil(((double)s.mx[a] - gridMin[a]) / cell[a]);
-		ql = std::min(std::max(ql, 0.0), 32767.0);
-		qh = std::min(std::max(qh, 0.0), 32767.0);
-		// outward, exactly: the decoded planes enclose the fp32 box
-		if (!(gridMin[a] + ql * cell[a] <= (double)s.mn[a]) || !(gridMin[a] + qh * cell[a] >= (double)s.mx[a])) {
-			return false;
-		}
-		word = (uint32_t)ql | ((uint32_t)qh << 16);
-		return true;
-	};
+	auto quantise = [&](const Slot &s, int a, uint32_t &word) { return wide_quantise(quant, a, s.mn[a], s.mx[a], word); };
 
 	// ---- collapse: a wide node takes the two children of a binary node and, while it has room, opens the inner child of
 	// largest surface area into its own two children ------------------------------------------------------------------------------

@@ -67,6 +67,27 @@ struct WideGrid {
 	float maxOrigin[3];     // rays starting farther than this from 0 on an axis walk the binary image (2^16 * K)
 };
 
+// what the builders quantise with: grid origin and cell size per axis, in double (cell a power of two: every product below is exact)
+struct WideQuant {
+	double gridMin[3], cell[3], invCell[3];
+};
+// The grid of a scene whose boxes lie in [lo, hi] (per axis K = 65536 cells, a power of two with 32767 cells >= the extent; h =
+// origin - K / 2 a float).  false: coordinates out of the range the grid is defined for.
+bool make_wide_grid(const double lo[3], const double hi[3], WideGrid &grid, WideQuant &quant);
+
+// lo | hi << 16 of the fp32 interval [mn, mx] on one axis, rounded outwards; false when the decoded planes would not enclose it
+// (host + device: the two builders must produce the same words)
+RESTIR_HD bool wide_quantise(const WideQuant &g, int a, float mn, float mx, uint32_t &word) {
+	double ql = floor(((double)mn - g.gridMin[a]) * g.invCell[a]), qh = ceil(((double)mx - g.gridMin[a]) * g.invCell[a]);
+	ql = fmin(fmax(ql, 0.0), 32767.0);
+	qh = fmin(fmax(qh, 0.0), 32767.0);
+	if (!(g.gridMin[a] + ql * g.cell[a] <= (double)mn) || !(g.gridMin[a] + qh * g.cell[a] >= (double)mx)) {
+		return false;
+	}
+	word = (uint32_t)ql | ((uint32_t)qh << 16);
+	return true;
+}
+
 struct WideImageInfo {
 	bool usable = false;
 	std::string why;

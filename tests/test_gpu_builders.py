@@ -70,17 +70,26 @@ def test_device_tree_equals_reference_tree(name):
     got = ctx.build_bvh_device(scene.triangles, want_nodes=False)
     ctx.synchronize()
     ms = (time.perf_counter() - t0) * 1e3
-    dev_ms = ctx.profile_end()["bvh_build (all kernels)"][1]
+    prof = ctx.profile_end()
+    dev_ms, wide_ms = prof["bvh_build (all kernels)"][1], prof.get("wide_build (all kernels)", (0, 0.0))[1]
     got = ctx.build_bvh_device(scene.triangles)
     assert np.array_equal(got, ref_nodes), f"{name}: {(got != ref_nodes).any(axis=1).sum()} nodes differ from the reference's tree"
     rc, info, _ = capi.check_aabb_tree(ref_nodes, scene.n_triangles)
     mine = ctx.bvh_info()
-    assert rc == 0 and mine["depth"] == info["depth"] and mine["nodes"] == info["nodes"]
-    # an uploaded tree gets the 4-wide image (derived on the host); a tree built on the device is walked through its binary image
-    assert info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE and mine["traversal"] == capi.RESTIR_TRAVERSAL_IMAGE
+    assert rc == 0 and mine["depth"] == info["depth"] and mine["nodes"] == info["nodes"] and mine["traversal"] == info["traversal"] == capi.RESTIR_TRAVERSAL_WIDE
+    # the 4-wide image derived on the device (restir_wide_build.cu) is the one the host derives from the same nodes (wide_image.cpp)
+    assert (mine["wide_nodes"], mine["wide_depth"]) == (info["wide_nodes"], info["wide_depth"])
+    dev_nodes, dev_order = ctx.wide_image()
+    up = capi.RestirContext(0)
+    up.upload_bvh(ref_nodes, scene.triangles)
+    host_nodes, host_order = up.wide_image()
+    up.close()
+    assert np.array_equal(dev_nodes, host_nodes), f"{name}: {(dev_nodes != host_nodes).any(axis=1).sum()} wide nodes differ"
+    assert np.array_equal(dev_order, host_order)
     assert mine["reference_stack_bound"] >= info["reference_stack_bound"]
     print(f"{name}: {scene.n_triangles} triangles, device build {dev_ms:.2f} ms on the stream (CUDA events around all of its kernels and per-level "
-          f"read-backs), {ms:.2f} ms wall with upload and install, depth {mine['depth']}")
+          f"read-backs) + {wide_ms:.2f} ms for its 4-wide image, {ms:.2f} ms wall with upload and install, depth {mine['depth']}, {mine['wide_nodes']} wide nodes in "
+          f"{mine['wide_depth']} levels")
     # the installed tree traces like the uploaded one
     po = ph.oracle()
     rng = np.random.default_rng(3)
