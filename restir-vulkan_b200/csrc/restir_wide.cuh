@@ -13,6 +13,10 @@
 #include "restir_trace.cuh"
 #include "wide_image.h"
 
+#ifndef RESTIR_WIDE_PREFETCH
+#define RESTIR_WIDE_PREFETCH 0 // experiment: 1 = prefetch the line of the first two children of every visited node into L1, 2 = both lines
+#endif
+
 namespace restir {
 
 struct U8 {
@@ -141,6 +145,18 @@ __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, co
 		group &= group - 1u; // the lowest set bit lies in the mask
 		const uint4 *n = wide + ((size_t)((group >> 4) + slot)) * 4u;
 		const U8 a = ldg256u(n), b = ldg256u(n + 2); // a: x words of the four slots, y words; b: z words, (childBase, triBase, inner, count)
+#if RESTIR_WIDE_PREFETCH > 0
+		// the children of a node are consecutive 64-byte nodes (two per 128-byte line): ask for them while the boxes are tested
+		if (b.v[6] != 0u) {
+			const uint4 *c = wide + (size_t)b.v[4] * 4u;
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
+#if RESTIR_WIDE_PREFETCH > 1
+			if (b.v[6] > 2u) {
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 8));
+			}
+#endif
+		}
+#endif
 		float2 nx, fx, ny, fy, nz, fz;
 		unsigned hits;
 		// slots 0 and 1
