@@ -156,7 +156,10 @@ __host__ __device__ inline uint32_t draws_per_candidate(bool pointMode) { return
 #define RESTIR_CANDIDATES_SKIP_AHEAD 0
 #endif
 // no minimum CTA count here: the loop is issue-bound, 64 registers (4 CTAs/SM) is what ptxas picks on its own and both 72 and 51 lose
-__global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
+#ifndef RESTIR_CANDIDATES_MIN_BLOCKS
+#define RESTIR_CANDIDATES_MIN_BLOCKS 4 // 64 registers: 0.6085 -> 0.602 ms against the 70 ptxas takes when left alone
+#endif
+__global__ void __launch_bounds__(kThreads, RESTIR_CANDIDATES_MIN_BLOCKS) omni_candidates_kernel(PassParams p, PackedReservoir *__restrict__ out) {
 	int x, y;
 	const bool inside = pixel_of_thread(p.band, x, y); // no early return: the skip-ahead loop votes with the whole warp
 	const SceneView &sc = p.scene;
@@ -258,12 +261,27 @@ __global__ void __launch_bounds__(kThreads) omni_candidates_kernel(PassParams p,
 				ln = mk3(na.x, na.y, na.z);
 				prob = prob / (fabsf(dot3(wi, ln)) * na.w);
 			}
-			float pHat = evaluate_phat(sf, albedoLum, lpos, ln, !pointMode, lum); // :135-139
-			// addSampleToReservoir + updateReservoirAt, reservoir.glsl:28-42, 6-26
-			float weight = pHat / prob;
+			// evaluatePHat (:135-139), then addSampleToReservoir + updateReservoirAt (reservoir.glsl:28-42, 6-26): eleven divisions,
+			// reciprocals and square roots — the divider's fast sequences without their wrappers, validated once (restir_math.cuh
+			// SpecOps), the ordinary operators when an operand was out of the range in which those sequences are the divider's own
+			float pHat, weight, sum, replacePossibility;
+			OpGuard guard;
+			pHat = evaluate_phat_t<SpecOps>(sf, albedoLum, lpos, ln, !pointMode, lum, guard);
+			SpecOps::check(pHat, guard);
+			SpecOps::check(prob, guard);
+			weight = SpecOps::div(pHat, prob);
+			sum = res.sumWeights + weight;
+			SpecOps::check(weight, guard);
+			SpecOps::check(sum, guard);
+			replacePossibility = SpecOps::div(weight, sum);
+			if (!guard.ok()) {
+				pHat = evaluate_phat_call(sf, albedoLum, lpos, ln, !pointMode, lum);
+				weight = pHat / prob;
+				sum = res.sumWeights + weight;
+				replacePossibility = weight / sum;
+			}
 			res.M += 1u;
-			res.sumWeights = res.sumWeights + weight;
-			float replacePossibility = weight / res.sumWeights;
+			res.sumWeights = sum;
 			if (pcg_float(rng) < replacePossibility) {
 				res.px = lpos.x; res.py = lpos.y; res.pz = lpos.z;
 				res.lightIndex = lightIndex;
