@@ -33,8 +33,10 @@ def main():
         d = dict(zip(head, row))
         name = d["Kernel Name"]
         label = name.split("(")[0].replace("void ", "").replace("restir::", "")
+        if label.startswith("trace_wide_kernel"):   # the kernel that walks the 4-wide image: same roles, same display names
+            label = label.replace("trace_wide_kernel", "trace_kernel")
         if label.startswith("trace_kernel"):
-            mode = label[label.index("<") + 1:].split(",")[0].replace("(int)", "").strip()
+            mode = label[label.index("<") + 1:].split(",")[0].replace("(int)", "").replace(">", "").strip()
             if mode == "2":
                 label = "trace_kernel<segments>"
             elif mode == "1":
