@@ -376,7 +376,7 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
         c.upload_lights(scene.point_blob, scene.tri_blob, scene.alias_blob)
         c.set_unbiased_neighbors(k if cfg["unbiased"] else 3)
         c.set_spatial_staging(args.spatial_staging == "on")
-        c.set_occluder_cache(args.occluder_cache == "on")
+        c.set_occluder_cache({"on": 1, "off": 0, "light": 2, "direction": 3}[args.occluder_cache])
         c.set_ray_elision({"on": 1, "off": 0, "dedupe": 2}[args.ray_elision])
         if variant != (1, False, False):
             c.set_reservoir_variant(*variant)
@@ -909,7 +909,7 @@ def main():
                     help="reference-order: walk the 80-byte nodes literally (A/B against the 64-byte re-stride)")
     ap.add_argument("--ray-elision", default="on", choices=["on", "off", "dedupe"],
                     help="unbiased pass: answer neighbour rays without a walk where that is exact (restir_set_ray_elision; A/B)")
-    ap.add_argument("--occluder-cache", default="on", choices=["on", "off"],
+    ap.add_argument("--occluder-cache", default="on", choices=["on", "off", "light", "direction"],
                     help="trace kernel: test the cached occluder of (screen region, light) before queueing a ray for a walk (exact; A/B)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): one config-sized band per GPU; strong: the config's frame split into N bands")

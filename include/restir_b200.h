@@ -212,8 +212,9 @@ int restir_set_traversal(restir_context *ctx, int mode);
  * triangle that occluded a ray, and tests it (the reference's triangle test and the reference's slab test on its leaf box)
  * before queueing a ray for a walk: "shadowed" needs one witness, and most shadowed rays of a region at a light share theirs.
  * The table only proposes witnesses — its contents cannot change a visibility bit — but shadow_rays_traced then depends on
- * what earlier frames left in it.  enable = 0 walks every ray that is not elided (A/B, deterministic counters); both settings
- * clear the table.  Default: 1. */
+ * what earlier frames left in it.  enable = 0 walks every ray that is not elided (A/B, deterministic counters); every call
+ * clears the table.  Default: 1 = entries chosen by light index for up to 4 096 lights and by the segment's direction (cube face
+ * + 8 x 8 grid) beyond, where a (region, light) pair practically never comes back; 2 / 3 force the first / the second (A/B). */
 int restir_set_occluder_cache(restir_context *ctx, int enable);
 
 typedef struct restir_bvh_info {

@@ -462,7 +462,8 @@ class RestirContext:
         return nodes[:n.value], order
 
     def set_occluder_cache(self, enable):
-        self._check(self.lib.restir_set_occluder_cache(self._ctx, C.c_int(1 if enable else 0)))
+        """0 off, 1 / True default (by light index up to 4 096 lights, by direction beyond), 2 by light index, 3 by direction."""
+        self._check(self.lib.restir_set_occluder_cache(self._ctx, C.c_int(int(enable))))
 
     def set_traversal(self, mode):
         """Takes effect at the next upload_bvh."""

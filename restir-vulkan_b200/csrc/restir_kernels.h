@@ -44,6 +44,8 @@ struct TraceParams {
 	unsigned *aliasCount;               // device counter of `aliases`
 	unsigned *occluders;                // occluder cache (restir_trace.cu): [screen region][256] -> tag << 24 | triangle record; null: off
 	unsigned regionsX;                  // regions (64 x 32 pixels) per region row
+	int occluderPretest;                // test the cached witness before a ray is queued (walks record witnesses either way)
+	int occluderByDirection;            // entries chosen by the segment's direction instead of the light index (many lights)
 	unsigned nTris;
 	unsigned nNodes;
 	FastDiv divW, divTilesX, divSlots;  // set by launch_trace

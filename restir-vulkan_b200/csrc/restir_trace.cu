@@ -160,11 +160,35 @@ template <int MODE> __device__ __forceinline__ int item_resolve(const TraceParam
 // triangle test.  Walks that find an occluder record it.  The table only ever proposes witnesses, so its contents (racy
 // plain stores, stale entries of earlier frames) cannot change a bit of the result.
 // Entry = tag (bits 8..15 of the light index) << 24 | triangle record; 0xffffffff = empty (records stay below 2^24).
+// With more lights than a region's entries can tell apart (tp.occluderByDirection: the 1 M-light frames, where a (region, light)
+// pair practically never comes back) the entry is chosen by the DIRECTION of the segment instead — cube face and an 8 x 8 grid
+// on it, 384 cells: rays of a region that leave in the same direction meet the same nearby geometry whatever light they aim at.
+// CPU estimate (960 x 540, 1 M lights, 64 candidates): 36 % of the shadowed restirOmni rays answered, against 12 % by light index;
+// with 200 lights it is the other way round (64 % against 76 %).
 constexpr unsigned kOccluderSlots = 256;
-__device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t opix, unsigned light) {
+__device__ __forceinline__ unsigned occluder_key(const TraceParams &tp, unsigned light, f3 p1, f3 p2) { // 16 bits: entry | tag << 8
+	if (!tp.occluderByDirection) {
+		return light & 0xffffu;
+	}
+	const f3 dir = p2 - p1;
+	const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+	unsigned face;
+	float u, v, m;
+	if (ax >= ay && ax >= az) {
+		face = dir.x > 0.0f ? 0u : 1u; m = ax; u = dir.y; v = dir.z;
+	} else if (ay >= az) {
+		face = dir.y > 0.0f ? 2u : 3u; m = ay; u = dir.x; v = dir.z;
+	} else {
+		face = dir.z > 0.0f ? 4u : 5u; m = az; u = dir.x; v = dir.y;
+	}
+	const float s = __fdividef(4.0f, m); // a heuristic key: any value is as correct as any other
+	const unsigned iu = min((unsigned)max((int)(u * s + 4.0f), 0), 7u), iv = min((unsigned)max((int)(v * s + 4.0f), 0), 7u);
+	return (face * 8u + iu) * 8u + iv;
+}
+__device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t opix, unsigned key16) {
 	const unsigned W = (unsigned)tp.band.W, n = (unsigned)opix;
 	const unsigned yl = fast_div(n, tp.divW), x = n - yl * W;
-	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (light & (kOccluderSlots - 1u));
+	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (key16 & (kOccluderSlots - 1u));
 }
 
 // ---- one walk per segment ---------------------------------------------------------------------------------------------------
@@ -230,12 +254,20 @@ template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const
 			if (MODE == kTraceUnbiased && WALK == kWalkWide && tp.dedupe != nullptr) {
 				alias = segment_claim(tp, item, pix, opix, aliasOf);
 			}
-			if (WALK == kWalkWide && tp.occluders != nullptr && !alias) {
-				const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, light));
+			if (WALK == kWalkWide && tp.occluders != nullptr && tp.occluderPretest && !alias) {
+				float4 w = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t = w;
+				if (tp.occluderByDirection) { // the key needs the segment
+					w = __ldg(tp.worldPos + opix);
+					t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+				}
+				const unsigned key16 = occluder_key(tp, light, mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z));
+				const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, key16));
 				const unsigned rec = e & 0xffffffu;
-				if ((e >> 24) == ((light >> 8) & 255u) && rec < tp.nTris) {
-					float4 w = __ldg(tp.worldPos + opix);
-					float4 t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+				if ((e >> 24) == (key16 >> 8) && rec < tp.nTris) {
+					if (!tp.occluderByDirection) {
+						w = __ldg(tp.worldPos + opix);
+						t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
+					}
 					f3 o, d;
 					segment_setup(mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z), o, d);
 					if (wide_ray_in_range(tp.grid, o, d) && wide_leaf_hit(tp.triEdges, rec, o, d)) {
@@ -627,8 +659,8 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 				const size_t out = item_segment<MODE>(tp, base + (key & kLocalMask), p1, p2, opix);
 				tp.shadowed[out] = rec != -1 ? 1 : 0;
 				if (MODE != kTraceSegments && rec >= 0 && tp.occluders != nullptr) { // the witness for the next ray of this region at this light
-					const unsigned light = key >> kLocalBits;
-					tp.occluders[occluder_entry(tp, opix, light)] = (((light >> 8) & 255u) << 24) | (unsigned)rec;
+					const unsigned key16 = occluder_key(tp, key >> kLocalBits, p1, p2);
+					tp.occluders[occluder_entry(tp, opix, key16)] = ((key16 >> 8) << 24) | (unsigned)rec;
 				}
 			}
 		}

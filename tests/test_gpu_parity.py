@@ -303,6 +303,11 @@ def test_occluder_cache_is_exact(name):
     # the same context again: the table now holds the witnesses of the last frame of the first run (another camera position)
     got = ph.run_cuda(case, ctx)
     ph.assert_frames_match(got, want, f"{name} cache on, stale entries")
+    ctx.set_occluder_cache(3)                                     # entries chosen by the segment's direction (the many-light default)
+    got = ph.run_cuda(case, ctx)
+    got = ph.run_cuda(case, ctx)
+    ph.assert_frames_match(got, want, f"{name} cache by direction")
+    assert sum(f["counters"]["shadow_rays_cached"] for f in got) > 0
     ctx.set_occluder_cache(0)
     got = ph.run_cuda(case, ctx)
     ph.assert_frames_match(got, want, f"{name} cache off")
