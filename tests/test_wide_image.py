@@ -136,3 +136,20 @@ def test_wide_margin_never_loses_a_box_the_reference_slab_test_passes():
     want = ph.oracle().trace_segments(ph.oracle_scene(scene), p1, p2)
     took = walked != 0
     assert took.mean() > 0.5 and np.array_equal(shadowed[took], want[took])
+
+
+def test_fast_div_formula_is_exact():
+    """csrc/restir_kernels.h FastDiv: n / d as the high half of n * ceil(2^64 / d) — the trace kernels divide item and pixel
+    numbers by the screen width, the tiles per row and the rays per pixel this way.  The formula, restated with Python's integers,
+    against n // d on the edges and on random values of the whole 32-bit range."""
+    rng = np.random.default_rng(17)
+    ds = [2, 3, 5, 7, 240, 1920, 1921, 3840, 7680, 65535, 65536, 65537, (1 << 20), (1 << 31) - 1, (1 << 31), (1 << 32) - 1] + \
+        [int(x) for x in rng.integers(2, 1 << 32, 200)]
+    for d in ds:
+        m = ((1 << 64) - 1) // d + 1
+        assert m < (1 << 64)
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 32) - 1, (1 << 32) - d, ((1 << 32) - 1) // d * d, ((1 << 32) - 1) // d * d - 1] + \
+            [int(x) for x in rng.integers(0, 1 << 32, 400)]
+        for n in ns:
+            if 0 <= n < (1 << 32):
+                assert (n * m) >> 64 == n // d, (n, d)
