@@ -331,25 +331,75 @@ template <int CHUNK> __device__ __forceinline__ void warp_sort(unsigned *keys, u
 	}
 }
 
-// the same network over the first n keys (n a power of two <= CHUNK, warp-uniform)
-__device__ __forceinline__ void warp_sort_n(unsigned *keys, unsigned n, unsigned lane) {
-#pragma unroll 1
-	for (unsigned k = 2; k <= n; k <<= 1) {
-#pragma unroll 1
-		for (unsigned j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-			for (unsigned t = lane; t < n / 2; t += 32) {
-				unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
-				unsigned a = keys[i], b = keys[i + j];
-				bool ascending = (i & k) == 0u;
-				if ((a > b) == ascending) {
-					keys[i] = b;
-					keys[i + j] = a;
+// The same network over the first n = 32 R keys with the keys in REGISTERS (key i = r * 32 + lane lives in register r of its lane):
+// a compare-exchange at distance j >= 32 pairs two registers of one lane, at distance j < 32 one shuffle fetches the partner's
+// key and the lane keeps the smaller or the larger — no shared-memory round trip, no index arithmetic, no warp barrier per
+// stage (n = 128: ~340 instructions against ~1 000 for the shared-memory loop; capture N: the sort was 8.5 % of the neighbour
+// kernel).  Fully unrolled per R.
+template <int R> __device__ __forceinline__ void warp_sort_regs(unsigned *keys, unsigned lane) {
+	unsigned v[R];
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		v[r] = keys[r * 32 + lane];
+	}
+#pragma unroll
+	for (int k = 2; k <= R * 32; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			if (j >= 32) {
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const int pr = r ^ (j / 32);
+					if (pr > r) {
+						const bool ascending = ((r * 32) & k) == 0; // k >= 64 here: the bit is one of r's
+						const unsigned lo = min(v[r], v[pr]), hi = max(v[r], v[pr]);
+						v[r] = ascending ? lo : hi;
+						v[pr] = ascending ? hi : lo;
+					}
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const unsigned other = __shfl_xor_sync(0xffffffffu, v[r], j);
+					const bool ascending = (((unsigned)(r * 32) + lane) & (unsigned)k) == 0u;
+					const bool lower = (lane & (unsigned)j) == 0u; // this lane holds the lower index of the pair
+					v[r] = lower == ascending ? min(v[r], other) : max(v[r], other);
 				}
 			}
-			__syncwarp();
 		}
 	}
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		keys[r * 32 + lane] = v[r];
+	}
+}
+// n in {32, 64, 128, 256, ...}: the register network up to 256 keys, the shared-memory loop beyond
+__device__ __forceinline__ void warp_sort_n(unsigned *keys, unsigned n, unsigned lane) {
+	switch (n) {
+	case 32: warp_sort_regs<1>(keys, lane); break;
+	case 64: warp_sort_regs<2>(keys, lane); break;
+	case 128: warp_sort_regs<4>(keys, lane); break;
+	case 256: warp_sort_regs<8>(keys, lane); break;
+	default:
+#pragma unroll 1
+		for (unsigned k = 2; k <= n; k <<= 1) {
+#pragma unroll 1
+			for (unsigned j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+				for (unsigned t = lane; t < n / 2; t += 32) {
+					unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+					unsigned a = keys[i], b = keys[i + j];
+					bool ascending = (i & k) == 0u;
+					if ((a > b) == ascending) {
+						keys[i] = b;
+						keys[i + j] = a;
+					}
+				}
+				__syncwarp();
+			}
+		}
+	}
+	__syncwarp();
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
