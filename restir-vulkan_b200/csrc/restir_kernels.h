@@ -64,6 +64,7 @@ struct TraceParams {
 	unsigned long long *counters;
 	unsigned *regionCursors, *smSlots; // RESTIR_TRACE_AFFINE: one chunk cursor per region of the work list, one arrival counter per SM
 	unsigned blocksPerSm;
+	float guidedShare;                 // RESTIR_TRACE_GUIDED / warps of the grid (set by the launcher): the part of the remaining items one fetch takes
 };
 constexpr unsigned kTraceMaxRegions = 4096, kTraceMaxSms = 1024; // regionCursors holds kTraceMaxRegions + kTraceMaxSms words, smSlots = regionCursors + kTraceMaxRegions
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);

@@ -435,6 +435,15 @@ static __device__ __forceinline__ bool trace_any_image_call(const float4 *__rest
 #ifndef RESTIR_TRACE_MIN_BLOCKS_WIDE
 #define RESTIR_TRACE_MIN_BLOCKS_WIDE 4
 #endif
+// RESTIR_TRACE_GUIDED = g > 0: guided self-scheduling of the wide kernel's work list.  A warp takes g x (items left / warps of the
+// grid) items, at most a chunk, at least RESTIR_TRACE_GUIDED_MIN: with 3-9 chunks per warp and ~0.1 ms per chunk the warps of the
+// fixed-chunk kernel finish up to a chunk apart and the launch ends with its last warp.  0: every fetch is a full chunk.
+#ifndef RESTIR_TRACE_GUIDED
+#define RESTIR_TRACE_GUIDED 0
+#endif
+#ifndef RESTIR_TRACE_GUIDED_MIN
+#define RESTIR_TRACE_GUIDED_MIN 32
+#endif
 template <int MODE, int WALK> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRACE_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams tp) {
 	static_assert(WALK != kWalkWide, "the wide image is walked by trace_wide_kernel");
 	constexpr bool IMAGE = WALK == kWalkImage;
@@ -615,17 +624,31 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 	}
 	__syncwarp();
 	for (;;) {
-		unsigned base = 0;
+		unsigned base = 0, size = (unsigned)CHUNK;
 		if (lane == 0) {
-			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)CHUNK), 0xffffffffull);
+#if RESTIR_TRACE_GUIDED > 0
+			// the end of the work list is handed out in smaller pieces: what a warp takes is its share of what is left (times
+			// RESTIR_TRACE_GUIDED), rounded down to a power of two, between 32 items and the full chunk
+			unsigned long long seen;
+			asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(tp.counters + kCounterWork));
+			const float left = seen < tp.nItems ? (float)(tp.nItems - seen) : 0.0f;
+			const unsigned share = (unsigned)min(left * tp.guidedShare, (float)CHUNK);
+			if (share < (unsigned)CHUNK) {
+				size = max(1u << (31 - __clz((int)max(share, 1u))), (unsigned)RESTIR_TRACE_GUIDED_MIN);
+			}
+#endif
+			base = (unsigned)min(atomicAdd(tp.counters + kCounterWork, (unsigned long long)size), 0xffffffffull);
 		}
 		base = __shfl_sync(full, base, 0);
 		if (base >= tp.nItems) {
 			break;
 		}
+#if RESTIR_TRACE_GUIDED > 0
+		size = __shfl_sync(full, size, 0);
+#endif
 		unsigned valid = 0;
 #pragma unroll 1
-		for (unsigned r = 0; r < (unsigned)CHUNK / 32; ++r) {
+		for (unsigned r = 0; r * 32u < size; ++r) {
 			unsigned local = r * 32u + lane;
 			unsigned answered = 0, cached = 0, aliasOf = 0xffffffffu;
 			unsigned key = item_key<MODE, WALK>(tp, base + local, local, answered, cached, aliasOf);
@@ -760,6 +783,7 @@ template <int MODE, int WALK> static cudaError_t launch_mode(const TraceParams &
 	unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)smCount * blocksPerSm, std::max<unsigned long long>(wanted, 1));
 	TraceParams launch = tp;
 	launch.blocksPerSm = (unsigned)blocksPerSm;
+	launch.guidedShare = (float)RESTIR_TRACE_GUIDED / (float)((unsigned long long)grid * kTraceWarps);
 #if RESTIR_TRACE_AFFINE
 	if (launch.regionCursors == nullptr || launch.smSlots == nullptr || chunks >= 0xffffffffull) {
 		return cudaErrorInvalidValue;

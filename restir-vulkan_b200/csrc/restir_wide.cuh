@@ -17,6 +17,19 @@
 #define RESTIR_WIDE_PREFETCH 0 // experiment: 1 = prefetch the line of the first two children of every visited node into L1, 2 = both lines
 #endif
 
+// RESTIR_WIDE_SAT 1: the [0, 1] clamp of the box test is done by saturating the x axis' multiply-adds (FMA pipe) instead of two
+// min / max per box (ALU pipe); 0: the clamps as separate operations.  Every box the reference's test passes is hit either way.
+#ifndef RESTIR_WIDE_SAT
+#define RESTIR_WIDE_SAT 1
+#endif
+#if RESTIR_WIDE_SAT
+#define WIDE_CLAMP_LO(x) (x)
+#define WIDE_CLAMP_HI(x) (x)
+#else
+#define WIDE_CLAMP_LO(x) fmaxf((x), 0.0f)
+#define WIDE_CLAMP_HI(x) fminf((x), 1.0f)
+#endif
+
 namespace restir {
 
 struct U8 {
@@ -100,6 +113,19 @@ __device__ __forceinline__ void wide_axis_pair(unsigned w0, unsigned w1, unsigne
 #endif
 }
 
+// The same on the axis whose parameters are SATURATED to [0, 1] (wide_image.h wide_box_hit: the clamp of the segment's range,
+// max(entry, 0) <= min(exit, 1), rides on one axis' multiply-adds instead of two min / max per box on the ALU pipe, the busiest
+// unit of this kernel at 61-66 %, ncu capture N; fma.sat has no packed form, so two scalar operations replace each FFMA2).
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+	float r;
+	asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+	return r;
+}
+__device__ __forceinline__ void wide_axis_pair_sat(unsigned w0, unsigned w1, unsigned selN, unsigned selF, float2 s, float2 cLo, float2 cHi, float2 &tn, float2 &tf) {
+	tn = make_float2(fma_sat(__uint_as_float(__byte_perm(w0, 0x3F000000u, selN)), s.x, cLo.x), fma_sat(__uint_as_float(__byte_perm(w1, 0x3F000000u, selN)), s.y, cLo.y));
+	tf = make_float2(fma_sat(__uint_as_float(__byte_perm(w0, 0x3F000000u, selF)), s.x, cHi.x), fma_sat(__uint_as_float(__byte_perm(w1, 0x3F000000u, selF)), s.y, cHi.y));
+}
+
 // (*) of wide_image.h at a leaf: the reference's triangle test, then the reference's slab test on the leaf's own fp32 box
 // (kept in the spare floats of the 64-byte triangle record: e2.z, min.xyz | max.xyz, -)
 __device__ __forceinline__ bool wide_leaf_hit(const float4 *__restrict__ triRec, unsigned id, f3 o, f3 d) {
@@ -160,30 +186,40 @@ __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, co
 		float2 nx, fx, ny, fy, nz, fz;
 		unsigned hits;
 		// slots 0 and 1
+#if RESTIR_WIDE_SAT
+		wide_axis_pair_sat(a.v[0], a.v[1], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+#else
 		wide_axis_pair(a.v[0], a.v[1], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+#endif
 		wide_axis_pair(a.v[4], a.v[5], r.selNy, r.selFy, r.sy, r.cLoY, r.cHiY, ny, fy);
 		wide_axis_pair(b.v[0], b.v[1], r.selNz, r.selFz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
-		// a slot is hit when max(entry, 0) <= min(exit, 1): the sign bit of the difference says "missed" (an exact 0 is +0: hit)
+		// a slot is hit when max(entry, 0) < min(exit, 1) — strictly: the margins leave every box the reference passes a positive
+		// gap (wide_image.h wide_box_hit) — so the sign bit of entry - exit says "hit".  With RESTIR_WIDE_SAT the x parameters arrive
+		// saturated to [0, 1], which is that clamp; a box beyond either end of the segment on x alone collapses onto 1 - 1 or 0 - 0,
+		// an exact +0: missed, as it must be.
 		float2 gap01;
 		{
-			float n0 = fmaxf(fmax3(nx.x, ny.x, nz.x), 0.0f), f0 = fminf(fmin3(fx.x, fy.x, fz.x), 1.0f);
-			float n1 = fmaxf(fmax3(nx.y, ny.y, nz.y), 0.0f), f1 = fminf(fmin3(fx.y, fy.y, fz.y), 1.0f);
-			gap01 = __fadd2_rn(make_float2(f0, f1), make_float2(-n0, -n1));
+			float n0 = WIDE_CLAMP_LO(fmax3(nx.x, ny.x, nz.x)), f0 = WIDE_CLAMP_HI(fmin3(fx.x, fy.x, fz.x));
+			float n1 = WIDE_CLAMP_LO(fmax3(nx.y, ny.y, nz.y)), f1 = WIDE_CLAMP_HI(fmin3(fx.y, fy.y, fz.y));
+			gap01 = __fadd2_rn(make_float2(n0, n1), make_float2(-f0, -f1));
 		}
 		// slots 2 and 3
+#if RESTIR_WIDE_SAT
+		wide_axis_pair_sat(a.v[2], a.v[3], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+#else
 		wide_axis_pair(a.v[2], a.v[3], r.selNx, r.selFx, r.sx, r.cLoX, r.cHiX, nx, fx);
+#endif
 		wide_axis_pair(a.v[6], a.v[7], r.selNy, r.selFy, r.sy, r.cLoY, r.cHiY, ny, fy);
 		wide_axis_pair(b.v[2], b.v[3], r.selNz, r.selFz, r.sz, r.cLoZ, r.cHiZ, nz, fz);
 		{
-			float n0 = fmaxf(fmax3(nx.x, ny.x, nz.x), 0.0f), f0 = fminf(fmin3(fx.x, fy.x, fz.x), 1.0f);
-			float n1 = fmaxf(fmax3(nx.y, ny.y, nz.y), 0.0f), f1 = fminf(fmin3(fx.y, fy.y, fz.y), 1.0f);
-			const float2 gap23 = __fadd2_rn(make_float2(f0, f1), make_float2(-n0, -n1));
+			float n0 = WIDE_CLAMP_LO(fmax3(nx.x, ny.x, nz.x)), f0 = WIDE_CLAMP_HI(fmin3(fx.x, fy.x, fz.x));
+			float n1 = WIDE_CLAMP_LO(fmax3(nx.y, ny.y, nz.y)), f1 = WIDE_CLAMP_HI(fmin3(fx.y, fy.y, fz.y));
+			const float2 gap23 = __fadd2_rn(make_float2(n0, n1), make_float2(-f0, -f1));
 			// the four sign bits, slot 0 in bit 0: each funnel shift appends one
-			unsigned missed = __float_as_uint(gap23.y) >> 31;
-			missed = __funnelshift_l(__float_as_uint(gap23.x), missed, 1);
-			missed = __funnelshift_l(__float_as_uint(gap01.y), missed, 1);
-			missed = __funnelshift_l(__float_as_uint(gap01.x), missed, 1);
-			hits = ~missed & 15u;
+			hits = __float_as_uint(gap23.y) >> 31;
+			hits = __funnelshift_l(__float_as_uint(gap23.x), hits, 1);
+			hits = __funnelshift_l(__float_as_uint(gap01.y), hits, 1);
+			hits = __funnelshift_l(__float_as_uint(gap01.x), hits, 1);
 		}
 		// hit leaves: slots [inner, count), records triBase + (slot - inner); empty slots are never hit (inverted boxes)
 		unsigned leaf = hits >> b.v[6];

@@ -162,15 +162,34 @@ RESTIR_HD float wide_plane_value(uint32_t word, uint32_t sel) {
 #endif
 }
 
-// entry / exit parameters of slot c of node n (conservative: see above)
+// fma.rn.sat.f32: the fused result clamped to [0, 1], NaN -> +0
+RESTIR_HD float wide_fma_sat(float a, float b, float c) {
+	float t = fmaf(a, b, c);
+	return t > 0.0f ? (t < 1.0f ? t : 1.0f) : 0.0f;
+}
+
+// entry / exit parameters of slot c of node n (conservative: see above).  The segment is t in [0, 1]: with exact planes a slot
+// would be hit when N = max(entry_x, entry_y, entry_z, 0) <= F = min(exit_x, exit_y, exit_z, 1).  Two refinements:
+//   * STRICT: hit <=> N < F.  For a box the reference passes (rmin < 1, rmax >= rmin, rmax > 0) every entry parameter here lies
+//     below the reference's and every exit parameter above it by more than 9 u Z > 0 (the margin m = 16 u Z against the 6.2 u Z the
+//     roundings can use up), so exit - entry > 0, exit > 0 and entry < 1, strictly: N < F in all four clamp combinations, and the
+//     difference of two different floats does not round to zero.  Nothing the reference passes sits on N == F.
+//   * SATURATED x: the device kernel gets both clamps for free by saturating the x parameters (fma.rn.sat, restir_wide.cuh):
+//     n' = max(sat(entry_x), entry_y, entry_z), f' = min(sat(exit_x), exit_y, exit_z).  If N < F then entry_x <= N < 1 and
+//     exit_x >= F > 0, so sat(entry_x) = max(entry_x, 0), sat(exit_x) = min(exit_x, 1), n' = N, f' = F: hit.  A box that only the
+//     clamp separates from the segment (beyond its end or behind its origin on x alone) collapses onto n' = f' = 1 or 0: the
+//     strict test says missed, as it should (with <= every such box would be visited: measured, 2.7x the walk time).  In
+//     general entry_x > 1 gives n' >= 1 >= f' and exit_x < 0 gives f' <= 0 <= n', misses like N >= F: n' < f' <=> N < F, the
+//     saturated test visits exactly the boxes the clamped one does.
 RESTIR_HD bool wide_box_hit(const WideNode &n, int c, const WideRay &r) {
 	float tn[3], tf[3];
 	for (int a = 0; a < 3; ++a) {
-		tn[a] = fmaf(wide_plane_value(n.q[a][c], r.selNear[a]), r.s[a], r.cLo[a]);
-		tf[a] = fmaf(wide_plane_value(n.q[a][c], r.selFar[a]), r.s[a], r.cHi[a]);
+		const float vn = wide_plane_value(n.q[a][c], r.selNear[a]), vf = wide_plane_value(n.q[a][c], r.selFar[a]);
+		tn[a] = a == 0 ? wide_fma_sat(vn, r.s[a], r.cLo[a]) : fmaf(vn, r.s[a], r.cLo[a]);
+		tf[a] = a == 0 ? wide_fma_sat(vf, r.s[a], r.cHi[a]) : fmaf(vf, r.s[a], r.cHi[a]);
 	}
 	float nearT = fmaxf(tn[0], fmaxf(tn[1], tn[2])), farT = fminf(tf[0], fminf(tf[1], tf[2]));
-	return nearT <= farT && nearT <= 1.0f && farT >= 0.0f;
+	return nearT - farT < 0.0f; // the kernel reads the sign bit of this difference
 }
 
 } // namespace restir
