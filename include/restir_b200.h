@@ -226,7 +226,7 @@ typedef struct restir_bvh_info {
 } restir_bvh_info;
 int restir_get_bvh_info(const restir_context *ctx, restir_bvh_info *out);
 /* Inspection (tests, tools): the 4-wide image the context walks — n_wide nodes of 64 bytes (csrc/wide_image.h WideNode: 12 words
- * of quantised planes, first child, first triangle record, inner count, slot count) and, per triangle record, the index of the
+ * of quantised planes, first child << 4, first triangle record - inner count, mask of the inner slots, slot count) and, per triangle record, the index of the
  * uploaded triangle it holds.  Either pointer may be NULL.  RESTIR_E_UNSUPPORTED when the tree is not walked wide.  The image of
  * a tree built by restir_build_bvh_device equals, byte for byte, the image restir_upload_bvh derives from the same nodes. */
 int restir_get_wide_image(restir_context *ctx, void *wide_nodes, uint32_t capacity, uint32_t *n_wide, uint32_t *tri_order);

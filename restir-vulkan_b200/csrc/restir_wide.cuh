@@ -30,6 +30,15 @@
 #define WIDE_CLAMP_HI(x) fminf((x), 1.0f)
 #endif
 
+// RESTIR_WIDE_FLAT_LOOP 1 (experiment): one loop branch per visit, the next group settled by predicated moves at the end of a
+// visit.  Measured (profiles/r2_p_flat.log): neighbours 0.879 -> 0.887 ms — the predicates cost four more ALU-pipe operations than
+// the convergence barriers and branches they replace, and the ALU pipe is what the walk is short of.
+#ifndef RESTIR_WIDE_FLAT_LOOP
+#define RESTIR_WIDE_FLAT_LOOP 0
+#endif
+// Also measured and removed (profiles/r2_p_imad.log): the four hit bits gathered on the FMA pipe (IMAD.HI by 2 = the sign bit, three
+// IMADs to combine) instead of four funnel shifts on the ALU pipe: neighbours 0.878 -> 0.900 ms (IMAD.HI is not a one-pass operation).
+
 namespace restir {
 
 struct U8 {
@@ -157,6 +166,18 @@ __device__ __forceinline__ bool wide_ray_in_range(const WideGrid &g, f3 o, f3 d)
 // tested (1.7 times per ray): six registers less across the walk.
 __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, const float4 *__restrict__ triRec, const WideLaneRay &r, const float *od,
                                               int stride) {
+#if RESTIR_WIDE_FLAT_LOOP
+	// One loop branch per visit: the group to visit next is settled at the END of a visit with predicated moves (push the siblings
+	// left over, take the hit inner children, or pop), and an empty group at the bottom of the stack ends the walk — no nested
+	// `if (empty) { if (top == 0) return; pop }` with its convergence barrier and two branches at the head of every visit.
+	unsigned stack[kWideStack + 1];
+	stack[0] = 0u; // the sentinel: popping it leaves an empty group
+	int top = 1;
+	int found = -1;
+	unsigned group = 1u; // node 0, one child to visit: the root
+	do {
+		const unsigned slot = (unsigned)__ffs((int)(group & 15u)) - 1u;
+#else
 	unsigned stack[kWideStack];
 	int top = 0;
 	unsigned group = 1u; // node 0, one child to visit: the root
@@ -168,16 +189,17 @@ __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, co
 			group = stack[--top];
 		}
 		const unsigned slot = (unsigned)__ffs((int)(group & 15u)) - 1u;
+#endif
 		group &= group - 1u; // the lowest set bit lies in the mask
 		const uint4 *n = wide + ((size_t)((group >> 4) + slot)) * 4u;
-		const U8 a = ldg256u(n), b = ldg256u(n + 2); // a: x words of the four slots, y words; b: z words, (childBase, triBase, inner, count)
+		const U8 a = ldg256u(n), b = ldg256u(n + 2); // a: x words of the four slots, y words; b: z words, (childGroup, recBase, innerMask, count)
 #if RESTIR_WIDE_PREFETCH > 0
 		// the children of a node are consecutive 64-byte nodes (two per 128-byte line): ask for them while the boxes are tested
 		if (b.v[6] != 0u) {
-			const uint4 *c = wide + (size_t)b.v[4] * 4u;
+			const uint4 *c = wide + (size_t)(b.v[4] >> 4) * 4u;
 			asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
 #if RESTIR_WIDE_PREFETCH > 1
-			if (b.v[6] > 2u) {
+			if (b.v[6] > 3u) {
 				asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 8));
 			}
 #endif
@@ -221,8 +243,8 @@ __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, co
 			hits = __funnelshift_l(__float_as_uint(gap01.y), hits, 1);
 			hits = __funnelshift_l(__float_as_uint(gap01.x), hits, 1);
 		}
-		// hit leaves: slots [inner, count), records triBase + (slot - inner); empty slots are never hit (inverted boxes)
-		unsigned leaf = hits >> b.v[6];
+		// hit leaves: the slots outside innerMask, the record of slot j is recBase + j; empty slots are never hit (inverted boxes)
+		unsigned leaf = hits & ~b.v[6];
 		if (leaf != 0u) {
 			const f3 o = mk3(od[0], od[stride], od[2 * stride]), d = mk3(od[3 * stride], od[4 * stride], od[5 * stride]);
 			const unsigned triBase = b.v[5];
@@ -231,19 +253,44 @@ __device__ __forceinline__ int trace_any_wide(const uint4 *__restrict__ wide, co
 				const unsigned j = (unsigned)__ffs((int)leaf) - 1u;
 				leaf &= leaf - 1u;
 				if (wide_leaf_hit(triRec, triBase + j, o, d)) {
+#if RESTIR_WIDE_FLAT_LOOP
+					found = (int)(triBase + j);
+					break;
+#else
 					return (int)(triBase + j);
+#endif
 				}
 			} while (leaf != 0u);
+#if RESTIR_WIDE_FLAT_LOOP
+			if (found >= 0) {
+				break;
+			}
+#endif
 		}
-		// hit inner children: slots [0, inner), nodes childBase + slot
-		const unsigned inner = hits & ~(0xffffffffu << b.v[6]);
+		// hit inner children: the slots of innerMask, nodes firstChild + slot
+		const unsigned inner = hits & b.v[6];
+#if RESTIR_WIDE_FLAT_LOOP
+		const bool has = inner != 0u, siblings = (group & 15u) != 0u;
+		if (has && siblings) {
+			stack[top] = group;
+		}
+		top += has && siblings ? 1 : 0;
+		if (!has && !siblings) {
+			group = stack[top - 1];
+		}
+		top -= !has && !siblings ? 1 : 0;
+		group = has ? (b.v[4] | inner) : group;
+	} while ((group & 15u) != 0u);
+	return found;
+#else
 		if (inner != 0u) {
 			if ((group & 15u) != 0u) {
 				stack[top++] = group;
 			}
-			group = (b.v[4] << 4) | inner;
+			group = b.v[4] | inner;
 		}
 	}
+#endif
 }
 
 } // namespace restir

@@ -105,8 +105,8 @@ __global__ void wide_expand_kernel(const restir_aabb_node *__restrict__ nodes, c
 		}
 	}
 	WideNode out;
-	out.childBase = out.triBase = 0; // wide_link_kernel
-	out.inner = (unsigned)inner;
+	out.childGroup = out.recBase = 0; // wide_link_kernel
+	out.innerMask = (1u << inner) - 1u;
 	out.count = (unsigned)n;
 	bool ok = true;
 #pragma unroll
@@ -143,9 +143,9 @@ __global__ void wide_link_kernel(const restir_aabb_node *__restrict__ nodes, uns
 	}
 	const unsigned w = begin + i;
 	const unsigned childBase = begin + count + innerScan[i], triBase = triTotal + leafScan[i];
-	const unsigned inner = wide[w].inner, n = wide[w].count;
-	wide[w].childBase = childBase;
-	wide[w].triBase = triBase;
+	const unsigned inner = (unsigned)__popc(wide[w].innerMask), n = wide[w].count;
+	wide[w].childGroup = childBase << 4;
+	wide[w].recBase = triBase - inner;
 	for (unsigned c = 0; c < n; ++c) {
 		const int2 ref = slotRef[(size_t)w * 4 + c];
 		if (c < inner) {

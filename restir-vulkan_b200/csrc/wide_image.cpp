@@ -186,9 +186,11 @@ bool build_wide_image(const restir_aabb_node *nodes, uint32_t nNodes, uint32_t n
 		// inner children first (the order of the slots is free: the answer is any-hit), each group in the tree's own order
 		std::stable_partition(s, s + count, [](const Slot &x) { return x.ref >= 0; });
 		WideNode n;
-		n.childBase = (uint32_t)binaryOf.size();
-		n.triBase = (uint32_t)triOrder.size();
-		n.inner = 0;
+		const uint32_t firstChild = (uint32_t)binaryOf.size(), firstRecord = (uint32_t)triOrder.size();
+		uint32_t inner = 0;
+		if (binaryOf.size() >= (1u << 28)) {
+			return refuse("more wide nodes than a group word can name");
+		}
 		n.count = (uint32_t)count;
 		for (int c = 0; c < 4; ++c) {
 			if (c >= count) {
@@ -203,7 +205,7 @@ bool build_wide_image(const restir_aabb_node *nodes, uint32_t nNodes, uint32_t n
 				}
 			}
 			if (s[c].ref >= 0) {
-				++n.inner;
+				++inner;
 				binaryOf.push_back(s[c].ref);
 				depthOf.push_back(depthOf[w] + 1);
 			} else {
@@ -216,6 +218,9 @@ bool build_wide_image(const restir_aabb_node *nodes, uint32_t nNodes, uint32_t n
 				}
 			}
 		}
+		n.childGroup = firstChild << 4;
+		n.recBase = firstRecord - inner;
+		n.innerMask = (1u << inner) - 1u;
 		info.depth = std::max(info.depth, depthOf[w] + 1);
 		out.push_back(n);
 	}
@@ -328,15 +333,15 @@ bool wide_walk_host(const restir_aabb_node *nodes, uint32_t nNodes, const restir
 			for (int c = 0; c < 4; ++c) {
 				if (wide_box_hit(nd, c, wr)) hits |= 1u << c;
 			}
-			for (unsigned lf = hits >> nd.inner; lf != 0u && !hit; lf &= lf - 1u) {
-				uint32_t rec = nd.triBase + (unsigned)__builtin_ctz(lf);
+			for (unsigned lf = hits & ~nd.innerMask; lf != 0u && !hit; lf &= lf - 1u) {
+				uint32_t rec = nd.recBase + (unsigned)__builtin_ctz(lf);
 				hit = host_triangle(tris[order[rec]], o, d) && host_box(o, inv, &leaf[(size_t)rec * 6], &leaf[(size_t)rec * 6 + 3]);
 			}
 			if (hit) break;
-			unsigned inner = hits & ~(0xffffffffu << nd.inner);
+			unsigned inner = hits & nd.innerMask;
 			if (inner != 0u) {
 				if ((group & 15u) != 0u) stack[top++] = group;
-				group = (nd.childBase << 4) | inner;
+				group = nd.childGroup | inner;
 			}
 		}
 		shadowed[i] = hit ? 1 : 0;

@@ -49,16 +49,21 @@ namespace restir {
 
 constexpr int kWideStack = 32; // entries of the walk's stack = levels of the wide tree (one entry per level: the pending siblings); deeper trees are not walked wide
 
-// Slots [0, inner) are inner children: wide nodes childBase + slot (the children of a node are numbered consecutively).  Slots
-// [inner, count) are leaves: triangle RECORDS triBase + (slot - inner) — the 64-byte (p1, e1, e2 | leaf box) records are laid
+// Slots [0, inner) are inner children: wide nodes firstChild + slot (the children of a node are numbered consecutively).  Slots
+// [inner, count) are leaves: triangle RECORDS firstRecord + (slot - inner) — the 64-byte (p1, e1, e2 | leaf box) records are laid
 // out in the order the wide leaves name them (triOrder), so neither kind of child needs an index word.  Slots >= count are
-// empty: lo = 32767, hi = 0 on every axis, an inverted box that no ray hits.
+// empty: lo = 32767, hi = 0 on every axis, an inverted box that no ray hits.  The four words after the planes hold these
+// numbers in the form the walk consumes them (one operation less each on the ALU pipe, the unit the walk is short of):
 struct alignas(64) WideNode {
-	uint32_t q[3][4];  // [axis][slot]: lo (15 bits) | hi (15 bits) << 16, grid cells
-	uint32_t childBase, triBase;
-	uint32_t inner;    // number of inner children, 0..4
-	uint32_t count;    // number of used slots, 2..4
+	uint32_t q[3][4];    // [axis][slot]: lo (15 bits) | hi (15 bits) << 16, grid cells
+	uint32_t childGroup; // firstChild << 4: or-ed with the mask of the hit inner slots it IS the walk's next group
+	uint32_t recBase;    // firstRecord - inner (mod 2^32): the record of leaf SLOT j is recBase + j
+	uint32_t innerMask;  // (1 << inner) - 1: the inner slots
+	uint32_t count;      // number of used slots, 2..4
 };
+RESTIR_HD uint32_t wide_inner_count(const WideNode &n) {
+	return n.innerMask == 0u ? 0u : n.innerMask == 1u ? 1u : n.innerMask == 3u ? 2u : n.innerMask == 7u ? 3u : 4u;
+}
 static_assert(sizeof(WideNode) == 64, "wide node is 64 bytes");
 
 // plane coordinate of grid value q on axis a:  h[a] + (0.5 + q / 65536) * K[a]   (K a power of two, h a float: all exact)
