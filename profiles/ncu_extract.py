@@ -18,6 +18,10 @@ METRICS = [
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    # which execution pipe the issued instructions go to (round 2, capture P: the walk is short of the ALU pipe)
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
 ]
 # display names of the trace kernel's launches, in launch order within a frame (restir_capi.cu)
 TRACE_ORDER = ["trace_kernel<pixel>", "trace_kernel<own>", "trace_kernel<neighbours>"]
