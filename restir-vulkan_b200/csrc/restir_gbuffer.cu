@@ -61,7 +61,7 @@ __device__ __forceinline__ F4 sample_texture(const GBufferScene &g, int index, b
 	uchar4 c01 = __ldg(t + (size_t)y1 * W + x0), c11 = __ldg(t + (size_t)y1 * W + x1);
 	float bx = 1.0f - ax, by = 1.0f - ay;
 #define RESTIR_BILERP(ch) \
-	(((float)c00.ch / 255.0f * bx + (float)c10.ch / 255.0f * ax) * by + ((float)c01.ch / 255.0f * bx + (float)c11.ch / 255.0f * ax) * ay)
+	((div_unorm8((float)c00.ch) * bx + div_unorm8((float)c10.ch) * ax) * by + (div_unorm8((float)c01.ch) * bx + div_unorm8((float)c11.ch) * ax) * ay)
 	F4 r{RESTIR_BILERP(x), RESTIR_BILERP(y), RESTIR_BILERP(z), RESTIR_BILERP(w)};
 #undef RESTIR_BILERP
 	return r;

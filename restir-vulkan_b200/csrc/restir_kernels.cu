@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 2) spatial_reuse_staged_kernel(PassP
 			const int st = (ny - y0) * kStageW + (nx - x0);
 			float nDepth = sDepth[st];
 			short4 nq = sNormal[st];
-			f3 nNor = mk3(fmaxf((float)nq.x / 32767.0f, -1.0f), fmaxf((float)nq.y / 32767.0f, -1.0f), fmaxf((float)nq.z / 32767.0f, -1.0f));
+			f3 nNor = mk3(fmaxf(div_snorm16((float)nq.x), -1.0f), fmaxf(div_snorm16((float)nq.y), -1.0f), fmaxf(div_snorm16((float)nq.z), -1.0f));
 			if (fabsf(nDepth - worldDepth) > p.u.spatialPosThreshold * fabsf(worldDepth) || dot3(nNor, normal) < cosThr) { // :65-70
 				continue;
 			}

@@ -35,7 +35,7 @@ __device__ __forceinline__ f3 fetch_albedo(const GBufferView &g, const float *lu
 		return mk3(0.0f, 0.0f, 0.0f);
 	}
 	uchar4 c = __ldg(g.albedo + i);
-	if (alpha) *alpha = (float)c.w / 255.0f;
+	if (alpha) *alpha = div_unorm8((float)c.w);
 	return mk3(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z));
 }
 __device__ __forceinline__ f3 fetch_normal(const GBufferView &g, size_t i) {
@@ -43,12 +43,12 @@ __device__ __forceinline__ f3 fetch_normal(const GBufferView &g, size_t i) {
 		return mk3(0.0f, 0.0f, 0.0f);
 	}
 	short4 n = __ldg(g.normal + i);
-	return mk3(fmaxf((float)n.x / 32767.0f, -1.0f), fmaxf((float)n.y / 32767.0f, -1.0f), fmaxf((float)n.z / 32767.0f, -1.0f));
+	return mk3(fmaxf(div_snorm16((float)n.x), -1.0f), fmaxf(div_snorm16((float)n.y), -1.0f), fmaxf(div_snorm16((float)n.z), -1.0f));
 }
 __device__ __forceinline__ void fetch_material(const GBufferView &g, size_t i, float &roughness, float &metallic) {
 	ushort2 m = __ldg(g.material + i);
-	roughness = (float)m.x / 65535.0f;
-	metallic = (float)m.y / 65535.0f;
+	roughness = div_unorm16((float)m.x);
+	metallic = div_unorm16((float)m.y);
 }
 __device__ __forceinline__ f3 fetch_world_pos(const GBufferView &g, size_t i) {
 	if (g.worldPos == nullptr) {

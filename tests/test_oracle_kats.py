@@ -66,3 +66,16 @@ def test_phat_closed_form_head_on():
     # behind the surface => 0 (restirUtils.glsl:8-10)
     args[0, 4] = -2
     assert po.evaluate_phat(args, alb, lum, rough, metal)[0] == 0.0
+
+
+def test_normalisation_divisions_without_the_divider(tmp_path):
+    """csrc/restir_pixel.cuh decodes SNORM16 / UNORM16 / UNORM8 texels as q = x c, q + (x - D q) c instead of x / D (a zero numerator
+    takes the divider's slow path, and G-buffers are full of zeros): tools/const_div_check.c compares the sequence with the division
+    for every integer the three formats hold."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "const_div_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(root, "tools", "const_div_check.c"), "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["0", "0", "0"], out.stdout
