@@ -1189,6 +1189,7 @@ int restir_pass_gbuffer(restir_context *ctx, int slot, const restir_camera *came
 	g.texels = ctx->gbTexels;
 	g.textureTable = ctx->gbTextureTable;
 	g.srgbThresholds = ctx->gbSrgbThresholds;
+	g.recordTri = ctx->wideOrder;
 	g.nMaterials = ctx->gbMaterials;
 	g.nTextures = ctx->gbTextures;
 	Band full = ctx->band; // every row the context holds: the reuse passes gather from the halo rows

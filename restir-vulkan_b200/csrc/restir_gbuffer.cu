@@ -11,6 +11,7 @@
 // repeat wrap, bilinear at level 0 (the reference's samplers add a mip chain and 16x anisotropy, which a driver defines).
 // Arithmetic policy as everywhere (restir_math.cuh, -fmad=false); the oracle twin is oracle_gbuffer_pass.
 #include "restir_kernels.h"
+#include "restir_trace.cuh" // ldg256: one 32-byte load
 
 namespace restir {
 
@@ -140,6 +141,7 @@ __global__ void vertex_stage_kernel(const restir_vertex *__restrict__ vertices, 
 	o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+template <bool IMAGE>
 __global__ void __launch_bounds__(kThreads) gbuffer_kernel(SceneView sc, GBufferScene g, Band band, RaycastCamera cam, float zNear, float zFar,
                                                           uchar4 *albedoOut, short4 *normalOut, ushort2 *materialOut, float4 *worldPosOut,
                                                           float *depthOut) {
@@ -161,83 +163,141 @@ __global__ void __launch_bounds__(kThreads) gbuffer_kernel(SceneView sc, GBuffer
 	// Closest hit = the depth test LESS over all fragments of the pixel.  The walk visits the nearer child first (slab entry
 	// parameter; ties: left first) so that `best` shrinks early and the farther subtrees are pruned by `rmin <= best`; the oracle
 	// twin walks in the same order (the pruning makes the result order-dependent in the last bit of near-ties).
+	// One candidate triangle: back-face culling, Moller-Trumbore, the near / far planes, the depth test with its tie rule, the mask.
+	auto consider = [&](int ti, f3 p1, f3 e1, f3 e2) {
+		if (!(dot3(cross3(e1, e2), dir) < 0.0f)) { // back-face culling, CCW front (pass.h:24-32)
+			return;
+		}
+		f3 pv = cross3(dir, e2);
+		float fdet = 1.0f / dot3(e1, pv);
+		f3 sv = pos - p1;
+		float u_ = fdet * dot3(sv, pv);
+		if (u_ < 0.0f || u_ > 1.0f) {
+			return;
+		}
+		f3 q = cross3(sv, e1);
+		float v_ = fdet * dot3(dir, q);
+		if (v_ < 0.0f || v_ + u_ > 1.0f) {
+			return;
+		}
+		float tt = fdet * dot3(e2, q);
+		// the view-space depth of the hit is tt (dir . fwd = 1): near and far planes clip like the rasteriser's
+		if (!(tt >= zNear && tt <= zFar) || !(tt < best || (tt == best && ti < bestTri))) {
+			return;
+		}
+		int mi = __ldg(g.triMaterial + ti);
+		if ((unsigned)mi < (unsigned)g.nMaterials && __ldg(&g.uniforms[mi].alphaMode) == RESTIR_ALPHA_MODE_MASK) { // gBuffer.frag:29-34
+			const float4 *at = g.attrs + (size_t)ti * 8;
+			float4 n0 = __ldg(at), n1 = __ldg(at + 2), n2 = __ldg(at + 4), vv = __ldg(at + 6);
+			float w0 = (1.0f - u_) - v_;
+			float uu = (n0.w * w0 + n1.w * u_) + n2.w * v_, vw = (vv.x * w0 + vv.y * u_) + vv.z * v_;
+			float alpha = sample_texture(g, __ldg(&g.bindings[mi].albedo), false, uu, vw).w * __ldg(&g.uniforms[mi].colorParam[3]);
+			if (alpha < __ldg(&g.uniforms[mi].alphaCutoff)) {
+				return;
+			}
+		}
+		best = tt;
+		bestTri = ti;
+		bu = u_;
+		bv = v_;
+	};
 	int stack[64];
 	int top = 1;
 	stack[0] = 0;
-	while (top > 0) {
-		const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
-		float4 ch = __ldg(n + 4);
-		int child[2] = {__float_as_int(ch.x), __float_as_int(ch.y)};
-		float rminOf[2];
-		bool hitBox[2];
+	if (IMAGE) {
+		// The same walk — same boxes, same children, same order, same operations — over the 64-byte image of the tree and the 64-byte
+		// (p1, e1, e2) triangle records the shadow rays use (traversal_image.h, restir_trace.cuh): two 32-byte loads per node instead of
+		// five 16-byte ones from an 80-byte stride, both boxes per packed FADD2 / FMUL2 (each half an IEEE operation: b + (-o) IS
+		// b - o), one 32-byte + one 4-byte load per triangle with the edges already subtracted.  With the 4-wide image in use the
+		// leaves of the binary image name triangle RECORDS; recordTri gives the triangle back (attributes, material, tie rule).
+		const float2 nox = make_float2(-pos.x, -pos.x), noy = make_float2(-pos.y, -pos.y), noz = make_float2(-pos.z, -pos.z);
+		const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+		while (top > 0) {
+			const float4 *n = sc.image + (size_t)(unsigned)stack[--top] * 4u;
+			const F8 lo = ldg256(n), hi = ldg256(n + 2); // (Lmin, Rmin, Lmax, Rmax) for x, for y | for z, (left, right, -, -)
+			const int child[2] = {__float_as_int(hi.v[4]), __float_as_int(hi.v[5])};
+			const float2 t1x = __fmul2_rn(__fadd2_rn(make_float2(lo.v[0], lo.v[1]), nox), ivx), t2x = __fmul2_rn(__fadd2_rn(make_float2(lo.v[2], lo.v[3]), nox), ivx);
+			const float2 t1y = __fmul2_rn(__fadd2_rn(make_float2(lo.v[4], lo.v[5]), noy), ivy), t2y = __fmul2_rn(__fadd2_rn(make_float2(lo.v[6], lo.v[7]), noy), ivy);
+			const float2 t1z = __fmul2_rn(__fadd2_rn(make_float2(hi.v[0], hi.v[1]), noz), ivz), t2z = __fmul2_rn(__fadd2_rn(make_float2(hi.v[2], hi.v[3]), noz), ivz);
+			float rminOf[2];
+			bool hitBox[2];
+			{
+				const float rmin = fmaxf(fminf(t1x.x, t2x.x), fmaxf(fminf(t1y.x, t2y.x), fminf(t1z.x, t2z.x)));
+				const float rmax = fminf(fmaxf(t1x.x, t2x.x), fminf(fmaxf(t1y.x, t2y.x), fmaxf(t1z.x, t2z.x)));
+				rminOf[0] = rmin;
+				hitBox[0] = rmin <= best && rmax >= rmin && rmax > 0.0f;
+			}
+			{
+				const float rmin = fmaxf(fminf(t1x.y, t2x.y), fmaxf(fminf(t1y.y, t2y.y), fminf(t1z.y, t2z.y)));
+				const float rmax = fminf(fmaxf(t1x.y, t2x.y), fminf(fmaxf(t1y.y, t2y.y), fmaxf(t1z.y, t2z.y)));
+				rminOf[1] = rmin;
+				hitBox[1] = rmin <= best && rmax >= rmin && rmax > 0.0f;
+			}
 #pragma unroll
-		for (int side = 0; side < 2; ++side) {
-			float4 bmin = __ldg(n + side * 2), bmax = __ldg(n + side * 2 + 1);
-			float t1x = (bmin.x - pos.x) * inv.x, t1y = (bmin.y - pos.y) * inv.y, t1z = (bmin.z - pos.z) * inv.z;
-			float t2x = (bmax.x - pos.x) * inv.x, t2y = (bmax.y - pos.y) * inv.y, t2z = (bmax.z - pos.z) * inv.z;
-			float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
-			float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
-			rminOf[side] = rmin;
-			hitBox[side] = rmin <= best && rmax >= rmin && rmax > 0.0f;
-		}
-		// leaves first (left, then right), then the inner children: the farther one is pushed first, so the nearer one is popped first
-#pragma unroll
-		for (int side = 0; side < 2; ++side) {
-			if (!hitBox[side] || child[side] >= 0) {
-				continue;
-			}
-			int ti = ~child[side];
-			const float4 *t = sc.tris + (size_t)ti * 3;
-			float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
-			f3 p1 = mk3(a.x, a.y, a.z);
-			f3 e1 = mk3(b.x, b.y, b.z) - p1;
-			f3 e2 = mk3(c.x, c.y, c.z) - p1;
-			if (!(dot3(cross3(e1, e2), dir) < 0.0f)) { // back-face culling, CCW front (pass.h:24-32)
-				continue;
-			}
-			f3 pv = cross3(dir, e2);
-			float fdet = 1.0f / dot3(e1, pv);
-			f3 sv = pos - p1;
-			float u_ = fdet * dot3(sv, pv);
-			if (u_ < 0.0f || u_ > 1.0f) {
-				continue;
-			}
-			f3 q = cross3(sv, e1);
-			float v_ = fdet * dot3(dir, q);
-			if (v_ < 0.0f || v_ + u_ > 1.0f) {
-				continue;
-			}
-			float tt = fdet * dot3(e2, q);
-			// the view-space depth of the hit is tt (dir . fwd = 1): near and far planes clip like the rasteriser's
-			if (!(tt >= zNear && tt <= zFar) || !(tt < best || (tt == best && ti < bestTri))) {
-				continue;
-			}
-			int mi = __ldg(g.triMaterial + ti);
-			if ((unsigned)mi < (unsigned)g.nMaterials && __ldg(&g.uniforms[mi].alphaMode) == RESTIR_ALPHA_MODE_MASK) { // gBuffer.frag:29-34
-				const float4 *at = g.attrs + (size_t)ti * 8;
-				float4 n0 = __ldg(at), n1 = __ldg(at + 2), n2 = __ldg(at + 4), vv = __ldg(at + 6);
-				float w0 = (1.0f - u_) - v_;
-				float uu = (n0.w * w0 + n1.w * u_) + n2.w * v_, vw = (vv.x * w0 + vv.y * u_) + vv.z * v_;
-				float alpha = sample_texture(g, __ldg(&g.bindings[mi].albedo), false, uu, vw).w * __ldg(&g.uniforms[mi].colorParam[3]);
-				if (alpha < __ldg(&g.uniforms[mi].alphaCutoff)) {
+			for (int side = 0; side < 2; ++side) {
+				if (!hitBox[side] || child[side] >= 0) {
 					continue;
 				}
+				const int rec = ~child[side];
+				const float4 *t = sc.triEdges + (size_t)rec * 4;
+				const F8 a = ldg256(t);
+				const float e2z = __ldg(reinterpret_cast<const float *>(t + 2));
+				const int ti = g.recordTri != nullptr ? (int)__ldg(g.recordTri + rec) : rec;
+				consider(ti, mk3(a.v[0], a.v[1], a.v[2]), mk3(a.v[3], a.v[4], a.v[5]), mk3(a.v[6], a.v[7], e2z));
 			}
-			best = tt;
-			bestTri = ti;
-			bu = u_;
-			bv = v_;
+			const bool il = hitBox[0] && child[0] >= 0, ir = hitBox[1] && child[1] >= 0;
+			if (il && ir) {
+				const bool leftNear = rminOf[0] <= rminOf[1];
+				if (top < 63) {
+					stack[top++] = leftNear ? child[1] : child[0];
+					stack[top++] = leftNear ? child[0] : child[1];
+				}
+			} else if (il || ir) {
+				if (top < 64) {
+					stack[top++] = il ? child[0] : child[1];
+				}
+			}
 		}
-		const bool il = hitBox[0] && child[0] >= 0, ir = hitBox[1] && child[1] >= 0;
-		if (il && ir) {
-			const bool leftNear = rminOf[0] <= rminOf[1];
-			if (top < 63) {
-				stack[top++] = leftNear ? child[1] : child[0];
-				stack[top++] = leftNear ? child[0] : child[1];
+	} else {
+		while (top > 0) {
+			const float4 *n = sc.nodes + (size_t)stack[--top] * 5;
+			float4 ch = __ldg(n + 4);
+			int child[2] = {__float_as_int(ch.x), __float_as_int(ch.y)};
+			float rminOf[2];
+			bool hitBox[2];
+#pragma unroll
+			for (int side = 0; side < 2; ++side) {
+				float4 bmin = __ldg(n + side * 2), bmax = __ldg(n + side * 2 + 1);
+				float t1x = (bmin.x - pos.x) * inv.x, t1y = (bmin.y - pos.y) * inv.y, t1z = (bmin.z - pos.z) * inv.z;
+				float t2x = (bmax.x - pos.x) * inv.x, t2y = (bmax.y - pos.y) * inv.y, t2z = (bmax.z - pos.z) * inv.z;
+				float rmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+				float rmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+				rminOf[side] = rmin;
+				hitBox[side] = rmin <= best && rmax >= rmin && rmax > 0.0f;
 			}
-		} else if (il || ir) {
-			if (top < 64) {
-				stack[top++] = il ? child[0] : child[1];
+			// leaves first (left, then right), then the inner children: the farther one is pushed first, so the nearer one is popped first
+#pragma unroll
+			for (int side = 0; side < 2; ++side) {
+				if (!hitBox[side] || child[side] >= 0) {
+					continue;
+				}
+				int ti = ~child[side];
+				const float4 *t = sc.tris + (size_t)ti * 3;
+				float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+				f3 p1 = mk3(a.x, a.y, a.z);
+				consider(ti, p1, mk3(b.x, b.y, b.z) - p1, mk3(c.x, c.y, c.z) - p1);
+			}
+			const bool il = hitBox[0] && child[0] >= 0, ir = hitBox[1] && child[1] >= 0;
+			if (il && ir) {
+				const bool leftNear = rminOf[0] <= rminOf[1];
+				if (top < 63) {
+					stack[top++] = leftNear ? child[1] : child[0];
+					stack[top++] = leftNear ? child[0] : child[1];
+				}
+			} else if (il || ir) {
+				if (top < 64) {
+					stack[top++] = il ? child[0] : child[1];
+				}
 			}
 		}
 	}
@@ -317,14 +377,20 @@ void launch_vertex_stage(const restir_vertex *vertices, const uint32_t *indices,
 void launch_gbuffer(const SceneView &sc, const GBufferScene &g, const Band &band, const RaycastCamera &cam, float zNear, float zFar, void *albedo,
                     void *normal, void *material, void *worldPos, void *depth, cudaStream_t s) {
 	dim3 grid((unsigned)((band.W + 31) / 32), (unsigned)((band.rowEnd - band.rowBegin + 7) / 8), 1);
-	gbuffer_kernel<<<grid, kThreads, 0, s>>>(sc, g, band, cam, zNear, zFar, (uchar4 *)albedo, (short4 *)normal, (ushort2 *)material,
-	                                         (float4 *)worldPos, (float *)depth);
+	if (sc.image != nullptr && sc.triEdges != nullptr) {
+		gbuffer_kernel<true><<<grid, kThreads, 0, s>>>(sc, g, band, cam, zNear, zFar, (uchar4 *)albedo, (short4 *)normal, (ushort2 *)material,
+		                                               (float4 *)worldPos, (float *)depth);
+	} else {
+		gbuffer_kernel<false><<<grid, kThreads, 0, s>>>(sc, g, band, cam, zNear, zFar, (uchar4 *)albedo, (short4 *)normal, (ushort2 *)material,
+		                                                (float4 *)worldPos, (float *)depth);
+	}
 }
 
 cudaError_t preload_gbuffer_kernels() {
 	cudaFuncAttributes a;
 	cudaError_t e = cudaFuncGetAttributes(&a, vertex_stage_kernel);
-	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gbuffer_kernel);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gbuffer_kernel<true>);
+	if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gbuffer_kernel<false>);
 	return e;
 }
 

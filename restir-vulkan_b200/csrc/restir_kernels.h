@@ -110,6 +110,7 @@ struct GBufferScene {
 	const uchar4 *texels;                      // every texture's level 0, back to back
 	const uint4 *textureTable;                 // per texture: (first texel, width, height, -)
 	const float *srgbThresholds;               // 256 floats: the smallest value that encodes to each 8-bit sRGB code
+	const uint32_t *recordTri;                 // with the 4-wide image in use the binary image's leaves name triangle RECORDS: record -> triangle; null: identity
 	int nMaterials, nTextures;
 };
 void launch_vertex_stage(const restir_vertex *vertices, const uint32_t *indices, const restir_draw *draws, const restir_model_matrices *matrices,
