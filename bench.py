@@ -643,8 +643,9 @@ def run_gpu_config(env, name, scaling, steps, warmup, full):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top], "kernel_ms": top_ms,
                 "launches_per_frame": kernel_launches[top],
                 "issue_frac": issue_frac.get(top),
-                "note": "the trace kernel is bound by instruction issue (65-68 % of the slots at 4 CTAs / SM and 13-23 of 32 lanes, ncu capture M), "
-                        "not by HBM: the 4-wide image and the triangle records (25 MB) are L2/L1-resident and DRAM sits below 3 % (profiles/); "
+                "note": "the trace kernel is bound by instruction issue and by the ALU pipe (66-71 % of the issue slots, ALU pipe 47-61 % against 22 % "
+                        "for the FMA pipe, at 4 CTAs / SM and 12-23 of 32 lanes, ncu captures P / Q), "
+                        "not by HBM: the 4-wide image and the triangle records (25 MB) are L2/L1-resident and DRAM sits below 5 % (profiles/); "
                         "its yardsticks are Mrays/s and lanes per instruction; the streaming kernels' "
                         "HBM fractions are in kernel_hbm_frac; issue_frac / kernel_issue_frac = warp instructions per launch "
                         "(profiles/traffic.json, from the ncu capture) over this run's kernel time and the SMs' issue rate (N = 1 only)"}
