@@ -200,7 +200,8 @@ int restir_set_unbiased_neighbors(restir_context *ctx, uint32_t count);
  *     rays outside the finite range walk the binary image.
  * IMAGE: the binary image only.  WIDE: same as AUTO.  REFERENCE_ORDER: walk the 80-byte nodes literally, dropped pushes
  * counted — also what AUTO falls back to when the stack could overflow.  restir_get_bvh_info tells which one is in use.
- * Takes effect at the next restir_upload_bvh.  Uploads whose child indices are out of range or that are not trees are rejected
+ * Takes effect at the next restir_upload_bvh (restir_pass_gbuffer, whose closest-hit walk reads the binary image and the same
+ * triangle records, honours REFERENCE_ORDER at once: same planes either way).  Uploads whose child indices are out of range or that are not trees are rejected
  * with RESTIR_E_INVALID.  restir_build_bvh_device derives both images on the device (csrc/restir_wide_build.cu). */
 #define RESTIR_TRAVERSAL_AUTO 0
 #define RESTIR_TRAVERSAL_REFERENCE_ORDER 1

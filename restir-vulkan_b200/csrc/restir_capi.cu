@@ -1195,8 +1195,12 @@ int restir_pass_gbuffer(restir_context *ctx, int slot, const restir_camera *came
 	Band full = ctx->band; // every row the context holds: the reuse passes gather from the halo rows
 	full.rowBegin = full.allocBegin;
 	full.rowEnd = full.allocEnd;
+	SceneView sv = sceneView(ctx);
+	if (ctx->traversal == RESTIR_TRAVERSAL_REFERENCE_ORDER) {
+		sv.image = nullptr; // the literal walk of the uploaded 80-byte nodes (what trees without an image get): same planes, kept testable
+	}
 	beforeLaunch(ctx, "gbuffer_kernel");
-	launch_gbuffer(sceneView(ctx), g, full, cam, camera->zNear, camera->zFar, ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1],
+	launch_gbuffer(sv, g, full, cam, camera->zNear, camera->zFar, ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1],
 	               ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3], ctx->ownedPlanes[slot][4], ctx->stream);
 	if ((rc = afterLaunch(ctx, "gbuffer_kernel")) != RESTIR_OK) return rc;
 	restir_gbuffer_planes dev{ctx->ownedPlanes[slot][0], ctx->ownedPlanes[slot][1], ctx->ownedPlanes[slot][2], ctx->ownedPlanes[slot][3],

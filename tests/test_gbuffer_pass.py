@@ -161,6 +161,11 @@ def test_gbuffer_pass_matches_oracle_twin(name, cam_key, size):
         want = po.gbuffer_pass(ph.oracle_scene(scene), oi, ocam, w, h)
         _compare_planes(ctx, k, want.planes(), h, w, f"{name} camera {k}")
         assert (want.depth < 1.0).mean() > 0.2
+    # the pass walks the 64-byte image of the tree and the shadow rays' triangle records; the literal walk of the uploaded 80-byte
+    # nodes (trees without an image; restir_set_traversal(REFERENCE_ORDER)) must produce the same planes
+    ctx.set_traversal(capi.RESTIR_TRAVERSAL_REFERENCE_ORDER)
+    ctx.pass_gbuffer(1, cam)
+    _compare_planes(ctx, 1, want.planes(), h, w, f"{name} camera 1, literal walk")
     ctx.close()
 
 
