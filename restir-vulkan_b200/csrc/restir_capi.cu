@@ -422,7 +422,8 @@ TraceParams traceParams(const restir_context *ctx) {
 	tp.nTris = ctx->nTris;
 	tp.occluders = (ctx->occluderCache && ctx->wide != nullptr && ctx->nTris < (1u << 24)) ? ctx->occluders : nullptr;
 	tp.regionsX = ctx->regionsX;
-	tp.occluderPretest = 1;
+	tp.occluderPretest = kOccluderWays > 1 ? 2 : 1; // restirOmni's rays try both witnesses of an entry (86 % of them are shadowed); the unbiased pass's
+	                                                 // mostly unshadowed rays only the most recent one (restir_pass_unbiased)
 	// 1: by light index while a region's 256 entries (x 256 tags) can tell the lights apart, by direction beyond; 2 / 3 force one
 	tp.occluderByDirection = ctx->occluderCache == 3 || (ctx->occluderCache == 1 && ctx->pointCount + ctx->triCount > 4096);
 	tp.band = ctx->band;
@@ -943,7 +944,7 @@ int restir_resize_band(restir_context *ctx, uint32_t width, uint32_t height, uin
 	// occluder cache: 256 entries per 64 x 32-pixel region of the rows this context holds, all empty
 	freeDev(ctx->occluders);
 	ctx->regionsX = (width + 63) / 64;
-	ctx->occluderEntries = (size_t)ctx->regionsX * (((size_t)(b.allocEnd - b.allocBegin) + 31) / 32) * 256;
+	ctx->occluderEntries = (size_t)ctx->regionsX * (((size_t)(b.allocEnd - b.allocBegin) + 31) / 32) * 256 * kOccluderWays;
 	CU(ctx, cudaMalloc(&ctx->occluders, ctx->occluderEntries * sizeof(unsigned)));
 	CU(ctx, cudaMemsetAsync(ctx->occluders, 0xff, ctx->occluderEntries * sizeof(unsigned), ctx->stream));
 	if (ctx->generic()) {

@@ -44,7 +44,7 @@ struct TraceParams {
 	unsigned *aliasCount;               // device counter of `aliases`
 	unsigned *occluders;                // occluder cache (restir_trace.cu): [screen region][256] -> tag << 24 | triangle record; null: off
 	unsigned regionsX;                  // regions (64 x 32 pixels) per region row
-	int occluderPretest;                // test the cached witness before a ray is queued (walks record witnesses either way)
+	int occluderPretest;                // test the cached witness(es) before a ray is queued: 0 no, 1 the most recent one, 2 both ways (walks record witnesses either way)
 	int occluderByDirection;            // entries chosen by the segment's direction instead of the light index (many lights)
 	unsigned nTris;
 	unsigned nNodes;
@@ -66,6 +66,11 @@ struct TraceParams {
 	unsigned blocksPerSm;
 	float guidedShare;                 // RESTIR_TRACE_GUIDED / warps of the grid (set by the launcher): the part of the remaining items one fetch takes
 };
+// witnesses kept per (screen region, key) of the occluder cache (restir_trace.cu), most recent first
+#ifndef RESTIR_OCCLUDER_WAYS
+#define RESTIR_OCCLUDER_WAYS 2
+#endif
+constexpr unsigned kOccluderWays = RESTIR_OCCLUDER_WAYS;
 constexpr unsigned kTraceMaxRegions = 4096, kTraceMaxSms = 1024; // regionCursors holds kTraceMaxRegions + kTraceMaxSms words, smSlots = regionCursors + kTraceMaxRegions
 cudaError_t launch_trace(const TraceParams &tp, int mode, int smCount, cudaStream_t s);
 

@@ -188,7 +188,7 @@ __device__ __forceinline__ unsigned occluder_key(const TraceParams &tp, unsigned
 __device__ __forceinline__ unsigned occluder_entry(const TraceParams &tp, size_t opix, unsigned key16) {
 	const unsigned W = (unsigned)tp.band.W, n = (unsigned)opix;
 	const unsigned yl = fast_div(n, tp.divW), x = n - yl * W;
-	return ((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (key16 & (kOccluderSlots - 1u));
+	return (((yl >> 5) * tp.regionsX + (x >> 6)) * kOccluderSlots + (key16 & (kOccluderSlots - 1u))) * kOccluderWays; // the first way
 }
 
 // ---- one walk per segment ---------------------------------------------------------------------------------------------------
@@ -261,8 +261,12 @@ template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const
 					t = __ldg(reinterpret_cast<const float4 *>(tp.reservoirs + pix));
 				}
 				const unsigned key16 = occluder_key(tp, light, mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z));
-				const unsigned e = __ldcg(tp.occluders + occluder_entry(tp, opix, key16));
-				const unsigned rec = e & 0xffffffu;
+				const unsigned *entry = tp.occluders + occluder_entry(tp, opix, key16);
+				unsigned e = __ldcg(entry), e2 = 0xffffffffu;
+				if (kOccluderWays > 1 && tp.occluderPretest > 1) { // the witness before the last one: a second chance where two occluders share a region's view of a light
+					e2 = __ldcg(entry + 1);
+				}
+				unsigned rec = e & 0xffffffu;
 				if ((e >> 24) == (key16 >> 8) && rec < tp.nTris) {
 					if (!tp.occluderByDirection) {
 						w = __ldg(tp.worldPos + opix);
@@ -270,10 +274,17 @@ template <int MODE, int WALK> __device__ __forceinline__ unsigned item_key(const
 					}
 					f3 o, d;
 					segment_setup(mk3(w.x, w.y, w.z), mk3(t.x, t.y, t.z), o, d);
-					if (wide_ray_in_range(tp.grid, o, d) && wide_leaf_hit(tp.triEdges, rec, o, d)) {
-						tp.shadowed[out] = 1;
-						cached++;
-						witnessed = true;
+					if (wide_ray_in_range(tp.grid, o, d)) {
+						bool hit = wide_leaf_hit(tp.triEdges, rec, o, d);
+						rec = e2 & 0xffffffu;
+						if (!hit && kOccluderWays > 1 && (e2 >> 24) == (key16 >> 8) && rec < tp.nTris) {
+							hit = wide_leaf_hit(tp.triEdges, rec, o, d);
+						}
+						if (hit) {
+							tp.shadowed[out] = 1;
+							cached++;
+							witnessed = true;
+						}
 					}
 				}
 			}
@@ -733,7 +744,17 @@ template <int MODE> __global__ void __launch_bounds__(kTraceThreads, RESTIR_TRAC
 				tp.shadowed[out] = rec != -1 ? 1 : 0;
 				if (MODE != kTraceSegments && rec >= 0 && tp.occluders != nullptr) { // the witness for the next ray of this region at this light
 					const unsigned key16 = occluder_key(tp, key >> kLocalBits, p1, p2);
-					tp.occluders[occluder_entry(tp, opix, key16)] = ((key16 >> 8) << 24) | (unsigned)rec;
+					unsigned *entry = tp.occluders + occluder_entry(tp, opix, key16);
+					const unsigned fresh = ((key16 >> 8) << 24) | (unsigned)rec;
+					if (kOccluderWays > 1) { // most recent first; the one it displaces moves to the second way
+						const unsigned last = __ldcg(entry);
+						if (last != fresh) {
+							entry[1] = last;
+							entry[0] = fresh;
+						}
+					} else {
+						entry[0] = fresh;
+					}
 				}
 			}
 		}
